@@ -1,0 +1,103 @@
+"""In-tree native build: nvcc for the sm_100a engine + g++ for the host model code.
+
+Outputs (git-ignored, shipped to the GPU box by gpurun):
+  voxcraft-sim_b200/lib/libvx3_b200.so         production build (FMA contraction on)
+  voxcraft-sim_b200/lib/libvx3_b200_strict.so  same sources with -fmad=false: used by the parity tests to
+                                               separate algorithmic differences from FMA contraction
+                                               (the reference x86-64 build does not contract)
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+INCLUDE = os.path.join(ROOT, "include")
+
+ENGINE_CU = ["engine/vx3_engine.cu"]
+HOST_CPP = ["host/vx3_materials.cpp", "host/vx3_builder.cpp", "host/vx3_vxa.cpp", "host/vx3_history.cpp", "host/vx3_manager.cpp"]
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _all_deps():
+    deps = []
+    for base, _, files in os.walk(CSRC):
+        deps += [os.path.join(base, f) for f in files]
+    deps += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    return deps
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd[:3]) + " ...")
+    if verbose and r.stdout.strip():
+        print(r.stdout)
+    return r.stdout
+
+
+def build_lib(strict=False, force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    name = "libvx3_b200_strict.so" if strict else "libvx3_b200.so"
+    out = os.path.join(LIBDIR, name)
+    srcs = [os.path.join(CSRC, s) for s in ENGINE_CU + HOST_CPP if os.path.exists(os.path.join(CSRC, s))]
+    if not force and not _newer(out, _all_deps()):
+        return out
+    cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-I", INCLUDE,
+           "-I", CSRC] + ARCH
+    if strict:
+        cmd += ["-fmad=false", "-DVX3_STRICT=1"]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", out] + srcs
+    _run(cmd, verbose)
+    return out
+
+
+def build_oracle(force=False, verbose=False):
+    """Builds the CHECKERS (tests/bench cpu_baseline only): oracle restatement and, when the reference
+    tree is present (this container), the unmodified reference CPU library under oracle/_ref."""
+    odir = os.path.join(ROOT, "oracle")
+    _run(["make", "-C", odir, "-j8", "oracle"], verbose)
+    ref = os.environ.get("VX3_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(ref, "src", "old")):
+        _run(["make", "-C", odir, "-j8", "ref", "REF=" + ref], verbose)
+        try:  # multi-core CPU baseline (the reference's own USE_OMP path); optional
+            _run(["make", "-C", odir, "-j8", "ref_omp", "REF=" + ref], verbose)
+        except RuntimeError:
+            print("note: OpenMP reference build unavailable (no libgomp for this g++)")
+    return os.path.join(odir, "libvx3_oracle.so")
+
+
+def build_all(force=False, verbose=False):
+    a = build_lib(strict=False, force=force, verbose=verbose)
+    b = build_lib(strict=True, force=force, verbose=verbose)
+    return a, b
+
+
+if __name__ == "__main__":
+    v = "-v" in sys.argv
+    f = "-f" in sys.argv
+    print(build_all(force=f, verbose=v))
+    print(build_oracle(verbose=v))
