@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the VX3 step loop on B200: voxel-steps/s (whole job, device-timed) + roofline + CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--impl b200|reference]
+
+One bench "step" = one pass of the hot path over one batch: `--sim-steps` calls of doTimeStep for every
+simulation of the workload (default 1000; K*sim-steps = 100,000 for config 2 with the default K=100).
+At N=1 the workload is BASELINE.json's config 2 (single 20x20x20 actuated body, collisions off).  For N>1 the
+path shards by independent simulation: every rank steps its own copy of the per-GPU workload,
+no data-path collective, scaling = weak; the only cross-rank traffic is the end-of-run gather of fitness results.
+
+Timing: W untimed warm-up steps, then exactly K steps between barrier+synchronize, device-timed with CUDA events
+on the engine's own stream (vx3_batch_last_timing), max over ranks.  `value` starts with the model resident in
+HBM; `e2e` re-creates the batch from HOST arrays every step (H2D), steps, and reads results + positions back
+(D2H) through the C ABI, inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import __graft_entry__ as graft  # noqa: E402
+
+METRIC = "voxel-steps/sec"
+UNIT = "voxel-steps/s"
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, pkg, per_gpu_sims):
+    from voxcraft_sim_b200 import workloads as W
+    if name == "c2":
+        specs = [W.c2_spec()]
+        label = "config2: single 20x20x20 multi-material actuated body, collisions off"
+    elif name == "c3":
+        specs = [W.c3_spec(k) for k in range(per_gpu_sims)]
+        label = "config3: batch of %d random 10x10x10 robots per GPU (vx3_node_worker fitness eval)" % per_gpu_sims
+    elif name == "c5":
+        specs = [W.c5_spec()]
+        label = "config5 (one GPU, no decomposition): single 200x200x100 body"
+    else:
+        raise SystemExit("unknown workload " + name)
+    return specs, label
+
+
+def reference_cpu_throughput(spec, target_seconds, omp=True):
+    """The reference's own CPU implementation (src/old compiled unmodified into oracle/_ref) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util  # checker plumbing
+    use_omp = omp and os.path.exists(util.REF_OMP_SO)
+    if not os.path.exists(util.REF_SO) and not use_omp:
+        return None
+    cores = os.cpu_count() or 1
+    if use_omp:
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sim = util.RefSim(spec, omp=use_omp)
+    dt = float(__import__("numpy").float32(0.9 * sim.recommended_dt()))
+    sim.step(10, dt)
+    t0 = time.perf_counter()
+    sim.step(20, dt)
+    per = (time.perf_counter() - t0) / 20
+    chunk = max(20, int(1.0 / max(per, 1e-9)))
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        n = sim.step(chunk, dt)
+        done += n
+        el = time.perf_counter() - t0
+        if el >= target_seconds or n < chunk:
+            break
+    return {"value": sim.nv * done / el, "unit": UNIT, "cores": cores if use_omp else 1, "kind": "reference",
+            "sample": "%d doTimeStep calls of the same %d-voxel model through the reference CPU library (src/old, %s), %.1f s"
+                      % (done, sim.nv, "-DUSE_OMP, %d threads" % cores if use_omp else "single thread as shipped", el),
+            "seconds": el, "steps": done, "voxels": sim.nv}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sim-steps", type=int, default=1000, help="doTimeStep calls per bench step")
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--sims-per-gpu", type=int, default=512, help="config 3: robots per GPU (4096 / 8)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fma", type=int, default=0, help="0 = the product (-fmad=false, parity-grade), 1 = FMA-contracted experimental build")
+    ap.add_argument("--no-persistent", action="store_true", help="force the streaming kernels")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = env_rank()
+    K, Wm = args.steps, max(args.warmup, 0)
+    graft.load_package()
+    specs, label = build_workload(args.workload, None, args.sims_per_gpu)
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        base = reference_cpu_throughput(specs[0], max(5.0, args.cpu_seconds))
+        if base is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (reference sources are not on this box)"}))
+            return 0
+        line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
+                "ms_per_step": 1e3 * base["seconds"] / base["steps"] * args.sim_steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": label, "sim_steps_per_step": args.sim_steps, "note": "CPU reference (src/old) has no per-voxel phase actuation"},
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from voxcraft_sim_b200.engine import Batch
+    from voxcraft_sim_b200.libs import load_engine
+    from voxcraft_sim_b200.workloads import alg_bytes_per_voxel_step
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    fma = bool(args.fma)
+    lib = load_engine(fma)
+    built = [s.build(lib) for s in specs]
+    descs = [d for _, d in built]
+    nvox = sum(d.contents.n_voxels for d in descs)
+    nlinks = sum(d.contents.n_links for d in descs)
+    S = args.sim_steps
+
+    batch = Batch(descs, fma=fma, device=local_rank)
+    if args.no_persistent:
+        batch.set_profiling(False, use_persistent=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        batch.step(S)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, launches = 0.0, 0
+    t_wall0 = time.perf_counter()
+    for _ in range(K):
+        batch.step(S)
+        ms, nl = batch.timing()
+        dev_ms += ms
+        launches += nl
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    res = batch.results()
+    diverged = sum(1 for r in res if r.status == 2)
+
+    # ---- roofline of the dominant kernel: a profiled pass (CUDA events around every launch, same stream) ----
+    batch.set_profiling(True, use_persistent=not args.no_persistent)
+    prof_steps = min(S, 200)
+    batch.step(prof_steps)
+    stats = {k: v for k, v in batch.kernel_stats().items() if v[1] > 0}
+    batch.set_profiling(False, use_persistent=not args.no_persistent)
+    total_prof = sum(v[0] for v in stats.values()) or 1.0
+    top = max(stats.items(), key=lambda kv: kv[1][0])
+    peak, peak_src = measured_peak_hbm()
+    b_alg = alg_bytes_per_voxel_step(nvox, nlinks)
+    if top[0] == "k_persistent":
+        # one launch covers many doTimeStep calls of the whole body: algorithmic bytes = B_alg * V * steps in the launch
+        alg_bytes_launch = b_alg * nvox * prof_steps / top[1][1]
+    elif top[0] == "k_links":
+        alg_bytes_launch = 184.0 * nlinks
+    elif top[0] == "k_voxels":
+        alg_bytes_launch = 228.0 * nvox
+    else:
+        alg_bytes_launch = b_alg * nvox
+    avg_launch_s = 1e-3 * top[1][0] / top[1][1]
+    achieved = alg_bytes_launch / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_share_of_step": top[1][0] / total_prof,
+                "alg_bytes_per_launch": alg_bytes_launch, "avg_launch_us": 1e6 * avg_launch_s,
+                "kernel_ms": {k: round(v[0], 4) for k, v in stats.items()}, "kernel_launches": {k: v[1] for k, v in stats.items()}}
+
+    # ---- e2e: host model -> vx3_batch_create (H2D) -> step -> results + positions (D2H), all inside the timed region ----
+    e2e = None
+    if not args.skip_e2e:
+        e2e_steps = max(1, min(K, 10))
+        h2d = 0
+        for d in descs:
+            m = d.contents
+            h2d += m.n_voxels * (3 * 2 + 4 + 24 + 32 + 24 + 24 + 4 + 4 + 8 + 24 + 4) + m.n_links * (4 * 4 + 72 + 4 * 4 + 4 + 4 + 8 + 12)
+        d2h = sum(C.sizeof(type(res[0])) for _ in res) + sum(d.contents.n_voxels * (48 + 4) for d in descs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bt = Batch(descs, fma=fma, device=local_rank)
+            if args.no_persistent:
+                bt.set_profiling(False, use_persistent=False)
+            bt.step(S)
+            bt.results()
+            for i in range(len(descs)):
+                bt.positions(i)
+            bt.close()
+        barrier()
+        e2e_t = time.perf_counter() - t0
+        e2e = {"t": e2e_t, "steps": e2e_steps, "h2d": h2d, "d2h": d2h}
+
+    # ---- aggregate over ranks: max time, summed work ----
+    tt = torch.tensor([dev_ms, wall, e2e["t"] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(nvox) * S * K, float(launches), float(diverged)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+        # end-of-batch fitness gather (the only cross-device step of the path)
+        fit = torch.tensor([r.fitness_score for r in res], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(fit) for _ in range(world)]
+        dist.all_gather(gathered, fit)
+    dev_ms_max, wall_max, e2e_max = [float(x) for x in tt.tolist()]
+    total_work, total_launches, total_div = [float(x) for x in work.tolist()]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu_baseline = reference_cpu_throughput(specs[0], args.cpu_seconds)
+        if cpu_baseline:
+            cpu_baseline = {k: cpu_baseline[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        value = total_work / (dev_ms_max * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": label, "voxels_per_gpu": nvox, "links_per_gpu": nlinks, "sims_per_gpu": len(descs),
+                           "sim_steps_per_step": S, "total_sim_steps": S * K, "build": "fma" if fma else "-fmad=false (parity-grade)",
+                           "path": "streaming" if args.no_persistent else "auto",
+                           "l2": "state is mutated by every step (each step reads what the previous one wrote); working set "
+                                 "%.1f MB %s the 126 MB L2" % ((nvox * 228 + nlinks * 184) / 1e6, "fits in" if nvox * 228 + nlinks * 184 < 100e6 else "exceeds"),
+                           "alg_bytes_per_voxel_step": b_alg, "wall_ms_per_step": 1e3 * wall_max / K, "diverged_sims": int(total_div)},
+                "roofline": roofline,
+                "hbm_roofline_equiv_frac": value * b_alg / (peak * 1e9 * world),
+                "cpu_baseline": cpu_baseline, "clocks": clocks, "gpu_launches": int(total_launches)}
+        if e2e:
+            ev = float(nvox) * S * e2e["steps"] * world / e2e_max
+            line["e2e"] = {"value": ev, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "steps": e2e["steps"], "what": "vx3_batch_create from host arrays + vx3_batch_step + vx3_batch_results/positions + destroy per step"}
+        print(json.dumps(line))
+    batch.close()
+    for b, _ in built:
+        lib.vx3_builder_destroy(b)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

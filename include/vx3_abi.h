@@ -326,6 +326,13 @@ int vx3_batch_recommended_dt(vx3_batch *b, int sim, double *out);
  * it issued. */
 int vx3_batch_last_timing(vx3_batch *b, double *ms, int64_t *launches);
 
+/* Bench hooks.  set_profiling(on): bracket every kernel launch of the following step/run calls with CUDA events
+ * on the batch's stream and accumulate the device time per kernel; use_persistent = 0 forces the streaming
+ * kernels even where the on-chip persistent kernel applies.  kernel_stats(index): name, accumulated
+ * milliseconds and launch count of kernel `index` (0, 1, ...); returns 1 past the last kernel. */
+int vx3_batch_set_profiling(vx3_batch *b, int on, int use_persistent);
+int vx3_batch_kernel_stats(vx3_batch *b, int index, char *name, int name_cap, double *total_ms, int64_t *launches);
+
 /* Sort results like sortResults (src/VX3/VX3_SimulationManager.cu:472,
  * VX3_SimulationResult.h:26-33): fitness descending, NaN last.  Host-only. */
 void vx3_sort_results(vx3_result *r, int n);
@@ -336,6 +343,8 @@ void vx3_batch_destroy(vx3_batch *b);
 const char *vx3_last_error(void);
 
 int vx3_abi_version(void);
+/* sizeof() of a struct of this header / vx3_model.h by name (binding self-check); 0 = unknown name. */
+size_t vx3_abi_sizeof(const char *struct_name);
 
 #ifdef __cplusplus
 }

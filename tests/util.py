@@ -89,26 +89,7 @@ def ref_load_spec(spec, omp=False):
 
 
 # ------------------------------------------------------------------ model factories
-def splitmix64(seed):
-    """PRNG used by the synthetic workloads."""
-    state = seed & 0xFFFFFFFFFFFFFFFF
-
-    def nxt():
-        nonlocal state
-        state = (state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
-        z = state
-        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-        return z ^ (z >> 31)
-    return nxt
-
-
-def add_abc_materials(spec, sticky=False):
-    """Materials A/B/C of SURVEY.md §8(d)."""
-    spec.add_material(name="A", elastic_mod=1e6, density=1e3, cte=0.01, u_static=1.0, u_dynamic=0.8, red=1.0, green=0.0, blue=0.0,
-                      sticky=int(sticky))
-    spec.add_material(name="B", elastic_mod=5e6, density=1.5e3, cte=-0.01, u_static=1.0, u_dynamic=0.8, red=0.0, green=1.0, blue=0.0)
-    spec.add_material(name="C", elastic_mod=1e6, density=1e3, cte=0.0, u_static=1.0, u_dynamic=0.8, red=0.0, green=0.0, blue=1.0)
+from voxcraft_sim_b200.workloads import add_abc_materials, splitmix64  # noqa: E402
 
 
 def cube_spec(n=(3, 3, 3), seed=42, actuated=True, lift=0, holes=0.0, name="cube", collisions=0, damping=(1.0, 0.8, 0.01)):
@@ -200,76 +181,7 @@ class RefSim:
         return sb.result()
 
 
-class EngineBatch:
-    """Thin wrapper over the C ABI for tests (the product path: fails loudly without the CUDA library/GPU)."""
-
-    def __init__(self, desc_ptrs, strict=False, device=0):
-        self.lib = load_engine(strict)
-        n = len(desc_ptrs)
-        arr = (abi.ModelDesc * n)()
-        for i, d in enumerate(desc_ptrs):
-            C.memmove(C.byref(arr[i]), d, C.sizeof(abi.ModelDesc))
-        self._arr = arr
-        self.n = n
-        self.h = C.c_void_p()
-        rc = self.lib.vx3_batch_create(device, arr, n, C.byref(self.h))
-        if rc != 0:
-            raise RuntimeError("vx3_batch_create failed (%d): %s" % (rc, self.lib.vx3_last_error().decode()))
-        self.sizes = [(d.contents.n_voxels, d.contents.n_links) for d in desc_ptrs]
-
-    def _check(self, rc, what):
-        if rc != 0:
-            raise RuntimeError("%s failed (%d): %s" % (what, rc, self.lib.vx3_last_error().decode()))
-
-    def step(self, k, dt=None):
-        if dt is None:
-            self._check(self.lib.vx3_batch_step(self.h, k), "vx3_batch_step")
-        else:
-            self._check(self.lib.vx3_batch_step_dt(self.h, k, dt), "vx3_batch_step_dt")
-
-    def run(self, max_steps=0, steps_per_launch=0, history=None):
-        o = abi.RunOpts(max_steps, steps_per_launch, 1 if history is not None else 0)
-        chunks = history
-
-        def cb(user, sim, data, n):
-            chunks.append((sim, C.string_at(data, n)))
-        fn = abi.HISTORY_CB(cb) if history is not None else abi.HISTORY_CB()
-        self._check(self.lib.vx3_batch_run(self.h, C.byref(o), fn, None), "vx3_batch_run")
-
-    def sync(self):
-        self._check(self.lib.vx3_batch_sync(self.h), "vx3_batch_sync")
-
-    def state(self, sim=0, link_cap=None):
-        nv, nl = self.sizes[sim]
-        sb = StateBuffers(nv, link_cap or max(nl * 2 + 64, 64))
-        self._check(self.lib.vx3_batch_state(self.h, sim, C.byref(sb.view)), "vx3_batch_state")
-        return sb.result()
-
-    def results(self):
-        arr = (abi.Result * self.n)()
-        self._check(self.lib.vx3_batch_results(self.h, arr), "vx3_batch_results")
-        return list(arr)
-
-    def recommended_dt(self, sim=0):
-        v = C.c_double()
-        self._check(self.lib.vx3_batch_recommended_dt(self.h, sim, C.byref(v)), "vx3_batch_recommended_dt")
-        return v.value
-
-    def timing(self):
-        ms, n = C.c_double(), C.c_int64()
-        self.lib.vx3_batch_last_timing(self.h, C.byref(ms), C.byref(n))
-        return ms.value, n.value
-
-    def close(self):
-        if self.h:
-            self.lib.vx3_batch_destroy(self.h)
-            self.h = C.c_void_p()
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+from voxcraft_sim_b200.engine import Batch as EngineBatch  # noqa: E402  (the product binding; fails loudly without the CUDA library/GPU)
 
 
 # ------------------------------------------------------------------ comparisons
@@ -357,7 +269,7 @@ def desc_arrays(d):
 def smoke_check():
     """__graft_entry__.smoke(): a small actuated body on cuda:0 through the C ABI vs the oracle."""
     spec = cube_spec((4, 4, 4), seed=7, actuated=True, name="smoke")
-    lib = load_engine(False)
+    lib = load_engine()
     b, d = spec.build(lib)
     try:
         eng = EngineBatch([d])

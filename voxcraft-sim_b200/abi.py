@@ -178,6 +178,10 @@ def declare_engine_api(lib):
     lib.vx3_batch_positions.argtypes = [vp, C.c_int, P(f64), P(f64), P(i32)]
     lib.vx3_batch_recommended_dt.argtypes = [vp, C.c_int, P(f64)]
     lib.vx3_batch_last_timing.argtypes = [vp, P(f64), P(i64)]
+    lib.vx3_batch_set_profiling.argtypes = [vp, C.c_int, C.c_int]
+    lib.vx3_batch_kernel_stats.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, P(f64), P(i64)]
+    lib.vx3_abi_sizeof.argtypes = [C.c_char_p]
+    lib.vx3_abi_sizeof.restype = C.c_size_t
     lib.vx3_sort_results.argtypes = [P(Result), C.c_int]
     lib.vx3_sort_results.restype = None
     lib.vx3_batch_destroy.argtypes = [vp]
@@ -189,7 +193,7 @@ def declare_engine_api(lib):
 
 ENGINE_SYMBOLS = ["vx3_batch_create", "vx3_batch_run", "vx3_batch_step", "vx3_batch_step_dt", "vx3_batch_sync",
                   "vx3_batch_state", "vx3_batch_results", "vx3_batch_positions", "vx3_batch_recommended_dt",
-                  "vx3_batch_last_timing", "vx3_sort_results", "vx3_batch_destroy", "vx3_last_error", "vx3_abi_version"]
+                  "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_last_error", "vx3_abi_version"]
 MODEL_SYMBOLS = ["vx3_material_params_default", "vx3_env_params_default", "vx3_sim_options_default", "vx3_builder_create",
                  "vx3_builder_destroy", "vx3_builder_add_material", "vx3_builder_set_env", "vx3_builder_set_options",
                  "vx3_builder_set_name", "vx3_builder_set_program", "vx3_builder_set_structure", "vx3_builder_set_external",

@@ -1,0 +1,157 @@
+// Device-side data model of a batch: structure-of-arrays with integer indices, all simulations of the
+// batch concatenated (voxel g = voff[sim] + local index; link slot g = loff[sim] + local index).
+//
+// Replaces the reference's array-of-fat-structs with raw device pointers
+// (VX3_Voxel src/VX3/VX3_Voxel.h:268-314, VX3_Link src/VX3/VX3_Link.h:209-245, materials
+// src/VX3/VX3_Material.h:107-166 / VX3_MaterialVoxel.h:50-59 / VX3_MaterialLink.h:24-37).
+#pragma once
+#include <cstdint>
+
+#include "../../../include/vx3_abi.h"
+#include "vx3_math.cuh"
+
+namespace vx3 {
+
+// device-only voxel flag bits (above the reference's boolStates bits, which keep their values)
+#define VXF_ENABLE_ATTACH (1 << 8) // VX3_Voxel::enableAttach (VX3_Voxel.h:302)
+#define VXF_REMOVED (1 << 9)       // VX3_Voxel::removed
+#define VXF_BOOLSTATE_MASK 0xFF
+
+// link state word = vx3_state_view.link_flags bits + axis + transient bit
+#define LKS_VALID VX3_LINKSTATE_LOCAL_VELOCITY_VALID
+#define LKS_SMALL VX3_LINKSTATE_SMALL_ANGLE
+#define LKS_DETACHED VX3_LINKSTATE_DETACHED
+#define LKS_REMOVED VX3_LINKSTATE_REMOVED
+#define LKS_AXIS_SHIFT 4
+#define LKS_AXIS_MASK (3 << LKS_AXIS_SHIFT)
+#define LKS_JUST_CREATED (1 << 6) // attached during the current step (cleared by the next link pass)
+#define LKS_NEWLINK_SHIFT VX3_LINKSTATE_NEWLINK_SHIFT
+#define LKS_PUBLIC_MASK (~(LKS_AXIS_MASK | LKS_JUST_CREATED))
+
+#define VX3_DEV_MAX_TOKENS 128 // per-voxel programs (force field, attach conditions) on the device evaluator
+#define VX3_MAX_PARTNERS 96    // contact partners of one voxel inside the collision envelope
+
+// Voxel material constants the step reads (all derived values precomputed in the reference's arithmetic).
+struct VoxMatC {
+    double nomSize;
+    double size[3];        // mat->size() = nomSize*extScale
+    double cilia;
+    double thermal_on_after, cilia_on_after, remove_after;
+    float alphaCTE, muStatic, muKinetic, massInverse;
+    float mass, momentInertiaInverse, globalDampT, globalDampR; // zetaGlobal*_2xSqMxExS, zetaGlobal*_2xSqIxExSxSxS
+    float colDampT, penStiff, gravityForce, dampMultNum;        // zetaCollision*_2xSqMxExS, (float)(2*E*nomSize), -mass*9.80665f*gravMult, 2*_sqrtMass*zetaInternal
+    float E;
+    int32_t fixed, sticky, is_target, is_measured, matid;
+    int32_t self_lmat; // link material of a (this,this) pair: used by attach (global link-material index), -1 if none
+    int32_t _pad;
+};
+
+// Link material constants (VX3_MaterialLink + the VX3_Material stress model).
+struct LinkMatC {
+    float E, nu, eHat, epsilonFail;
+    float a1, a2, b1, b2, b3;
+    float sqA1, sqA2xIp, sqB1, sqB2xFMp, sqB3xIp;
+    int32_t linear;
+    int32_t data_off, n_data; // into the strain/stress pool (device layout: duplicated leading 0)
+    int32_t _pad;
+};
+
+struct ExtC { // VX3_External
+    int32_t dof;
+    float force[3], moment[3];
+    double translation[3];
+    double rotq[4];
+};
+
+// per-simulation constants
+struct SimC {
+    int32_t voff, nvox, loff, lcap, nhostlinks;
+    int32_t vary_temp, enable_expansion;
+    int32_t enable_collision, enable_attach, enable_detach, enable_cilia;
+    int32_t safety_guard;
+    int32_t has_ff, has_attach_cond; // any force-field / attach-condition program present
+    int32_t prog_off[VX3_PROG_COUNT], prog_n[VX3_PROG_COUNT];
+    int32_t tgt_off, ntgt;
+    int32_t chunk_off, nchunks; // CoM reduction chunks
+    double temp_amp, temp_period;
+    double vox_size, pair_radius; // MaxDistInVoxelLengthsToCountAsPair * voxSize (0 = closeness off)
+    double cell_inv;              // 1 / collision grid cell edge
+    double dt_frac, optimal_dt;
+};
+
+// per-simulation dynamic scalars (VX3_VoxelyzeKernel members that change during the run)
+struct SimD {
+    double t;          // currentTime
+    long long steps;   // CurStepCount
+    int32_t status;    // vx3_status
+    int32_t diverged;  // set by the link pass of the current step
+    int32_t link_cnt;  // d_v_links.size()
+    int32_t collision_count;
+    int32_t nsurface;
+    int32_t angle_samples;
+    int32_t num_close_pairs;
+    int32_t err;
+    int32_t attach_events, detach_events;
+    float dt;          // step in use (float, VX3_VoxelyzeKernel.cu:237,253)
+    int32_t _pad;
+    double com[3], com_hist[2][3], com0[3];
+    double recent_angle, target_closeness, fitness;
+    double total_dist;
+    int32_t n_measured, _pad2;
+};
+
+struct Chunk { int32_t sim, vstart, vcount, _pad; };
+
+struct Cand { // attach candidate (VX3_VoxelyzeKernel.cu:729-812), sorted by (hi, lo) before resolution
+    unsigned long long key; // hi<<32 | lo (global voxel indices)
+    int32_t info;           // dir1 | dir2<<3 | axis<<6 | reverse<<8
+    int32_t _pad;
+};
+
+// All device arrays of a batch (plain pointers; owned by the host Batch object).
+struct Dev {
+    int32_t nsims, nvox, nlinkslots, nchunks;
+    const SimC *simc;
+    SimD *simd;
+    const VoxMatC *vmat_tab;
+    const LinkMatC *lmat_tab;
+    const float *strain_pool, *stress_pool;
+    const vx3_token *tokens;
+    const ExtC *exts;
+    const Chunk *chunks;
+    const int32_t *targets;
+    // voxels
+    double *pose;     // [nvox][8]: pos xyz, orient wxyz, pad
+    double *mom;      // [nvox][6]: linMom, angMom
+    int32_t *vflags;  // boolStates | VXF_*
+    const int32_t *vmat; // global voxel-material index
+    const int32_t *vsim;
+    const double *phase;
+    float *tempe, *prevdt;
+    int32_t *vlinks;  // [nvox][6] global link slot or -1
+    const int32_t *vext;
+    const int16_t *ixyz; // [nvox][3]
+    double *contact;  // [nvox][3] (NULL if no sim collides)
+    const double *base_cilia, *shift_cilia; // [nvox][3] or NULL
+    double *initpos;  // [nvox][3]
+    // links
+    int2 *lends;      // (vneg, vpos) global voxel indices; x<0 = empty pool slot
+    int32_t *lstate;
+    int32_t *lmat;
+    double *lhist;    // [slots][9]: pos2, angle1v, angle2v
+    double *lrest;
+    float4 *lstrain;  // strain, maxStrain, strainOffset, _stress
+    float2 *larea;    // currentTransverseArea, currentTransverseStrainSum
+    double *lforce;   // [slots][12]: forceNeg, momentNeg, forcePos, momentPos
+    // collision grid (hashed uniform grid)
+    int32_t hmask;
+    int32_t *cell_cnt, *cell_start, *cell_cursor, *cell_items;
+    int4 *vcell;      // cx, cy, cz, bucket (bucket<0: not in grid)
+    Cand *cands;
+    int32_t *cand_count;
+    int32_t cand_cap;
+    // CoM partials [nchunks][6]: sum m*x, m*y, m*z, m, sum dist, n_measured
+    double *com_part;
+};
+
+} // namespace vx3

@@ -1,0 +1,1011 @@
+// C ABI of the engine (include/vx3_abi.h): batch construction, the step/run drivers and read-back.
+// Host orchestration only — all physics is in the kernels (vx3_kernels.cuh, vx3_persistent.cuh).
+// There is NO CPU fallback: without a usable sm_100 device every entry point fails with VX3_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/vx3_abi.h"
+#include "../../../include/vx3_model.h"
+#include "vx3_kernels.cuh"
+#include "vx3_persistent.cuh"
+#include "vx3_history.h"
+
+using namespace vx3;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                                        \
+    do {                                                                                                                \
+        cudaError_t e_ = (call);                                                                                        \
+        if (e_ != cudaSuccess) return fail(VX3_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+extern "C" const char *vx3_last_error(void) { return g_err.c_str(); }
+extern "C" int vx3_abi_version(void) { return VX3_ABI_VERSION; }
+extern "C" size_t vx3_abi_sizeof(const char *name) {
+    if (!name) return 0;
+#define SZ(T) if (!strcmp(name, #T)) return sizeof(T)
+    SZ(vx3_token); SZ(vx3_program); SZ(vx3_voxel_material); SZ(vx3_link_material); SZ(vx3_external); SZ(vx3_sim_options);
+    SZ(vx3_model_desc); SZ(vx3_result); SZ(vx3_state_view); SZ(vx3_run_opts); SZ(vx3_material_params); SZ(vx3_env_params);
+#undef SZ
+    return 0;
+}
+
+// ------------------------------------------------------------------ per-kernel timing (bench hook)
+enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_COM, KC_TAIL, KC_PERSISTENT, KC_COUNT };
+static const char *const kKernelNames[KC_COUNT] = {"k_links", "k_voxels", "k_grid_count", "k_grid_scan", "k_grid_fill", "k_contact", "k_resolve",
+                                                   "k_detach", "k_surface", "k_com_partial", "k_tail", "k_persistent"};
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev; // pairs
+    std::vector<int> cls;
+    size_t used = 0;
+    double ms[KC_COUNT] = {};
+    long long cnt[KC_COUNT] = {};
+    bool begin(int c, cudaStream_t st) {
+        if (!on || used + 2 > ev.size()) return false;
+        cls.push_back(c);
+        cudaEventRecord(ev[used], st);
+        return true;
+    }
+    void end(cudaStream_t st) {
+        cudaEventRecord(ev[used + 1], st);
+        used += 2;
+    }
+    void collect() { // after the stream has been synchronised
+        for (size_t i = 0; i + 1 < used; i += 2) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) {
+                ms[cls[i / 2]] += t;
+                cnt[cls[i / 2]]++;
+            }
+        }
+        used = 0;
+        cls.clear();
+    }
+};
+
+// ------------------------------------------------------------------ batch object
+struct vx3_batch {
+    Profiler prof;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> allocs;
+    Dev D;
+    int nsims = 0;
+    std::vector<SimC> simc;
+    std::vector<std::string> names;
+    std::vector<int> n_vmats; // per sim, for reporting
+    std::vector<std::vector<int>> lmat_global; // per sim: local link-material index -> global
+    std::vector<std::vector<int>> matid;       // per sim: local voxel-material index -> matid
+    std::vector<std::vector<int>> vmat_local;  // per sim: voxel -> local material index
+    std::vector<std::vector<float>> matcolor;  // per sim: r,g,b,a per material (0..1) for the history header
+    std::vector<vx3_sim_options> opts;
+    std::vector<std::vector<vx3_voxel_material>> h_vmats; // per sim host copy (data pointers cleared) for the history writer
+    std::vector<LinkMatC> h_lmat_tab;
+    bool any_collide = false, any_sticky = false, any_detach = false;
+    long long hsteps = 0; // doTimeStep calls issued so far (all running simulations advance together)
+    std::vector<float> hdt; // per-sim dt in use
+    double last_ms = 0;
+    long long last_launches = 0;
+    long long launches = 0;
+    PersistentPlan pplan; // on-chip path for a single small collision-free body
+    bool use_persistent = true;
+
+    template <class T> int alloc(T **p, size_t n, bool zero = true) {
+        *p = nullptr;
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+        if (e != cudaSuccess) return fail(VX3_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        allocs.push_back(*p);
+        if (zero) {
+            e = cudaMemsetAsync(*p, 0, n * sizeof(T), stream);
+            if (e != cudaSuccess) return fail(VX3_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+        }
+        return VX3_OK;
+    }
+    template <class T> int upload(T **p, const std::vector<T> &h) {
+        int rc = alloc(p, h.size(), h.empty());
+        if (rc) return rc;
+        if (!h.empty()) {
+            cudaError_t e = cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) return fail(VX3_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+            e = cudaStreamSynchronize(stream); // h may be a temporary
+            if (e != cudaSuccess) return fail(VX3_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+        }
+        return VX3_OK;
+    }
+};
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// VX3_MaterialLink(mat, mat) for attach-created links between two voxels of the same material:
+// updateAll (src/VX3/VX3_MaterialLink.cu:53-127; only the linear model can be blended on the device,
+// VX3_Material.cu:234) + updateDerived (:129-149).
+static void make_self_linkmat(const vx3_voxel_material &a, LinkMatC &o, std::vector<float> &sd, std::vector<float> &ss) {
+    const vx3_voxel_material &b = a;
+    memset(&o, 0, sizeof(o));
+    const double nomSize = 0.5 * (a.nomSize + b.nomSize);
+    float stressFail, f1 = a.sigmaFail, f2 = b.sigmaFail;
+    if (f1 == -1.0f) stressFail = f2;
+    else if (f2 == -1.0f) stressFail = f1;
+    else stressFail = f1 < f2 ? f1 : f2;
+    const float youngsModulus = 2.0f * a.E * b.E / (a.E + b.E);
+    float tmpfailureStress = stressFail;
+    if (tmpfailureStress == -1) tmpfailureStress = 1000000;
+    const float tmpfailStrain = tmpfailureStress / youngsModulus;
+    sd = {0.0f, 0.0f, tmpfailStrain}; // device layout: duplicated leading 0 (VX3_Material.cu:463-477)
+    ss = {0.0f, 0.0f, tmpfailureStress};
+    o.linear = 1;
+    o.E = youngsModulus;
+    o.epsilonFail = (stressFail == -1) ? -1 : tmpfailStrain;
+    if (a.nu == 0 && b.nu == 0) o.nu = 0;
+    else {
+        float tmpEHat = 2 * a.eHat * b.eHat / (a.eHat + b.eHat);
+        float tmpE = o.E;
+        float c2 = (tmpEHat - tmpE) / (2 * tmpEHat) + 0.0625;
+        o.nu = sqrt(c2) - 0.25;
+    }
+    o.eHat = o.E / ((1 - 2 * o.nu) * (1 + o.nu));
+    const float L = (float)nomSize, E = o.E, nu = o.nu;
+    o.a1 = E * L;
+    o.a2 = E * L * L * L / (12.0f * (1 + nu));
+    o.b1 = E * L;
+    o.b2 = E * L * L / 2.0f;
+    o.b3 = E * L * L * L / 6.0f;
+    o.sqA1 = sqrtf(o.a1);
+    o.sqA2xIp = sqrtf(o.a2 * L * L / 6.0f);
+    o.sqB1 = sqrtf(o.b1);
+    o.sqB2xFMp = sqrtf(o.b2 * L / 2.0f);
+    o.sqB3xIp = sqrtf(o.b3 * L * L / 6.0f);
+}
+
+static std::string blob(const void *p, size_t n) { return std::string((const char *)p, n); }
+
+static int validate_model(const vx3_model_desc &m, int idx) {
+    auto bad = [&](const char *what) { return fail(VX3_ERR_INVALID, "model " + std::to_string(idx) + ": " + what); };
+    if (m.n_voxels <= 0) return bad("no voxels");
+    if (m.n_links < 0 || m.n_voxel_mats <= 0) return bad("bad counts");
+    if (!m.voxel_mats || !m.vox_mat || !m.pos || !m.vox_flags || !m.vox_links || !m.ix || !m.iy || !m.iz) return bad("missing voxel arrays");
+    if (m.n_links > 0 && (!m.link_mats || !m.link_vneg || !m.link_vpos || !m.link_axis || !m.link_mat)) return bad("missing link arrays");
+    for (int i = 0; i < m.n_voxels; i++)
+        if (m.vox_mat[i] < 0 || m.vox_mat[i] >= m.n_voxel_mats) return bad("voxel material index out of range");
+    for (int i = 0; i < m.n_links; i++) {
+        if (m.link_vneg[i] < 0 || m.link_vneg[i] >= m.n_voxels || m.link_vpos[i] < 0 || m.link_vpos[i] >= m.n_voxels) return bad("link end out of range");
+        if (m.link_mat[i] < 0 || m.link_mat[i] >= m.n_link_mats) return bad("link material index out of range");
+        if (m.link_axis[i] < 0 || m.link_axis[i] > 2) return bad("link axis out of range");
+    }
+    for (int i = 0; i < 6 * m.n_voxels; i++)
+        if (m.vox_links[i] >= m.n_links) return bad("voxel link slot out of range");
+    if (m.opt.enable_signals) return bad("EnableSignals is not supported by this engine yet");
+    if (m.opt.secondary_experiment) return bad("SecondaryExperiment is not supported by this engine yet");
+    for (int s = 0; s < VX3_PROG_COUNT; s++) {
+        if (m.prog[s].n < 0 || m.prog[s].n > VX3_MAX_TOKENS) return bad("token program too long");
+        if (m.prog[s].n > 0 && !m.prog[s].tok) return bad("token program pointer missing");
+        if (s >= VX3_PROG_FORCE_X && m.prog[s].n > VX3_DEV_MAX_TOKENS) return bad("per-voxel token programs are limited to 128 tokens");
+    }
+    return VX3_OK;
+}
+
+static void run_com(vx3_batch *b, int mode) {
+    k_com_partial<<<b->D.nchunks, VX3_BLOCK, 0, b->stream>>>(b->D);
+    k_sim_update<<<cdiv(b->nsims, 128), 128, 0, b->stream>>>(b->D, mode);
+    b->launches += 2;
+}
+
+extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n, vx3_batch **out) {
+    if (!out) return fail(VX3_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!models || n <= 0) return fail(VX3_ERR_INVALID, "no models");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(VX3_ERR_NO_DEVICE, "no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(VX3_ERR_NO_DEVICE, "device index out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(VX3_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+    for (int i = 0; i < n; i++) {
+        int rc = validate_model(models[i], i);
+        if (rc) return rc;
+    }
+    CK(cudaSetDevice(device));
+    vx3_batch *b = new vx3_batch();
+    b->device = device;
+    b->nsims = n;
+    auto cleanup = [&](int rc) {
+        vx3_batch_destroy(b);
+        return rc;
+    };
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(VX3_ERR_CUDA, "cudaStreamCreate failed"));
+    cudaEventCreate(&b->ev0);
+    cudaEventCreate(&b->ev1);
+
+    // ---- global tables ----
+    std::vector<VoxMatC> vmat_tab;
+    std::vector<LinkMatC> lmat_tab;
+    std::vector<float> strain_pool, stress_pool;
+    std::map<std::string, int> vmat_index, lmat_index;
+    std::vector<vx3_token> tokens;
+    std::vector<ExtC> exts;
+    std::vector<Chunk> chunks;
+    std::vector<int32_t> targets;
+    std::vector<SimD> simd(n);
+    b->simc.resize(n);
+    b->names.resize(n);
+    b->lmat_global.resize(n);
+    b->matid.resize(n);
+    b->vmat_local.resize(n);
+    b->matcolor.resize(n);
+    b->opts.resize(n);
+    b->h_vmats.resize(n);
+    b->hdt.assign(n, 0.0f);
+
+    auto add_linkmat = [&](LinkMatC lm, const std::vector<float> &sd, const std::vector<float> &ss) -> int {
+        lm.data_off = 0;
+        lm.n_data = (int)sd.size();
+        std::string key = blob(&lm, sizeof(lm)) + blob(sd.data(), sd.size() * 4) + blob(ss.data(), ss.size() * 4);
+        auto it = lmat_index.find(key);
+        if (it != lmat_index.end()) return it->second;
+        lm.data_off = (int)strain_pool.size();
+        strain_pool.insert(strain_pool.end(), sd.begin(), sd.end());
+        stress_pool.insert(stress_pool.end(), ss.begin(), ss.end());
+        lmat_tab.push_back(lm);
+        lmat_index[key] = (int)lmat_tab.size() - 1;
+        return (int)lmat_tab.size() - 1;
+    };
+
+    size_t nvox = 0, nslots = 0;
+    for (int s = 0; s < n; s++) {
+        const vx3_model_desc &m = models[s];
+        bool sticky = false;
+        for (int i = 0; i < m.n_voxel_mats; i++) sticky |= m.voxel_mats[i].sticky != 0;
+        const bool collide = m.opt.enable_collision || m.opt.enable_attach;
+        int lcap = m.n_links;
+        if (collide && sticky) lcap = m.link_capacity > m.n_links ? m.link_capacity : m.n_links + 6 * m.n_voxels + 1024;
+        SimC &S = b->simc[s];
+        memset(&S, 0, sizeof(S));
+        S.voff = (int)nvox;
+        S.nvox = m.n_voxels;
+        S.loff = (int)nslots;
+        S.lcap = lcap;
+        S.nhostlinks = m.n_links;
+        nvox += m.n_voxels;
+        nslots += lcap;
+        if (nvox > 0x3FFFFFFF || nslots > 0x7FFFFFF0) return cleanup(fail(VX3_ERR_INVALID, "batch too large for 32-bit indices"));
+        b->any_collide |= collide;
+        b->any_sticky |= collide && sticky;
+        b->any_detach |= m.opt.enable_detach != 0;
+    }
+
+    std::vector<double> pose(nvox * 8, 0.0), mom(nvox * 6, 0.0), phase(nvox, 0.0), initpos(nvox * 3);
+    std::vector<int32_t> vflags(nvox), vmat(nvox), vsim(nvox), vlinks(nvox * 6), vext(nvox, -1);
+    std::vector<float> tempe(nvox, 0.0f), prevdt(nvox, 0.0f);
+    std::vector<int16_t> ixyz(nvox * 3);
+    std::vector<double> base_cilia, shift_cilia;
+    bool any_cilia = false;
+    for (int s = 0; s < n; s++) any_cilia |= models[s].opt.enable_cilia != 0;
+    if (any_cilia) {
+        base_cilia.assign(nvox * 3, 0.0);
+        shift_cilia.assign(nvox * 3, 0.0);
+    }
+    std::vector<int2> lends(nslots, make_int2(-1, -1));
+    std::vector<int32_t> lstate(nslots, 0), lmat(nslots, 0);
+    std::vector<double> lhist(nslots * 9, 0.0), lrest(nslots, 0.0);
+    std::vector<float4> lstrain(nslots, make_float4(0, 0, 0, 0));
+    std::vector<float2> larea(nslots, make_float2(0, 0));
+
+    for (int s = 0; s < n; s++) {
+        const vx3_model_desc &m = models[s];
+        SimC &S = b->simc[s];
+        SimD &dy = simd[s];
+        memset(&dy, 0, sizeof(dy));
+        b->names[s] = std::string(m.name, strnlen(m.name, sizeof(m.name)));
+        b->opts[s] = m.opt;
+        // link materials of the model, then the (m,m) pair of every sticky material (attach)
+        std::vector<int> &lg = b->lmat_global[s];
+        lg.resize(m.n_link_mats);
+        for (int i = 0; i < m.n_link_mats; i++) {
+            const vx3_link_material &in = m.link_mats[i];
+            LinkMatC lm;
+            memset(&lm, 0, sizeof(lm));
+            lm.E = in.m.E; lm.nu = in.m.nu; lm.eHat = in.m.eHat; lm.epsilonFail = in.m.epsilonFail;
+            lm.a1 = in.a1; lm.a2 = in.a2; lm.b1 = in.b1; lm.b2 = in.b2; lm.b3 = in.b3;
+            lm.sqA1 = in.sqA1; lm.sqA2xIp = in.sqA2xIp; lm.sqB1 = in.sqB1; lm.sqB2xFMp = in.sqB2xFMp; lm.sqB3xIp = in.sqB3xIp;
+            lm.linear = in.m.linear;
+            std::vector<float> sd{0.0f}, ss{0.0f}; // syncVectors pushes a 0, then the host data (which starts with 0)
+            for (int k = 0; k < in.m.n_data; k++) {
+                sd.push_back(in.m.strain_data ? in.m.strain_data[k] : 0.0f);
+                ss.push_back(in.m.stress_data ? in.m.stress_data[k] : 0.0f);
+            }
+            while (sd.size() < 2) { sd.push_back(0.0f); ss.push_back(0.0f); }
+            lg[i] = add_linkmat(lm, sd, ss);
+        }
+        std::vector<int> vm_global(m.n_voxel_mats);
+        b->matid[s].resize(m.n_voxel_mats);
+        double maxSize = 0, maxCte = 0;
+        for (int i = 0; i < m.n_voxel_mats; i++) {
+            const vx3_voxel_material &in = m.voxel_mats[i];
+            VoxMatC vm;
+            memset(&vm, 0, sizeof(vm));
+            vm.nomSize = in.nomSize;
+            for (int k = 0; k < 3; k++) {
+                vm.size[k] = in.nomSize * in.extScale[k];
+                maxSize = std::max(maxSize, fabs(vm.size[k]));
+            }
+            maxCte = std::max(maxCte, (double)fabsf(in.alphaCTE));
+            vm.cilia = in.cilia;
+            vm.thermal_on_after = in.thermal_on_after_s;
+            vm.cilia_on_after = in.cilia_on_after_s;
+            vm.remove_after = in.remove_after_s;
+            vm.alphaCTE = in.alphaCTE; vm.muStatic = in.muStatic; vm.muKinetic = in.muKinetic;
+            vm.massInverse = in.massInverse; vm.mass = in.mass; vm.momentInertiaInverse = in.momentInertiaInverse;
+            vm.globalDampT = in.zetaGlobal * in._2xSqMxExS;
+            vm.globalDampR = in.zetaGlobal * in._2xSqIxExSxSxS;
+            vm.colDampT = in.zetaCollision * in._2xSqMxExS;
+            vm.penStiff = (float)(2 * in.E * in.nomSize);
+            vm.gravityForce = -in.mass * 9.80665f * in.gravMult;
+            vm.dampMultNum = 2 * in.sqrtMass * in.zetaInternal;
+            vm.E = in.E;
+            vm.fixed = in.fixed != 0; vm.sticky = in.sticky != 0; vm.is_target = in.is_target != 0; vm.is_measured = in.is_measured != 0;
+            vm.matid = in.matid;
+            vm.self_lmat = -1;
+            if (in.sticky && S.lcap > m.n_links) {
+                int found = -1;
+                for (int k = 0; k < m.n_link_mats && found < 0; k++)
+                    if (m.link_mats[k].vox1_mat == i && m.link_mats[k].vox2_mat == i) found = lg[k];
+                if (found < 0) {
+                    LinkMatC lm;
+                    std::vector<float> sd, ss;
+                    make_self_linkmat(in, lm, sd, ss);
+                    found = add_linkmat(lm, sd, ss);
+                }
+                vm.self_lmat = found;
+            }
+            std::string key = blob(&vm, sizeof(vm));
+            auto it = vmat_index.find(key);
+            if (it == vmat_index.end()) {
+                vmat_tab.push_back(vm);
+                it = vmat_index.emplace(key, (int)vmat_tab.size() - 1).first;
+            }
+            vm_global[i] = it->second;
+            b->matid[s][i] = in.matid;
+            b->h_vmats[s].push_back(in);
+            b->h_vmats[s].back().strain_data = b->h_vmats[s].back().stress_data = nullptr;
+            b->matcolor[s].push_back(in.r / 255.0f);
+            b->matcolor[s].push_back(in.g / 255.0f);
+            b->matcolor[s].push_back(in.b / 255.0f);
+            b->matcolor[s].push_back(in.a / 255.0f);
+        }
+        // programs
+        for (int p = 0; p < VX3_PROG_COUNT; p++) {
+            S.prog_off[p] = (int)tokens.size();
+            S.prog_n[p] = m.prog[p].n;
+            for (int k = 0; k < m.prog[p].n; k++) tokens.push_back(m.prog[p].tok[k]);
+        }
+        S.has_ff = S.prog_n[VX3_PROG_FORCE_X] > 0 || S.prog_n[VX3_PROG_FORCE_Y] > 0 || S.prog_n[VX3_PROG_FORCE_Z] > 0;
+        S.has_attach_cond = 0;
+        for (int c = 0; c < 5; c++) S.has_attach_cond |= S.prog_n[VX3_PROG_ATTACH_0 + c] > 0;
+        S.vary_temp = m.opt.vary_temp_enabled != 0;
+        S.enable_expansion = m.opt.enable_expansion != 0;
+        S.enable_collision = m.opt.enable_collision != 0;
+        S.enable_attach = m.opt.enable_attach != 0;
+        S.enable_detach = m.opt.enable_detach != 0;
+        S.enable_cilia = m.opt.enable_cilia != 0;
+        S.safety_guard = m.opt.safety_guard;
+        S.temp_amp = m.opt.temp_amplitude;
+        S.temp_period = m.opt.temp_period;
+        S.vox_size = m.opt.vox_size;
+        S.pair_radius = m.opt.max_dist_in_voxel_lengths_to_count_as_pair * m.opt.vox_size;
+        S.dt_frac = m.opt.dt_frac;
+        S.optimal_dt = vx3_model_recommended_dt(&m);
+        // voxels
+        const int vo = S.voff;
+        b->vmat_local[s].assign(m.vox_mat, m.vox_mat + m.n_voxels);
+        double maxT = fabs(m.opt.temp_amplitude);
+        const int ext_base = (int)exts.size();
+        for (int i = 0; i < m.n_externals; i++) {
+            const vx3_external &e = m.externals[i];
+            ExtC x;
+            memset(&x, 0, sizeof(x));
+            x.dof = e.dof_fixed;
+            for (int k = 0; k < 3; k++) { x.force[k] = e.force[k]; x.moment[k] = e.moment[k]; x.translation[k] = e.translation[k]; }
+            for (int k = 0; k < 4; k++) x.rotq[k] = e.rotation_q[k];
+            exts.push_back(x);
+        }
+        S.tgt_off = (int)targets.size();
+        for (int i = 0; i < m.n_voxels; i++) {
+            const size_t g = (size_t)vo + i;
+            pose[8 * g + 0] = m.pos[3 * i]; pose[8 * g + 1] = m.pos[3 * i + 1]; pose[8 * g + 2] = m.pos[3 * i + 2];
+            if (m.orient) for (int k = 0; k < 4; k++) pose[8 * g + 3 + k] = m.orient[4 * i + k];
+            else pose[8 * g + 3] = 1.0;
+            for (int k = 0; k < 3; k++) {
+                initpos[3 * g + k] = m.pos[3 * i + k];
+                if (m.lin_mom) mom[6 * g + k] = m.lin_mom[3 * i + k];
+                if (m.ang_mom) mom[6 * g + 3 + k] = m.ang_mom[3 * i + k];
+            }
+            vflags[g] = (m.vox_flags[i] & VXF_BOOLSTATE_MASK) | VXF_ENABLE_ATTACH;
+            vmat[g] = vm_global[m.vox_mat[i]];
+            vsim[g] = s;
+            if (m.phase_offset) phase[g] = m.phase_offset[i];
+            if (m.temp) {
+                tempe[g] = m.temp[i];
+                maxT = std::max(maxT, (double)fabsf(m.temp[i]));
+            }
+            for (int k = 0; k < 6; k++) {
+                int li = m.vox_links[6 * i + k];
+                vlinks[6 * g + k] = li >= 0 ? S.loff + li : -1;
+            }
+            if (m.vox_ext && m.vox_ext[i] >= 0) {
+                if (m.vox_ext[i] >= m.n_externals) return cleanup(fail(VX3_ERR_INVALID, "external index out of range"));
+                vext[g] = ext_base + m.vox_ext[i];
+            }
+            ixyz[3 * g] = m.ix[i]; ixyz[3 * g + 1] = m.iy[i]; ixyz[3 * g + 2] = m.iz[i];
+            if (any_cilia) for (int k = 0; k < 3; k++) {
+                if (m.base_cilia) base_cilia[3 * g + k] = m.base_cilia[3 * i + k];
+                if (m.shift_cilia) shift_cilia[3 * g + k] = m.shift_cilia[3 * i + k];
+            }
+            if (m.voxel_mats[m.vox_mat[i]].is_target) targets.push_back((int)g); // registerTargets
+        }
+        S.ntgt = (int)targets.size() - S.tgt_off;
+        // collision grid cell: at least the largest possible collision envelope (2 * 0.625 * baseSizeAverage)
+        const double cell = 2 * VX3_COLLISION_ENVELOPE_RADIUS * maxSize * (1 + maxT * maxCte) * (1 + 1e-6);
+        S.cell_inv = cell > 0 ? 1.0 / cell : 1.0;
+        // links
+        for (int i = 0; i < m.n_links; i++) {
+            const size_t g = (size_t)S.loff + i;
+            const int vn = m.link_vneg[i], vp = m.link_vpos[i], ax = m.link_axis[i];
+            lends[g] = make_int2(vo + vn, vo + vp);
+            lmat[g] = lg[m.link_mat[i]];
+            int st = (ax << LKS_AXIS_SHIFT);
+            if (!m.link_small_angle || m.link_small_angle[i]) st |= LKS_SMALL;
+            if (m.link_flags && (m.link_flags[i] & VX3_LINK_LOCAL_VELOCITY_VALID)) st |= LKS_VALID;
+            lstate[g] = st;
+            for (int k = 0; k < 3; k++) {
+                if (m.link_pos2) lhist[9 * g + k] = m.link_pos2[3 * i + k];
+                if (m.link_angle1v) lhist[9 * g + 3 + k] = m.link_angle1v[3 * i + k];
+                if (m.link_angle2v) lhist[9 * g + 6 + k] = m.link_angle2v[3 * i + k];
+            }
+            const vx3_voxel_material &mn = m.voxel_mats[m.vox_mat[vn]], &mp = m.voxel_mats[m.vox_mat[vp]];
+            const float tn = m.temp ? m.temp[vn] : 0.0f, tp = m.temp ? m.temp[vp] : 0.0f;
+            // VX3_Link::reset() defaults (VX3_Link.cu:58-70) unless the model carries link state
+            if (m.link_rest_length) lrest[g] = m.link_rest_length[i];
+            else lrest[g] = 0.5 * ((mn.nomSize * mn.extScale[ax]) * (1 + tn * mn.alphaCTE) + (mp.nomSize * mp.extScale[ax]) * (1 + tp * mp.alphaCTE));
+            float4 sn = make_float4(0, 0, 0, 0);
+            if (m.link_strain) sn.x = m.link_strain[i];
+            if (m.link_max_strain) sn.y = m.link_max_strain[i];
+            if (m.link_strain_offset) sn.z = m.link_strain_offset[i];
+            if (m.link_stress) sn.w = m.link_stress[i];
+            lstrain[g] = sn;
+            const float a0 = (float)mn.nomSize, a1 = (float)mp.nomSize;
+            larea[g] = make_float2(m.link_transverse_area ? m.link_transverse_area[i] : 0.5f * (a0 * a0 + a1 * a1),
+                                   m.link_transverse_strain_sum ? m.link_transverse_strain_sum[i] : 0.0f);
+        }
+        // CoM chunks
+        S.chunk_off = (int)chunks.size();
+        const int CH = 4096;
+        for (int c0 = 0; c0 < m.n_voxels; c0 += CH) chunks.push_back(Chunk{s, vo + c0, std::min(CH, m.n_voxels - c0), 0});
+        S.nchunks = (int)chunks.size() - S.chunk_off;
+        dy.status = VX3_SIM_RUNNING;
+        dy.link_cnt = m.n_links;
+    }
+
+    Dev &D = b->D;
+    memset(&D, 0, sizeof(D));
+    D.nsims = n;
+    D.nvox = (int)nvox;
+    D.nlinkslots = (int)nslots;
+    D.nchunks = (int)chunks.size();
+#define UP(field, vec)                                                                                                  \
+    do {                                                                                                                \
+        std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type *p_ = nullptr;                            \
+        int rc_ = b->upload(&p_, vec);                                                                                  \
+        if (rc_) return cleanup(rc_);                                                                                   \
+        D.field = p_;                                                                                                   \
+    } while (0)
+    UP(simc, b->simc);
+    UP(simd, simd);
+    UP(vmat_tab, vmat_tab);
+    UP(lmat_tab, lmat_tab);
+    b->h_lmat_tab = lmat_tab;
+    UP(strain_pool, strain_pool);
+    UP(stress_pool, stress_pool);
+    UP(tokens, tokens);
+    UP(exts, exts);
+    UP(chunks, chunks);
+    UP(targets, targets);
+    UP(pose, pose);
+    UP(mom, mom);
+    UP(vflags, vflags);
+    UP(vmat, vmat);
+    UP(vsim, vsim);
+    UP(phase, phase);
+    UP(tempe, tempe);
+    UP(prevdt, prevdt);
+    UP(vlinks, vlinks);
+    UP(vext, vext);
+    UP(ixyz, ixyz);
+    UP(initpos, initpos);
+    if (any_cilia) {
+        UP(base_cilia, base_cilia);
+        UP(shift_cilia, shift_cilia);
+    }
+    UP(lends, lends);
+    UP(lstate, lstate);
+    UP(lmat, lmat);
+    UP(lhist, lhist);
+    UP(lrest, lrest);
+    UP(lstrain, lstrain);
+    UP(larea, larea);
+#undef UP
+    int rc;
+    if ((rc = b->alloc(&D.lforce, nslots * 12))) return cleanup(rc);
+    if ((rc = b->alloc(&D.com_part, chunks.size() * 6))) return cleanup(rc);
+    if (b->any_collide) {
+        int H = 1024;
+        while (H < 2 * (int)nvox && H < (1 << 24)) H <<= 1;
+        D.hmask = H - 1;
+        if ((rc = b->alloc(&D.contact, nvox * 3))) return cleanup(rc);
+        if ((rc = b->alloc(&D.cell_cnt, (size_t)H))) return cleanup(rc);
+        if ((rc = b->alloc(&D.cell_start, (size_t)H + 1))) return cleanup(rc);
+        if ((rc = b->alloc(&D.cell_cursor, (size_t)H))) return cleanup(rc);
+        if ((rc = b->alloc(&D.cell_items, nvox))) return cleanup(rc);
+        if ((rc = b->alloc(&D.vcell, nvox))) return cleanup(rc);
+        D.cand_cap = 2048;
+        if ((rc = b->alloc(&D.cands, (size_t)D.cand_cap))) return cleanup(rc);
+        if ((rc = b->alloc(&D.cand_count, 1))) return cleanup(rc);
+    }
+    // device-side init at the top of CUDA_Simulation (VX3_SimulationManager.cu:20-24,54-55)
+    run_com(b, 0);
+    k_set_dt<<<cdiv(n, 128), 128, 0, b->stream>>>(D, -1.0f);
+    for (int s = 0; s < n; s++) {
+        double od = b->simc[s].optimal_dt;
+        if (od < 1e-10) od = 1e-10;
+        b->hdt[s] = (float)(b->simc[s].dt_frac * od);
+    }
+    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach, any_cilia, prop);
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaGetLastError());
+    *out = b;
+    return VX3_OK;
+}
+
+extern "C" void vx3_batch_destroy(vx3_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    persistent_free(b->pplan);
+    for (auto &e : b->prof.ev) cudaEventDestroy(e);
+    for (void *p : b->allocs) cudaFree(p);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+// ------------------------------------------------------------------ stepping
+static int set_dt(vx3_batch *b, float dt) {
+    k_set_dt<<<cdiv(b->nsims, 128), 128, 0, b->stream>>>(b->D, dt);
+    b->launches++;
+    for (int s = 0; s < b->nsims; s++) {
+        if (dt < 0) {
+            double od = b->simc[s].optimal_dt;
+            if (od < 1e-10) od = 1e-10;
+            b->hdt[s] = (float)(b->simc[s].dt_frac * od);
+        } else
+            b->hdt[s] = dt;
+    }
+    return VX3_OK;
+}
+
+// does any simulation sample its centre of mass at doTimeStep call number `step` (1-based CurStepCount)?
+static bool com_step(const vx3_batch *b, long long step) {
+    for (int s = 0; s < b->nsims; s++) {
+        if (b->hdt[s] == 0) continue;
+        const int cycle = (int)(b->simc[s].temp_period / b->hdt[s]);
+        if (cycle > 0 && step % cycle == 0) return true;
+    }
+    return false;
+}
+// number of steps from hsteps until (and including) the next CoM sampling step; 0 = never
+static long long next_com_step(const vx3_batch *b) {
+    long long best = 0;
+    for (int s = 0; s < b->nsims; s++) {
+        if (b->hdt[s] == 0) continue;
+        const int cycle = (int)(b->simc[s].temp_period / b->hdt[s]);
+        if (cycle <= 0) continue;
+        const long long nxt = (b->hsteps / cycle + 1) * cycle - b->hsteps;
+        if (best == 0 || nxt < best) best = nxt;
+    }
+    return best;
+}
+
+#define LAUNCH(cls, kern, grid, block, ...)                                                                            \
+    do {                                                                                                                \
+        const bool p_ = b->prof.begin(cls, st);                                                                         \
+        kern<<<grid, block, 0, st>>>(__VA_ARGS__);                                                                      \
+        if (p_) b->prof.end(st);                                                                                        \
+        b->launches++;                                                                                                  \
+    } while (0)
+
+static void launch_step(vx3_batch *b, bool check_stop) {
+    const Dev &D = b->D;
+    cudaStream_t st = b->stream;
+    if (D.nlinkslots > 0) LAUNCH(KC_LINKS, k_links, cdiv(D.nlinkslots, VX3_BLOCK), VX3_BLOCK, D);
+    if (b->any_collide) {
+        LAUNCH(KC_GRID_COUNT, k_grid_count, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
+        LAUNCH(KC_GRID_SCAN, k_grid_scan, 1, 1024, D);
+        LAUNCH(KC_GRID_FILL, k_grid_fill, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
+        LAUNCH(KC_CONTACT, k_contact, cdiv(D.nvox, 128), 128, D);
+        if (b->any_sticky) LAUNCH(KC_RESOLVE, k_resolve, 1, 1024, D);
+    } else if (b->any_detach) { // keep the surface flags current (regenerateSurfaceVoxels after a detach)
+        LAUNCH(KC_SURFACE, k_surface, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
+    }
+    if (b->any_detach && D.nlinkslots > 0) LAUNCH(KC_DETACH, k_detach, cdiv(D.nlinkslots, VX3_BLOCK), VX3_BLOCK, D);
+    LAUNCH(KC_VOXELS, k_voxels, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
+    const bool com = com_step(b, b->hsteps + 1);
+    if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
+    LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, com ? 1 : 0, check_stop ? 1 : 0);
+    b->hsteps++;
+}
+
+// advance k steps; the on-chip persistent kernel takes the stretches between CoM sampling steps when the batch
+// qualifies (single small collision-free body), the streaming kernels do the rest
+static int advance(vx3_batch *b, long long k, bool check_stop) {
+    while (k > 0) {
+        if (b->use_persistent && b->pplan.ok) {
+            long long nxt = next_com_step(b); // steps until the next sampling step (it must run on the streaming path)
+            long long run = (nxt == 0) ? k : std::min(k, nxt - 1);
+            if (run > 0) {
+                const bool p_ = b->prof.begin(KC_PERSISTENT, b->stream);
+                int rc = persistent_run(b->pplan, b->D, b->stream, run, check_stop, &b->launches);
+                if (p_) b->prof.end(b->stream);
+                if (rc) return fail(VX3_ERR_CUDA, "persistent kernel launch failed");
+                b->hsteps += run;
+                k -= run;
+                continue;
+            }
+        }
+        launch_step(b, check_stop);
+        k--;
+    }
+    return VX3_OK;
+}
+
+static int check_device_errors(vx3_batch *b) {
+    std::vector<SimD> h(b->nsims);
+    CK(cudaMemcpyAsync(h.data(), b->D.simd, sizeof(SimD) * b->nsims, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int s = 0; s < b->nsims; s++)
+        if (h[s].err) return fail(h[s].err, "simulation " + std::to_string(s) + ": device-side capacity/consistency error (link pool, partner list or attach candidates)");
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_step_dt(vx3_batch *b, int64_t k, float dt) {
+    if (!b || k < 0) return fail(VX3_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(b->device));
+    const long long l0 = b->launches;
+    set_dt(b, dt);
+    CK(cudaEventRecord(b->ev0, b->stream));
+    int rc = advance(b, k, false);
+    if (rc) return rc;
+    CK(cudaEventRecord(b->ev1, b->stream));
+    CK(cudaEventSynchronize(b->ev1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    b->last_ms = ms;
+    b->last_launches = b->launches - l0;
+    b->prof.collect();
+    return check_device_errors(b);
+}
+
+extern "C" int vx3_batch_step(vx3_batch *b, int64_t k) { return vx3_batch_step_dt(b, k, -1.0f); }
+
+extern "C" int vx3_batch_sync(vx3_batch *b) {
+    if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    return VX3_OK;
+}
+
+static int fetch_simd(vx3_batch *b, std::vector<SimD> &h) {
+    h.resize(b->nsims);
+    CK(cudaMemcpyAsync(h.data(), b->D.simd, sizeof(SimD) * b->nsims, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history_cb cb, void *user) {
+    if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
+    CK(cudaSetDevice(b->device));
+    long long max_steps = (opts && opts->max_steps > 0) ? opts->max_steps : 1000000;
+    int chunk = (opts && opts->steps_per_launch > 0) ? opts->steps_per_launch : 0;
+    const bool history = opts && opts->emit_history && cb;
+    const long long l0 = b->launches;
+    set_dt(b, -1.0f);
+    std::vector<SimD> h;
+    int rc = fetch_simd(b, h);
+    if (rc) return rc;
+    // history frame cadence (VX3_SimulationManager.cu:56,71)
+    std::vector<long long> frame_every(b->nsims, 0);
+    HistoryWriter hw;
+    if (history) {
+        for (int s = 0; s < b->nsims; s++) {
+            const vx3_sim_options &o = b->opts[s];
+            if (o.record_step_size > 0) {
+                double rec = b->simc[s].optimal_dt; // recommendedTimeStep()
+                frame_every[s] = (long long)(int)(o.record_step_size / (10000.0 * rec * o.dt_frac)) + 1;
+                std::string hdr = hw.header(b->matid[s], b->matcolor[s], o.vox_size);
+                cb(user, s, hdr.data(), hdr.size());
+            }
+        }
+    }
+    CK(cudaEventRecord(b->ev0, b->stream));
+    k_sim_update<<<cdiv(b->nsims, 128), 128, 0, b->stream>>>(b->D, 2); // StopConditionMet() before the first step
+    b->launches++;
+    long long j = 0; // loop index of CUDA_Simulation (:62); all simulations start this run at j = 0
+    if (chunk <= 0) {
+        long long perstep = std::max<long long>(1, (long long)b->D.nvox + b->D.nlinkslots);
+        chunk = (int)std::max<long long>(16, std::min<long long>(4096, 40000000 / perstep));
+    }
+    while (j < max_steps) {
+        // frames are emitted at the top of loop iteration j when j % real_stepsize == 0, after that iteration's step (:70-114)
+        long long todo = std::min<long long>(chunk, max_steps - j);
+        if (history) {
+            for (int s = 0; s < b->nsims; s++)
+                if (frame_every[s] > 0) {
+                    long long nf = frame_every[s] - (j % frame_every[s]); // steps until a frame step is completed
+                    if (j % frame_every[s] == 0) nf = 1;
+                    todo = std::min(todo, nf);
+                }
+        }
+        rc = advance(b, todo, true);
+        if (rc) return rc;
+        j += todo;
+        rc = fetch_simd(b, h);
+        if (rc) return rc;
+        bool running = false;
+        for (int s = 0; s < b->nsims; s++) {
+            if (h[s].err) return fail(h[s].err, "simulation " + std::to_string(s) + ": device-side capacity/consistency error");
+            running |= h[s].status == VX3_SIM_RUNNING;
+        }
+        if (history) {
+            for (int s = 0; s < b->nsims; s++) {
+                if (frame_every[s] <= 0) continue;
+                // iteration jj = j-1 just completed its doTimeStep; the reference prints when jj % real_stepsize == 0
+                // and the simulation executed that step (it breaks out of the loop before printing otherwise)
+                const long long jj = j - 1;
+                if (jj % frame_every[s] != 0) continue;
+                if (h[s].steps != j) continue; // stopped or diverged earlier
+                if (h[s].status == VX3_SIM_DIVERGED) continue;
+                std::string fr;
+                rc = history_frame(b, s, jj, h[s].t, hw, fr);
+                if (rc) return rc;
+                cb(user, s, fr.data(), fr.size());
+            }
+        }
+        if (!running) break;
+    }
+    if (j >= max_steps) {
+        k_step_cap<<<cdiv(b->nsims, 128), 128, 0, b->stream>>>(b->D);
+        b->launches++;
+    }
+    run_com(b, 1); // updateCurrentCenterOfMass + computeFitness (:116-117)
+    CK(cudaEventRecord(b->ev1, b->stream));
+    CK(cudaEventSynchronize(b->ev1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    b->last_ms = ms;
+    b->last_launches = b->launches - l0;
+    b->prof.collect();
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_set_profiling(vx3_batch *b, int on, int use_persistent) {
+    if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
+    CK(cudaSetDevice(b->device));
+    b->use_persistent = use_persistent != 0;
+    b->prof.on = on != 0;
+    if (on && b->prof.ev.empty()) {
+        b->prof.ev.resize(16384);
+        for (auto &e : b->prof.ev) CK(cudaEventCreate(&e));
+    }
+    for (int k = 0; k < KC_COUNT; k++) {
+        b->prof.ms[k] = 0;
+        b->prof.cnt[k] = 0;
+    }
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_kernel_stats(vx3_batch *b, int index, char *name, int name_cap, double *total_ms, int64_t *launches) {
+    if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
+    if (index < 0 || index >= KC_COUNT) return 1; // end of list
+    if (name && name_cap > 0) {
+        strncpy(name, kKernelNames[index], name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (total_ms) *total_ms = b->prof.ms[index];
+    if (launches) *launches = b->prof.cnt[index];
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_last_timing(vx3_batch *b, double *ms, int64_t *launches) {
+    if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
+    if (ms) *ms = b->last_ms;
+    if (launches) *launches = b->last_launches;
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_recommended_dt(vx3_batch *b, int sim, double *out) {
+    if (!b || sim < 0 || sim >= b->nsims || !out) return fail(VX3_ERR_INVALID, "bad arguments");
+    *out = b->simc[sim].optimal_dt;
+    return VX3_OK;
+}
+
+// ------------------------------------------------------------------ read-back
+template <class T> static int d2h(vx3_batch *b, std::vector<T> &h, const T *d, size_t off, size_t n) {
+    h.resize(n);
+    if (n == 0) return VX3_OK;
+    CK(cudaMemcpyAsync(h.data(), d + off, n * sizeof(T), cudaMemcpyDeviceToHost, b->stream));
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
+    if (!b || !w || sim < 0 || sim >= b->nsims) return fail(VX3_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(b->device));
+    const SimC &S = b->simc[sim];
+    std::vector<SimD> hd;
+    int rc = fetch_simd(b, hd);
+    if (rc) return rc;
+    const int nv = S.nvox, nl = hd[sim].link_cnt;
+    if (w->n_voxels < nv || w->n_links < nl) {
+        w->n_voxels = nv;
+        w->n_links = nl;
+        return fail(VX3_ERR_INVALID, "state view buffers too small");
+    }
+    w->n_voxels = nv;
+    w->n_links = nl;
+    const Dev &D = b->D;
+    std::vector<double> pose, mom, contact, lhist, lrest, lforce;
+    std::vector<int32_t> vflags, vlinks, lstate, lmat;
+    std::vector<float> tempe;
+    std::vector<int2> lends;
+    std::vector<float4> lstrain;
+    if ((rc = d2h(b, pose, D.pose, 8 * (size_t)S.voff, 8 * (size_t)nv))) return rc;
+    if ((rc = d2h(b, mom, D.mom, 6 * (size_t)S.voff, 6 * (size_t)nv))) return rc;
+    if ((rc = d2h(b, vflags, D.vflags, S.voff, nv))) return rc;
+    if ((rc = d2h(b, tempe, D.tempe, S.voff, nv))) return rc;
+    if ((rc = d2h(b, vlinks, D.vlinks, 6 * (size_t)S.voff, 6 * (size_t)nv))) return rc;
+    if (D.contact && (rc = d2h(b, contact, D.contact, 3 * (size_t)S.voff, 3 * (size_t)nv))) return rc;
+    if ((rc = d2h(b, lends, D.lends, S.loff, nl))) return rc;
+    if ((rc = d2h(b, lstate, D.lstate, S.loff, nl))) return rc;
+    if ((rc = d2h(b, lmat, D.lmat, S.loff, nl))) return rc;
+    if ((rc = d2h(b, lhist, D.lhist, 9 * (size_t)S.loff, 9 * (size_t)nl))) return rc;
+    if ((rc = d2h(b, lrest, D.lrest, S.loff, nl))) return rc;
+    if ((rc = d2h(b, lforce, D.lforce, 12 * (size_t)S.loff, 12 * (size_t)nl))) return rc;
+    if ((rc = d2h(b, lstrain, D.lstrain, S.loff, nl))) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < nv; i++) {
+        for (int k = 0; k < 3; k++) {
+            if (w->pos) w->pos[3 * i + k] = pose[8 * (size_t)i + k];
+            if (w->lin_mom) w->lin_mom[3 * i + k] = mom[6 * (size_t)i + k];
+            if (w->ang_mom) w->ang_mom[3 * i + k] = mom[6 * (size_t)i + 3 + k];
+            if (w->contact_force) w->contact_force[3 * i + k] = contact.empty() ? 0.0 : contact[3 * (size_t)i + k];
+        }
+        if (w->orient) for (int k = 0; k < 4; k++) w->orient[4 * i + k] = pose[8 * (size_t)i + 3 + k];
+        if (w->vox_flags) w->vox_flags[i] = vflags[i] & VXF_BOOLSTATE_MASK;
+        if (w->temp) w->temp[i] = tempe[i];
+        if (w->vox_links) for (int k = 0; k < 6; k++) w->vox_links[6 * i + k] = vlinks[6 * (size_t)i + k] >= 0 ? vlinks[6 * (size_t)i + k] - S.loff : -1;
+    }
+    // global link-material index -> the simulation's local index (attach-created materials follow the model's)
+    std::map<int, int> lm_local;
+    for (size_t i = 0; i < b->lmat_global[sim].size(); i++) lm_local.emplace(b->lmat_global[sim][i], (int)i);
+    int next_local = (int)b->lmat_global[sim].size();
+    for (int i = 0; i < nl; i++) {
+        if (w->link_vneg) w->link_vneg[i] = lends[i].x - S.voff;
+        if (w->link_vpos) w->link_vpos[i] = lends[i].y - S.voff;
+        if (w->link_axis) w->link_axis[i] = (lstate[i] & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+        if (w->link_mat) {
+            auto it = lm_local.find(lmat[i]);
+            if (it == lm_local.end()) it = lm_local.emplace(lmat[i], next_local++).first;
+            w->link_mat[i] = it->second;
+        }
+        for (int k = 0; k < 3; k++) {
+            if (w->link_pos2) w->link_pos2[3 * i + k] = lhist[9 * (size_t)i + k];
+            if (w->link_angle1v) w->link_angle1v[3 * i + k] = lhist[9 * (size_t)i + 3 + k];
+            if (w->link_angle2v) w->link_angle2v[3 * i + k] = lhist[9 * (size_t)i + 6 + k];
+            if (w->link_force_neg) w->link_force_neg[3 * i + k] = lforce[12 * (size_t)i + k];
+            if (w->link_moment_neg) w->link_moment_neg[3 * i + k] = lforce[12 * (size_t)i + 3 + k];
+            if (w->link_force_pos) w->link_force_pos[3 * i + k] = lforce[12 * (size_t)i + 6 + k];
+            if (w->link_moment_pos) w->link_moment_pos[3 * i + k] = lforce[12 * (size_t)i + 9 + k];
+        }
+        if (w->link_strain) w->link_strain[i] = lstrain[i].x;
+        if (w->link_max_strain) w->link_max_strain[i] = lstrain[i].y;
+        if (w->link_strain_offset) w->link_strain_offset[i] = lstrain[i].z;
+        if (w->link_stress) w->link_stress[i] = lstrain[i].w;
+        if (w->link_flags) w->link_flags[i] = lstate[i] & LKS_PUBLIC_MASK;
+        if (w->link_rest_length) w->link_rest_length[i] = lrest[i];
+    }
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_results(vx3_batch *b, vx3_result *out) {
+    if (!b || !out) return fail(VX3_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(b->device));
+    run_com(b, 1);
+    std::vector<SimD> h;
+    int rc = fetch_simd(b, h);
+    if (rc) return rc;
+    for (int s = 0; s < b->nsims; s++) {
+        vx3_result &r = out[s];
+        memset(&r, 0, sizeof(r));
+        strncpy(r.name, b->names[s].c_str(), sizeof(r.name) - 1);
+        const SimD &d = h[s];
+        r.status = d.status;
+        r.num_voxel = b->simc[s].nvox;
+        r.num_measured_voxel = d.n_measured;
+        r.num_close_pairs = d.num_close_pairs;
+        r.steps = d.steps;
+        r.num_links = d.link_cnt;
+        r.collision_count = d.collision_count;
+        r.current_time = d.t;
+        r.fitness_score = d.status == VX3_SIM_DIVERGED ? NAN : d.fitness;
+        r.vox_size = b->simc[s].vox_size;
+        for (int k = 0; k < 3; k++) {
+            r.initial_com[k] = d.com0[k];
+            r.current_com[k] = d.com[k];
+        }
+        r.total_distance_of_all_voxels = d.total_dist;
+        r.recent_angle = d.recent_angle;
+        r.target_closeness = d.target_closeness;
+        r.dt = d.dt;
+    }
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_positions(vx3_batch *b, int sim, double *init_pos, double *pos, int32_t *mats) {
+    if (!b || sim < 0 || sim >= b->nsims) return fail(VX3_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(b->device));
+    const SimC &S = b->simc[sim];
+    std::vector<double> pose, ip;
+    int rc;
+    if ((rc = d2h(b, pose, b->D.pose, 8 * (size_t)S.voff, 8 * (size_t)S.nvox))) return rc;
+    if ((rc = d2h(b, ip, (const double *)b->D.initpos, 3 * (size_t)S.voff, 3 * (size_t)S.nvox))) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < S.nvox; i++) {
+        for (int k = 0; k < 3; k++) {
+            if (pos) pos[3 * i + k] = pose[8 * (size_t)i + k];
+            if (init_pos) init_pos[3 * i + k] = ip[3 * (size_t)i + k];
+        }
+        if (mats) mats[i] = b->matid[sim][b->vmat_local[sim][i]];
+    }
+    return VX3_OK;
+}
+
+// sortResults (VX3_SimulationManager.cu:472) with VX3_SimulationResult::compareFitnessScore
+// (VX3_SimulationResult.h:26-33): fitness descending, NaN last.  Host-only.
+extern "C" void vx3_sort_results(vx3_result *r, int n) {
+    if (!r || n <= 1) return;
+    std::stable_sort(r, r + n, [](const vx3_result &a, const vx3_result &b) {
+        const bool an = std::isnan(a.fitness_score), bn = std::isnan(b.fitness_score);
+        if (an) return false;
+        if (bn) return true;
+        return a.fitness_score > b.fitness_score;
+    });
+}
+
+#include "vx3_history.inl"

@@ -10,14 +10,15 @@ ROOT = os.path.dirname(HERE)
 _cache = {}
 
 
-def engine_path(strict=False):
-    return os.path.join(HERE, "lib", "libvx3_b200_strict.so" if strict else "libvx3_b200.so")
+def engine_path(fma=False):
+    return os.path.join(HERE, "lib", "libvx3_b200_fma.so" if fma else "libvx3_b200.so")
 
 
-def load_engine(strict=False):
-    key = ("engine", strict)
+def load_engine(fma=False):
+    """fma=False: the product (parity-grade, -fmad=false).  fma=True: the FMA-contracted experimental build."""
+    key = ("engine", fma)
     if key not in _cache:
-        p = engine_path(strict)
+        p = engine_path(fma)
         if not os.path.exists(p):
             raise ImportError("native engine %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)" % p)
