@@ -40,10 +40,13 @@ def check_state(se, so, what, kin=TOL_KIN, link=TOL_LINK, links=True):
     return w
 
 
-def run_pair(spec, steps, fma=False, dt_scale=0.9, links=True, check_every=None):
+def run_pair(spec, steps, fma=False, dt_scale=0.9, links=True, check_every=None, persistent=True):
+    """persistent=True lets the engine pick the on-chip persistent kernel where it applies (single collision-free
+    body); False forces the streaming kernels; "mixed" alternates between the two from chunk to chunk."""
     lib, b, d = build(spec, fma)
     try:
         eng = EngineBatch([d], fma=fma)
+        eng.set_profiling(False, use_persistent=bool(persistent))
         orc = OracleSim(d)
         dt = float(np.float32(dt_scale * orc.recommended_dt()))
         chunk = check_every or steps
@@ -51,6 +54,8 @@ def run_pair(spec, steps, fma=False, dt_scale=0.9, links=True, check_every=None)
         worst = {}
         while done < steps:
             k = min(chunk, steps - done)
+            if persistent == "mixed":
+                eng.set_profiling(False, use_persistent=(done // chunk) % 2 == 0)
             eng.step(k, dt)
             assert orc.step(k, dt) == k
             done += k
@@ -85,17 +90,37 @@ def test_single_voxel_drop(fma):
 
 
 @pytest.mark.parametrize("fma", [False, True])
+@pytest.mark.parametrize("persistent", [True, False, "mixed"])
 @pytest.mark.parametrize("shape,steps", [((2, 1, 1), 1000), ((3, 3, 3), 1000), ((6, 6, 6), 400)])
-def test_actuated_body(shape, steps, fma):
+def test_actuated_body(shape, steps, fma, persistent):
     spec = cube_spec(shape, seed=11, actuated=True, name="act%dx%dx%d" % shape)
-    run_pair(spec, steps, fma, check_every=100)
+    run_pair(spec, steps, fma, check_every=100, persistent=persistent)
+
+
+def test_persistent_equals_streaming_bitwise():
+    """The on-chip persistent kernel and the streaming kernels run the same arithmetic: identical bits after 700 steps."""
+    spec = cube_spec((7, 6, 5), seed=17, actuated=True, holes=0.1, name="bitwise")
+    lib, b, d = build(spec)
+    try:
+        out = []
+        for use in (True, False):
+            eng = EngineBatch([d])
+            eng.set_profiling(False, use_persistent=use)
+            eng.step(700)
+            out.append(eng.state(0))
+            eng.close()
+        util.assert_bit_equal(out[0], out[1], KIN + LINKF + LINKS + ["link_flags", "vox_flags", "temp", "link_rest_length", "link_strain",
+                                                                      "link_max_strain", "link_stress"], "persistent vs streaming")
+    finally:
+        lib.vx3_builder_destroy(b)
 
 
 @pytest.mark.parametrize("fma", [False, True])
-def test_body_with_holes_and_lift(fma):
+@pytest.mark.parametrize("persistent", [True, False])
+def test_body_with_holes_and_lift(fma, persistent):
     """Ragged lattice (random holes), dropped from 2 voxels up: exercises missing links, free fall, floor contact, friction."""
     spec = cube_spec((5, 4, 3), seed=5, actuated=True, lift=2, holes=0.25, name="ragged")
-    run_pair(spec, 1500, fma, check_every=250)
+    run_pair(spec, 1500, fma, check_every=250, persistent=persistent)
 
 
 def test_passive_large_angle():

@@ -569,6 +569,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     }
     // device-side init at the top of CUDA_Simulation (VX3_SimulationManager.cu:20-24,54-55)
     run_com(b, 0);
+    k_temp_init<<<cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, 0, b->stream>>>(D);
     k_set_dt<<<cdiv(n, 128), 128, 0, b->stream>>>(D, -1.0f);
     for (int s = 0; s < n; s++) {
         double od = b->simc[s].optimal_dt;

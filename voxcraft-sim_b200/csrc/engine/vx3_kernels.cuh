@@ -20,12 +20,22 @@ __device__ __forceinline__ V3 load_pos(const double *__restrict__ pose, int v) {
     const double2 a = s[0];
     return V3(a.x, a.y, s[1].x);
 }
-__device__ __forceinline__ void store_pose(double *pose, int v, const V3 &p, const Q4 &q) {
+// The 8th double of the pose record carries the voxel's temperature AT THE CURRENT SIMULATION TIME (what
+// gpu_update_temperature will set at the start of the next step): the voxel pass computes it once per voxel, the
+// link pass reads it with the pose instead of evaluating sin() for both ends of every link.
+__device__ __forceinline__ void load_pose_t(const double *__restrict__ pose, int v, V3 &p, Q4 &q, float &tempe) {
+    const double2 *s = reinterpret_cast<const double2 *>(pose + 8 * (size_t)v);
+    const double2 a = s[0], b = s[1], c = s[2], d = s[3];
+    p = V3(a.x, a.y, b.x);
+    q = Q4(b.y, c.x, c.y, d.x);
+    tempe = (float)d.y;
+}
+__device__ __forceinline__ void store_pose(double *pose, int v, const V3 &p, const Q4 &q, float tempe_next) {
     double2 *s = reinterpret_cast<double2 *>(pose + 8 * (size_t)v);
     s[0] = make_double2(p.x, p.y);
     s[1] = make_double2(p.z, q.w);
     s[2] = make_double2(q.x, q.y);
-    s[3] = make_double2(q.z, 0.0);
+    s[3] = make_double2(q.z, (double)tempe_next);
 }
 __device__ __forceinline__ V3 load3(const double *__restrict__ a, size_t i) { return V3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
 __device__ __forceinline__ void store3(double *a, size_t i, const V3 &v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
@@ -52,20 +62,18 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_links(Dev D) {
     const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
     L.state &= ~LKS_JUST_CREATED;
     L.rest = D.lrest[g];
+    V3 pN, pP;
+    Q4 qN, qP;
+    float tN, tP; // the ends' temperatures for this step (computed by the voxel pass of the previous step)
+    load_pose_t(D.pose, e.x, pN, qN, tN);
+    load_pose_t(D.pose, e.y, pP, qP, tP);
     if (S.vary_temp && S.temp_period > 0) { // updateRestLength() from either end's setTemperature (VX3_Voxel.cu:107-113)
         const double t = dy.t;
-        const bool actN = thermal_active(S, mN, 0, t), actP = thermal_active(S, mP, 0, t);
-        if (actN || actP) {
-            const float tN = actN ? voxel_temperature(S, t, D.phase[e.x]) : D.tempe[e.x];
-            const float tP = actP ? voxel_temperature(S, t, D.phase[e.y]) : D.tempe[e.y];
+        if (thermal_active(S, mN, 0, t) || thermal_active(S, mP, 0, t)) {
             L.rest = 0.5 * (base_size_axis(mN, tN, axis) + base_size_axis(mP, tP, axis));
             D.lrest[g] = L.rest;
         }
     }
-    V3 pN, pP;
-    Q4 qN, qP;
-    load_pose(D.pose, e.x, pN, qN);
-    load_pose(D.pose, e.y, pP, qP);
     const double *h = D.lhist + 9 * (size_t)g;
     L.pos2 = V3(h[0], h[1], h[2]);
     L.angle1v = V3(h[3], h[4], h[5]);
@@ -97,9 +105,9 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_links(Dev D) {
 }
 
 // ------------------------------------------------------------------ voxels
-__device__ __forceinline__ void prog_vars(const SimC &S, const SimD &dy, double x, double y, double z, double *vars) {
+__device__ __forceinline__ void prog_vars(const SimC &S, const SimD &dy, double t, double x, double y, double z, double *vars) {
     vars[0] = x; vars[1] = y; vars[2] = z;
-    vars[3] = dy.collision_count; vars[4] = dy.t; vars[5] = dy.recent_angle; vars[6] = dy.target_closeness;
+    vars[3] = dy.collision_count; vars[4] = t; vars[5] = dy.recent_angle; vars[6] = dy.target_closeness;
     vars[7] = dy.num_close_pairs; vars[8] = S.nvox;
 }
 __device__ __forceinline__ double eval_slot(const Dev &D, const SimC &S, int slot, const double *vars, double dflt) {
@@ -122,15 +130,17 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_voxels(Dev D) {
     VoxRegs r;
     r.flags = D.vflags[v];
     const VoxMatC &m = D.vmat_tab[D.vmat[v]];
-    float tempe = D.tempe[v];
-    if (thermal_active(S, m, r.flags, t)) {
-        tempe = voxel_temperature(S, t, D.phase[v]);
-        D.tempe[v] = tempe;
+    float tempe;
+    load_pose_t(D.pose, v, r.pos, r.orient, tempe); // this step's temperature (gpu_update_temperature at time t)
+    D.tempe[v] = tempe;
+    // temperature the next step will start with (time t + dt), see store_pose
+    const double tnext = t + dtF;
+    const float tempe_next = thermal_active(S, m, r.flags, tnext) ? voxel_temperature(S, tnext, D.phase[v]) : tempe;
+    if ((r.flags & VXF_REMOVED) || m.fixed) {
+        if (tempe_next != tempe) D.pose[8 * (size_t)v + 7] = (double)tempe_next;
+        return;
     }
-    if (r.flags & VXF_REMOVED) return;
-    if (m.fixed) return;
     D.prevdt[v] = (float)dt;
-    load_pose(D.pose, v, r.pos, r.orient);
     const double *mo = D.mom + 6 * (size_t)v;
     r.linMom = V3(mo[0], mo[1], mo[2]);
     r.angMom = V3(mo[3], mo[4], mo[5]);
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_voxels(Dev D) {
     const bool fixedAll = px && (px->dof & 0x3F) == 0x3F;
     if (S.has_ff && !fixedAll) {
         double vars[9];
-        prog_vars(S, dy, r.pos.x, r.pos.y, r.pos.z, vars);
+        prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
         ff.x = eval_slot(D, S, VX3_PROG_FORCE_X, vars, 0.0);
         ff.y = eval_slot(D, S, VX3_PROG_FORCE_Y, vars, 0.0);
         ff.z = eval_slot(D, S, VX3_PROG_FORCE_Z, vars, 0.0);
@@ -170,13 +180,13 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_voxels(Dev D) {
     // enableAttach = AND of the five attach conditions at the new position (:609-621)
     if (S.has_attach_cond) {
         double vars[9];
-        prog_vars(S, dy, r.pos.x, r.pos.y, r.pos.z, vars);
+        prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
         bool all = true;
         for (int c = 0; c < 5 && all; c++) all = eval_slot(D, S, VX3_PROG_ATTACH_0 + c, vars, 1.0) > 0;
         if (all) r.flags |= VXF_ENABLE_ATTACH;
         else r.flags &= ~VXF_ENABLE_ATTACH;
     }
-    store_pose(D.pose, v, r.pos, r.orient);
+    store_pose(D.pose, v, r.pos, r.orient, tempe_next);
     double *mw = D.mom + 6 * (size_t)v;
     mw[0] = r.linMom.x; mw[1] = r.linMom.y; mw[2] = r.linMom.z;
     mw[3] = r.angMom.x; mw[4] = r.angMom.y; mw[5] = r.angMom.z;
@@ -190,7 +200,7 @@ __device__ __forceinline__ unsigned cell_hash(int sim, int cx, int cy, int cz) {
 __device__ __forceinline__ bool sim_collides(const SimC &S) { return S.enable_collision || S.enable_attach; }
 
 // regenerateSurfaceVoxels (:495-513) + uniform-grid insert (replaces the O(S^2) sweep of gpu_update_attach :833-843).
-// Also stores this step's temperature so the contact phase sees what updateTemperature (:219-235) set.
+// Also publishes this step's temperature (what updateTemperature :219-235 set) for the contact phase.
 __global__ void __launch_bounds__(VX3_BLOCK) k_grid_count(Dev D) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= D.nvox) return;
@@ -200,8 +210,7 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_count(Dev D) {
     int4 vc = make_int4(0, 0, 0, -1);
     if (dy.status == VX3_SIM_RUNNING && !dy.diverged && dy.dt != 0 && sim_collides(S)) {
         int flags = D.vflags[v];
-        const VoxMatC &m = D.vmat_tab[D.vmat[v]];
-        if (thermal_active(S, m, flags, dy.t)) D.tempe[v] = voxel_temperature(S, dy.t, D.phase[v]);
+        D.tempe[v] = (float)D.pose[8 * (size_t)v + 7]; // this step's temperature, for the contact phase
         bool interior = true; // VX3_Voxel::updateSurface (VX3_Voxel.cu:515-524): the bit named SURFACE means interior
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -584,7 +593,7 @@ __device__ __forceinline__ void com_finalize(const Dev &D, const SimC &S, SimD &
 __device__ __forceinline__ bool stop_condition_met(const Dev &D, const SimC &S, const SimD &dy) { // :162-182
     if (S.prog_n[VX3_PROG_STOP] <= 0) return false;
     double vars[9];
-    prog_vars(S, dy, dy.com[0], dy.com[1], dy.com[2], vars);
+    prog_vars(S, dy, dy.t, dy.com[0], dy.com[1], dy.com[2], vars);
     bool ok;
     return mt_eval<VX3_MAX_TOKENS>(D.tokens + S.prog_off[VX3_PROG_STOP], S.prog_n[VX3_PROG_STOP], vars, &ok) > 0;
 }
@@ -682,10 +691,23 @@ __global__ void k_sim_update(Dev D, int mode) {
     if (S.prog_n[VX3_PROG_FITNESS] <= 0) dy.fitness = 0;
     else { // computeFitness (:530-534)
         double vars[9];
-        prog_vars(S, dy, dy.com[0] - dy.com0[0], dy.com[1] - dy.com0[1], dy.com[2] - dy.com0[2], vars);
+        prog_vars(S, dy, dy.t, dy.com[0] - dy.com0[0], dy.com[1] - dy.com0[1], dy.com[2] - dy.com0[2], vars);
         bool ok;
         dy.fitness = mt_eval<VX3_MAX_TOKENS>(D.tokens + S.prog_off[VX3_PROG_FITNESS], S.prog_n[VX3_PROG_FITNESS], vars, &ok);
     }
+}
+
+// temperature at the current time into the pose records (batch creation): gpu_update_temperature of the first step
+__global__ void __launch_bounds__(VX3_BLOCK) k_temp_init(Dev D) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= D.nvox) return;
+    const int sim = D.vsim[v];
+    const SimC &S = D.simc[sim];
+    const VoxMatC &m = D.vmat_tab[D.vmat[v]];
+    const double t = D.simd[sim].t;
+    float tempe = D.tempe[v];
+    if (thermal_active(S, m, D.vflags[v], t)) tempe = voxel_temperature(S, t, D.phase[v]);
+    D.pose[8 * (size_t)v + 7] = (double)tempe;
 }
 
 __global__ void k_set_dt(Dev D, float dt) { // dt < 0: DtFrac * recommendedTimeStep() (:244-254)
