@@ -11,6 +11,9 @@ _cache = {}
 
 
 def engine_path(fma=False):
+    override = os.environ.get("VX3_ENGINE_LIB")  # developer experiments only (A/B builds of the same sources)
+    if override:
+        return override
     return os.path.join(HERE, "lib", "libvx3_b200_fma.so" if fma else "libvx3_b200.so")
 
 
