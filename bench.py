@@ -101,6 +101,9 @@ def build_workload(name, pkg, per_gpu_sims):
     elif name == "c3":
         specs = [W.c3_spec(k) for k in range(per_gpu_sims)]
         label = "config3: batch of %d random 10x10x10 robots per GPU (vx3_node_worker fitness eval)" % per_gpu_sims
+    elif name == "c4":
+        specs = [W.c4_spec()]
+        label = "config4: pile of 512 sticky 4x4x4 bodies, collisions + attach + detach"
     elif name == "c5":
         specs = [W.c5_spec()]
         label = "config5 (one GPU, no decomposition): single 200x200x100 body"

@@ -83,6 +83,14 @@ int vx3_builder_set_external(vx3_builder *b, int voxel_index, const vx3_external
  * references stay valid until the builder is destroyed or built again. */
 const vx3_model_desc *vx3_builder_build(vx3_builder *b);
 
+/* VXA / VXD front end.  Parses the VXA text, applies the VXD overrides (children of <VXD> carrying
+ * replace="VXA.path" replace that subtree of the base VXA, src/Utils/ctool.h:49-57) and returns a builder ready
+ * for vx3_builder_build().  Replaces CVX_Sim::ReadVXA (src/VXA/VX_Sim.cpp:155-294), CVX_Environment::ReadXML
+ * (src/old/VX_Environment.cpp:101-178), CVX_Object::ReadXML (src/VXA/VX_Object.cpp), the VX3 tag reads and
+ * ParseMathTree of readVXD (src/VX3/VX3_SimulationManager.cu:157-376).  NULL on error (vx3_model_last_error). */
+vx3_builder *vx3_vxa_parse(const char *vxa_xml, const char *vxd_xml /* may be NULL */, const char *name /* may be NULL */);
+vx3_builder *vx3_vxa_load(const char *vxa_path, const char *vxd_path /* may be NULL */);
+
 /* Host recommendedTimeStep (src/VX3/VX3_VoxelyzeKernel.cu:184-217) on a flat model. */
 double vx3_model_recommended_dt(const vx3_model_desc *m);
 

@@ -20,9 +20,9 @@ def declared_functions(header):
 def test_library_exports_every_declared_symbol():
     for fma in (False, True):
         lib = C.CDLL(engine_path(fma))
-        for header in ("vx3_abi.h", "vx3_model.h"):
+        for header in ("vx3_abi.h", "vx3_model.h", "vx3_worker.h"):
             names = declared_functions(header)
-            assert len(names) >= 10
+            assert len(names) >= 3
             for n in names:
                 assert hasattr(lib, n), "%s: symbol %s (declared in %s) is not exported" % (engine_path(fma), n, header)
 
@@ -30,6 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_python_lists_match_headers():
     assert sorted(abi.ENGINE_SYMBOLS) == declared_functions("vx3_abi.h")
     assert sorted(abi.MODEL_SYMBOLS) == declared_functions("vx3_model.h")
+    assert sorted(abi.WORKER_SYMBOLS) == declared_functions("vx3_worker.h")
 
 
 def test_struct_sizes_match_the_compiled_headers():

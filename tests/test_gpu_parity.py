@@ -253,6 +253,30 @@ def test_collisions_and_attach(sticky):
         lib.vx3_builder_destroy(b)
 
 
+def test_config4_small_pile():
+    """Config 4 at oracle-checkable size: 2x2x2 grid of 3^3 sticky actuated bodies dropped onto each other
+    (collisions + attach + detach enabled), hashed-grid contacts vs the oracle's all-pairs sweep."""
+    from voxcraft_sim_b200 import workloads as W
+    spec = W.c4_spec(grid=(2, 2, 2), body=3, name="c4small")
+    lib, b, d = build(spec)
+    try:
+        eng = EngineBatch([d])
+        orc = OracleSim(d)
+        total = 0
+        for i in range(8):
+            eng.step(500)
+            orc.step(500, -1.0)
+            total += 500
+            se, so = eng.state(0, link_cap=4096), orc.state()
+            assert se["link_vneg"].shape == so["link_vneg"].shape, "link count differs at step %d" % total
+            for k in ("link_vneg", "link_vpos", "link_axis", "vox_links", "link_flags", "vox_flags"):
+                np.testing.assert_array_equal(se[k], so[k], err_msg="%s at step %d" % (k, total))
+            check_state(se, so, "c4small step %d" % total, kin=1e-8, link=1e-6)
+        assert orc.counts()["attach"] > 0
+    finally:
+        lib.vx3_builder_destroy(b)
+
+
 def test_detach():
     spec = collide_spec(True, detach=True, name="detach")
     lib, b, d = build(spec)

@@ -159,6 +159,10 @@ def declare_model_api(lib):
     lib.vx3_builder_set_external.argtypes = [vp, C.c_int, P(External)]
     lib.vx3_builder_build.argtypes = [vp]
     lib.vx3_builder_build.restype = P(ModelDesc)
+    lib.vx3_vxa_parse.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    lib.vx3_vxa_parse.restype = vp
+    lib.vx3_vxa_load.argtypes = [C.c_char_p, C.c_char_p]
+    lib.vx3_vxa_load.restype = vp
     lib.vx3_model_recommended_dt.argtypes = [P(ModelDesc)]
     lib.vx3_model_recommended_dt.restype = f64
     lib.vx3_model_last_error.restype = C.c_char_p
@@ -194,7 +198,8 @@ def declare_engine_api(lib):
 ENGINE_SYMBOLS = ["vx3_batch_create", "vx3_batch_run", "vx3_batch_step", "vx3_batch_step_dt", "vx3_batch_sync",
                   "vx3_batch_state", "vx3_batch_results", "vx3_batch_positions", "vx3_batch_recommended_dt",
                   "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_last_error", "vx3_abi_version"]
+WORKER_SYMBOLS = ["vx3_worker_run_vxt", "vx3_worker_run_files", "vx3_write_report"]
 MODEL_SYMBOLS = ["vx3_material_params_default", "vx3_env_params_default", "vx3_sim_options_default", "vx3_builder_create",
                  "vx3_builder_destroy", "vx3_builder_add_material", "vx3_builder_set_env", "vx3_builder_set_options",
                  "vx3_builder_set_name", "vx3_builder_set_program", "vx3_builder_set_structure", "vx3_builder_set_external",
-                 "vx3_builder_build", "vx3_model_recommended_dt", "vx3_model_last_error"]
+                 "vx3_builder_build", "vx3_vxa_parse", "vx3_vxa_load", "vx3_model_recommended_dt", "vx3_model_last_error"]

@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 INCLUDE = os.path.join(ROOT, "include")
 
 ENGINE_CU = ["engine/vx3_engine.cu"]
-HOST_CPP = ["host/vx3_materials.cpp", "host/vx3_builder.cpp", "host/vx3_vxa.cpp", "host/vx3_history.cpp", "host/vx3_manager.cpp"]
+HOST_CPP = ["host/vx3_materials.cpp", "host/vx3_builder.cpp", "host/vx3_xml.cpp", "host/vx3_vxa.cpp", "host/vx3_worker.cpp"]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -76,6 +76,22 @@ def build_lib(fma=False, force=False, verbose=False):
     return out
 
 
+def build_exes(force=False, verbose=False):
+    """vx3_node_worker and voxcraft-sim (drop-in executables) next to the library; rpath = $ORIGIN."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    outs = []
+    for name, src, link in (("vx3_node_worker", "exe/vx3_node_worker.cpp", True), ("voxcraft-sim", "exe/voxcraft-sim.cpp", False)):
+        out = os.path.join(LIBDIR, name)
+        srcp = os.path.join(CSRC, src)
+        if force or _newer(out, [srcp, os.path.join(LIBDIR, "libvx3_b200.so")] + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]):
+            cmd = ["g++", "-std=c++17", "-O2", "-I", INCLUDE, srcp, "-o", out]
+            if link:
+                cmd += ["-L", LIBDIR, "-lvx3_b200", "-Wl,-rpath,$ORIGIN"]
+            _run(cmd, verbose)
+        outs.append(out)
+    return outs
+
+
 def build_oracle(force=False, verbose=False):
     """Builds the CHECKERS (tests/bench cpu_baseline only): oracle restatement and, when the reference
     tree is present (this container), the unmodified reference CPU library under oracle/_ref."""
@@ -94,6 +110,7 @@ def build_oracle(force=False, verbose=False):
 def build_all(force=False, verbose=False):
     a = build_lib(fma=False, force=force, verbose=verbose)
     b = build_lib(fma=True, force=force, verbose=verbose)
+    build_exes(force=force, verbose=verbose)
     return a, b
 
 

@@ -8,6 +8,13 @@
 namespace vx3 {
 
 #define VX3_BLOCK 256
+// occupancy targets of the two streaming hot kernels (CTAs of VX3_BLOCK threads per SM); tuned on B200, see DESIGN.md §4
+#ifndef VX3_LINKS_MIN_CTAS
+#define VX3_LINKS_MIN_CTAS 2
+#endif
+#ifndef VX3_VOXELS_MIN_CTAS
+#define VX3_VOXELS_MIN_CTAS 2
+#endif
 
 __device__ __forceinline__ void load_pose(const double *__restrict__ pose, int v, V3 &p, Q4 &q) {
     const double2 *s = reinterpret_cast<const double2 *>(pose + 8 * (size_t)v);
@@ -43,30 +50,49 @@ __device__ __forceinline__ void store3(double *a, size_t i, const V3 &v) { a[3 *
 // ------------------------------------------------------------------ links
 // gpu_update_links (VX3_VoxelyzeKernel.cu:566-581) with the temperature-driven rest-length refresh of
 // gpu_update_temperature (:625-650) folded in.
-__global__ void __launch_bounds__(VX3_BLOCK) k_links(Dev D) {
+__global__ void __launch_bounds__(VX3_BLOCK, VX3_LINKS_MIN_CTAS) k_links(Dev D) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= D.nlinkslots) return;
+    // Loads are issued in dependency LEVELS, each level before any branch that could separate it from the next:
+    // the kernel is latency bound (ncu: long-scoreboard stalls dominate), so the number of serialised DRAM round
+    // trips matters more than a few loads wasted on skipped links.
+    // ---- level 1: everything indexed by the link slot ----
     const int2 e = D.lends[g];
-    if (e.x < 0) return;
     LinkRegs L;
     L.state = D.lstate[g];
-    if (L.state & (LKS_DETACHED | LKS_REMOVED)) return;
-    const int sim = D.vsim[e.x];
-    const SimC &S = D.simc[sim];
-    SimD &dy = D.simd[sim];
-    if (dy.status != VX3_SIM_RUNNING) return;
-    const float dt = dy.dt;
-    if (dt == 0) return;
-    const VoxMatC &mN = D.vmat_tab[D.vmat[e.x]], &mP = D.vmat_tab[D.vmat[e.y]];
-    if (mN.fixed && mP.fixed) return;
-    const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
-    L.state &= ~LKS_JUST_CREATED;
+    const int lmi = D.lmat[g];
+    const double *h = D.lhist + 9 * (size_t)g;
+    L.pos2 = V3(h[0], h[1], h[2]);
+    L.angle1v = V3(h[3], h[4], h[5]);
+    L.angle2v = V3(h[6], h[7], h[8]);
+    const float4 sn = D.lstrain[g];
+    const float2 ar = D.larea[g];
     L.rest = D.lrest[g];
+    if (e.x < 0) return;
+    // ---- level 2: everything indexed by the two end voxels (+ the link material) ----
     V3 pN, pP;
     Q4 qN, qP;
     float tN, tP; // the ends' temperatures for this step (computed by the voxel pass of the previous step)
     load_pose_t(D.pose, e.x, pN, qN, tN);
     load_pose_t(D.pose, e.y, pP, qP, tP);
+    const int vmN = D.vmat[e.x], vmP = D.vmat[e.y];
+    const float pdN = D.prevdt[e.x], pdP = D.prevdt[e.y];
+    const int sim = D.nsims == 1 ? 0 : D.vsim[e.x];
+    const LinkMatC &lm = D.lmat_tab[lmi];
+    // ---- level 3: small tables (L1/L2 resident) ----
+    const SimC &S = D.simc[sim];
+    SimD &dy = D.simd[sim];
+    const VoxMatC &mN = D.vmat_tab[vmN], &mP = D.vmat_tab[vmP];
+    const int status = dy.status;
+    const float dt = dy.dt;
+    const bool fixedBoth = mN.fixed && mP.fixed;
+    const float numN = mN.dampMultNum, numP = mP.dampMultNum;
+    if (L.state & (LKS_DETACHED | LKS_REMOVED)) return;
+    if (status != VX3_SIM_RUNNING || dt == 0 || fixedBoth) return;
+    const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+    L.state &= ~LKS_JUST_CREATED;
+    L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
+    L.area = ar.x; L.tsum = ar.y;
     if (S.vary_temp && S.temp_period > 0) { // updateRestLength() from either end's setTemperature (VX3_Voxel.cu:107-113)
         const double t = dy.t;
         if (thermal_active(S, mN, 0, t) || thermal_active(S, mP, 0, t)) {
@@ -74,17 +100,8 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_links(Dev D) {
             D.lrest[g] = L.rest;
         }
     }
-    const double *h = D.lhist + 9 * (size_t)g;
-    L.pos2 = V3(h[0], h[1], h[2]);
-    L.angle1v = V3(h[3], h[4], h[5]);
-    L.angle2v = V3(h[6], h[7], h[8]);
-    const float4 sn = D.lstrain[g];
-    L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
-    const float2 ar = D.larea[g];
-    L.area = ar.x; L.tsum = ar.y;
-    const LinkMatC &lm = D.lmat_tab[D.lmat[g]];
     // dampingMultiplier() = 2*_sqrtMass*zetaInternal/previousDt (float)
-    const float dmN = mN.dampMultNum / D.prevdt[e.x], dmP = mP.dampMultNum / D.prevdt[e.y];
+    const float dmN = numN / pdN, dmP = numP / pdP;
     LinkOut o;
     link_update_forces(L, lm, D.strain_pool, D.stress_pool, pN, qN, pP, qP, dmN, dmP, o);
     double *hw = D.lhist + 9 * (size_t)g;
@@ -117,42 +134,55 @@ __device__ __forceinline__ double eval_slot(const Dev &D, const SimC &S, int slo
 }
 
 // gpu_update_voxels (VX3_VoxelyzeKernel.cu:582-623) -> VX3_Voxel::timeStep
-__global__ void __launch_bounds__(VX3_BLOCK) k_voxels(Dev D) {
+__global__ void __launch_bounds__(VX3_BLOCK, VX3_VOXELS_MIN_CTAS) k_voxels(Dev D) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= D.nvox) return;
-    const int sim = D.vsim[v];
+    // loads in dependency levels (see k_links)
+    // ---- level 1: everything indexed by the voxel ----
+    VoxRegs r;
+    float tempe;
+    load_pose_t(D.pose, v, r.pos, r.orient, tempe); // this step's temperature (gpu_update_temperature at time t)
+    r.flags = D.vflags[v];
+    const int vmi = D.vmat[v];
+    const int sim = D.nsims == 1 ? 0 : D.vsim[v];
+    const double *mo = D.mom + 6 * (size_t)v;
+    r.linMom = V3(mo[0], mo[1], mo[2]);
+    r.angMom = V3(mo[3], mo[4], mo[5]);
+    int vl[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) vl[i] = D.vlinks[6 * (size_t)v + i];
+    const double phase = D.phase[v];
+    // ---- level 2: link end forces, tables ----
+    double2 fa[6], fb[6], fc[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (vl[i] >= 0) {
+            const double2 *f = reinterpret_cast<const double2 *>(D.lforce + 12 * (size_t)vl[i] + ((i & 1) ? 6 : 0));
+            fa[i] = f[0]; fb[i] = f[1]; fc[i] = f[2];
+        }
+    }
     const SimC &S = D.simc[sim];
     const SimD &dy = D.simd[sim];
+    const VoxMatC &m = D.vmat_tab[vmi];
     if (dy.status != VX3_SIM_RUNNING || dy.diverged) return;
     const float dtF = dy.dt;
     if (dtF == 0) return;
     const double dt = dtF, t = dy.t;
-    VoxRegs r;
-    r.flags = D.vflags[v];
-    const VoxMatC &m = D.vmat_tab[D.vmat[v]];
-    float tempe;
-    load_pose_t(D.pose, v, r.pos, r.orient, tempe); // this step's temperature (gpu_update_temperature at time t)
     D.tempe[v] = tempe;
     // temperature the next step will start with (time t + dt), see store_pose
     const double tnext = t + dtF;
-    const float tempe_next = thermal_active(S, m, r.flags, tnext) ? voxel_temperature(S, tnext, D.phase[v]) : tempe;
+    const float tempe_next = thermal_active(S, m, r.flags, tnext) ? voxel_temperature(S, tnext, phase) : tempe;
     if ((r.flags & VXF_REMOVED) || m.fixed) {
         if (tempe_next != tempe) D.pose[8 * (size_t)v + 7] = (double)tempe_next;
         return;
     }
     D.prevdt[v] = (float)dt;
-    const double *mo = D.mom + 6 * (size_t)v;
-    r.linMom = V3(mo[0], mo[1], mo[2]);
-    r.angMom = V3(mo[3], mo[4], mo[5]);
     V3 F(0, 0, 0), M(0, 0, 0);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        const int li = D.vlinks[6 * (size_t)v + i];
-        if (li >= 0) {
-            const double2 *f = reinterpret_cast<const double2 *>(D.lforce + 12 * (size_t)li + ((i & 1) ? 6 : 0));
-            const double2 a = f[0], b = f[1], c = f[2];
-            F += V3(a.x, a.y, b.x);
-            M += V3(b.y, c.x, c.y);
+        if (vl[i] >= 0) {
+            F += V3(fa[i].x, fa[i].y, fb[i].x);
+            M += V3(fb[i].y, fc[i].x, fc[i].y);
         }
     }
     V3 contact(0, 0, 0);
@@ -248,14 +278,21 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_surface(Dev D) {
     if (nf != flags) D.vflags[v] = nf;
 }
 
-// exclusive scan of the bucket counts (single CTA), resets the counters for the next step
+// exclusive scan of the bucket counts (single CTA, int4-vectorised), resets the counters for the next step
 __global__ void __launch_bounds__(1024) k_grid_scan(Dev D) {
     __shared__ int part[1024];
-    const int H = D.hmask + 1;
-    const int per = (H + 1023) / 1024;
-    const int b0 = threadIdx.x * per, b1 = min(H, b0 + per);
+    const int H = D.hmask + 1;            // power of two >= 1024
+    const int per = H / 1024;             // buckets per thread (multiple of 4 when H >= 4096)
+    const int b0 = threadIdx.x * per;
     int s = 0;
-    for (int i = b0; i < b1; i++) s += D.cell_cnt[i];
+    if (per >= 4) {
+        const int4 *c4 = reinterpret_cast<const int4 *>(D.cell_cnt + b0);
+        for (int i = 0; i < per / 4; i++) {
+            const int4 c = c4[i];
+            s += c.x + c.y + c.z + c.w;
+        }
+    } else
+        for (int i = 0; i < per; i++) s += D.cell_cnt[b0 + i];
     part[threadIdx.x] = s;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) { // Hillis-Steele inclusive scan
@@ -265,13 +302,27 @@ __global__ void __launch_bounds__(1024) k_grid_scan(Dev D) {
         __syncthreads();
     }
     int run = part[threadIdx.x] - s;
-    for (int i = b0; i < b1; i++) {
-        const int c = D.cell_cnt[i];
-        D.cell_start[i] = run;
-        D.cell_cursor[i] = run;
-        D.cell_cnt[i] = 0;
-        run += c;
-    }
+    if (per >= 4) {
+        int4 *c4 = reinterpret_cast<int4 *>(D.cell_cnt + b0);
+        int4 *s4 = reinterpret_cast<int4 *>(D.cell_start + b0);
+        int4 *u4 = reinterpret_cast<int4 *>(D.cell_cursor + b0);
+        for (int i = 0; i < per / 4; i++) {
+            const int4 c = c4[i];
+            int4 o;
+            o.x = run; o.y = o.x + c.x; o.z = o.y + c.y; o.w = o.z + c.z;
+            run = o.w + c.w;
+            s4[i] = o;
+            u4[i] = o;
+            c4[i] = make_int4(0, 0, 0, 0);
+        }
+    } else
+        for (int i = 0; i < per; i++) {
+            const int c = D.cell_cnt[b0 + i];
+            D.cell_start[b0 + i] = run;
+            D.cell_cursor[b0 + i] = run;
+            D.cell_cnt[b0 + i] = 0;
+            run += c;
+        }
     if (threadIdx.x == 1023) D.cell_start[H] = part[1023];
     if (threadIdx.x == 0) *D.cand_count = 0;
 }

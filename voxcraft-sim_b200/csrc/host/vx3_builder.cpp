@@ -15,6 +15,7 @@ using namespace vx3;
 
 static thread_local std::string g_model_err;
 extern "C" const char *vx3_model_last_error(void) { return g_model_err.c_str(); }
+void vx3_model_set_error(const std::string &msg) { g_model_err = msg; }
 
 struct vx3_builder {
     double latDim = 0.001;

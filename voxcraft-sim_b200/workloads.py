@@ -114,7 +114,7 @@ def c4_spec(grid=(8, 8, 8), body=4, name="c4_pile"):
     bodies horizontally and 2 vertically, dropped onto the floor; collisions + attach + detach."""
     gx, gy, gz = grid
     spec = ModelSpec(0.01, name)
-    spec.add_material(name="S", mat_model=1, elastic_mod=1e6, fail_stress=4e4, density=1e3, cte=0.01, u_static=1.0, u_dynamic=0.8,
+    spec.add_material(name="S", mat_model=1, elastic_mod=1e6, fail_stress=3.5e5, density=1e3, cte=0.01, u_static=1.0, u_dynamic=0.8,
                       sticky=1, red=1.0, green=0.6, blue=0.1)
     _common(spec, collisions=1)
     spec.set_options(enable_collision=1, enable_attach=1, enable_detach=1)
