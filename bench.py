@@ -119,9 +119,12 @@ def reference_cpu_throughput(spec, target_seconds, omp=True):
     use_omp = omp and os.path.exists(util.REF_OMP_SO)
     if not os.path.exists(util.REF_SO) and not use_omp:
         return None
-    cores = os.cpu_count() or 1
-    if use_omp:
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    if use_omp:  # torchrun presets OMP_NUM_THREADS=1: the CPU arm uses every host core it may run on
+        os.environ["OMP_NUM_THREADS"] = str(cores)
     sim = util.RefSim(spec, omp=use_omp)
     dt = float(__import__("numpy").float32(0.9 * sim.recommended_dt()))
     sim.step(10, dt)

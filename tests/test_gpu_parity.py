@@ -296,6 +296,33 @@ def test_detach():
         lib.vx3_builder_destroy(b)
 
 
+def test_secondary_experiment_removal_and_reinit():
+    """SecondaryExperiment: voxels of a material leave the simulation after a set time (with their links), and the
+    initial positions / initial CoM are re-initialised once (VX3_VoxelyzeKernel.cu:336-399)."""
+    spec = cube_spec((4, 3, 3), seed=29, actuated=True, name="secondary")
+    spec.materials[1]["remove_after_s"] = 0.008
+    spec.set_options(secondary_experiment=1, reinit_initial_position_after_s=0.004)
+    spec.set_env(temp_period=0.002)  # CoM sampled often, so the re-initialised CoM is not the initial one
+    lib, b, d = build(spec)
+    try:
+        eng = EngineBatch([d])
+        orc = OracleSim(d)
+        for i in range(6):
+            eng.step(100)
+            orc.step(100, -1.0)
+            se, so = eng.state(0), orc.state()
+            for k in ("vox_links", "link_flags", "vox_flags"):
+                np.testing.assert_array_equal(se[k], so[k], err_msg="%s chunk %d" % (k, i))
+            check_state(se, so, "secondary chunk %d" % i)
+            re, ro = eng.results()[0], orc.result()
+            np.testing.assert_allclose(list(re.initial_com), list(ro.initial_com), rtol=1e-12, atol=1e-18)
+            np.testing.assert_allclose(re.total_distance_of_all_voxels, ro.total_distance_of_all_voxels, rtol=1e-9, atol=1e-15)
+        assert (so["link_flags"] & abi.LINKSTATE_REMOVED).any(), "scenario must remove links"
+        assert list(ro.initial_com) != [0.0, 0.0, 0.0]
+    finally:
+        lib.vx3_builder_destroy(b)
+
+
 def test_no_device_side_cpu_fallback_symbols():
     """The product library must not contain the oracle: its only physics lives in CUDA kernels."""
     lib = util.load_engine()

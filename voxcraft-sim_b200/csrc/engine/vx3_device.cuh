@@ -73,6 +73,8 @@ struct SimC {
     int32_t prog_off[VX3_PROG_COUNT], prog_n[VX3_PROG_COUNT];
     int32_t tgt_off, ntgt;
     int32_t chunk_off, nchunks; // CoM reduction chunks
+    int32_t secondary_experiment, _pad0;
+    double reinit_after; // ReinitializeInitialPositionAfterThisManySeconds
     double temp_amp, temp_period;
     double vox_size, pair_radius; // MaxDistInVoxelLengthsToCountAsPair * voxSize (0 = closeness off)
     double cell_inv;              // 1 / collision grid cell edge
@@ -97,7 +99,8 @@ struct SimD {
     double com[3], com_hist[2][3], com0[3];
     double recent_angle, target_closeness, fitness;
     double total_dist;
-    int32_t n_measured, _pad2;
+    int32_t n_measured;
+    int32_t initpos_reinitialized; // InitialPositionReinitialized
 };
 
 struct Chunk { int32_t sim, vstart, vcount, _pad; };

@@ -42,9 +42,9 @@ extern "C" size_t vx3_abi_sizeof(const char *name) {
 }
 
 // ------------------------------------------------------------------ per-kernel timing (bench hook)
-enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_COM, KC_TAIL, KC_PERSISTENT, KC_COUNT };
+enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_COM, KC_TAIL, KC_PERSISTENT, KC_COUNT };
 static const char *const kKernelNames[KC_COUNT] = {"k_links", "k_voxels", "k_grid_count", "k_grid_scan", "k_grid_fill", "k_contact", "k_resolve",
-                                                   "k_detach", "k_surface", "k_com_partial", "k_tail", "k_persistent"};
+                                                   "k_detach", "k_surface", "k_secondary", "k_com_partial", "k_tail", "k_persistent"};
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> ev; // pairs
@@ -94,7 +94,7 @@ struct vx3_batch {
     std::vector<vx3_sim_options> opts;
     std::vector<std::vector<vx3_voxel_material>> h_vmats; // per sim host copy (data pointers cleared) for the history writer
     std::vector<LinkMatC> h_lmat_tab;
-    bool any_collide = false, any_sticky = false, any_detach = false;
+    bool any_collide = false, any_sticky = false, any_detach = false, any_secondary = false;
     long long hsteps = 0; // doTimeStep calls issued so far (all running simulations advance together)
     std::vector<float> hdt; // per-sim dt in use
     double last_ms = 0;
@@ -189,7 +189,6 @@ static int validate_model(const vx3_model_desc &m, int idx) {
     for (int i = 0; i < 6 * m.n_voxels; i++)
         if (m.vox_links[i] >= m.n_links) return bad("voxel link slot out of range");
     if (m.opt.enable_signals) return bad("EnableSignals is not supported by this engine yet");
-    if (m.opt.secondary_experiment) return bad("SecondaryExperiment is not supported by this engine yet");
     for (int s = 0; s < VX3_PROG_COUNT; s++) {
         if (m.prog[s].n < 0 || m.prog[s].n > VX3_MAX_TOKENS) return bad("token program too long");
         if (m.prog[s].n > 0 && !m.prog[s].tok) return bad("token program pointer missing");
@@ -288,6 +287,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         b->any_collide |= collide;
         b->any_sticky |= collide && sticky;
         b->any_detach |= m.opt.enable_detach != 0;
+        b->any_secondary |= m.opt.secondary_experiment != 0;
     }
 
     std::vector<double> pose(nvox * 8, 0.0), mom(nvox * 6, 0.0), phase(nvox, 0.0), initpos(nvox * 3);
@@ -405,6 +405,8 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.enable_detach = m.opt.enable_detach != 0;
         S.enable_cilia = m.opt.enable_cilia != 0;
         S.safety_guard = m.opt.safety_guard;
+        S.secondary_experiment = m.opt.secondary_experiment != 0;
+        S.reinit_after = m.opt.reinit_initial_position_after_s;
         S.temp_amp = m.opt.temp_amplitude;
         S.temp_period = m.opt.temp_period;
         S.vox_size = m.opt.vox_size;
@@ -576,7 +578,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         if (od < 1e-10) od = 1e-10;
         b->hdt[s] = (float)(b->simc[s].dt_frac * od);
     }
-    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach, any_cilia, prop);
+    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary, any_cilia, prop, lends, vlinks);
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaGetLastError());
     *out = b;
@@ -651,12 +653,13 @@ static void launch_step(vx3_batch *b, bool check_stop) {
         LAUNCH(KC_GRID_FILL, k_grid_fill, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
         LAUNCH(KC_CONTACT, k_contact, cdiv(D.nvox, 128), 128, D);
         if (b->any_sticky) LAUNCH(KC_RESOLVE, k_resolve, 1, 1024, D);
-    } else if (b->any_detach) { // keep the surface flags current (regenerateSurfaceVoxels after a detach)
+    } else if (b->any_detach || b->any_secondary) { // keep the surface flags current (regenerateSurfaceVoxels after a detach / removal)
         LAUNCH(KC_SURFACE, k_surface, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     }
     if (b->any_detach && D.nlinkslots > 0) LAUNCH(KC_DETACH, k_detach, cdiv(D.nlinkslots, VX3_BLOCK), VX3_BLOCK, D);
     LAUNCH(KC_VOXELS, k_voxels, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     const bool com = com_step(b, b->hsteps + 1);
+    if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
     LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, com ? 1 : 0, check_stop ? 1 : 0);
     b->hsteps++;

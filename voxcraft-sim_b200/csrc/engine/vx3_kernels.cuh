@@ -601,6 +601,39 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_detach(Dev D) {
     atomicAdd(&dy.detach_events, 1);
 }
 
+// SecondaryExperiment (VX3_VoxelyzeKernel.cu:336-350): removeVoxels (:365-399) per voxel — a voxel whose material's
+// RemoveFromSimulationAfterThisManySeconds has passed is marked removed together with its links, and both ends'
+// slots are cleared — and the one-time re-initialisation of the initial positions (saveInitialPosition).
+// Runs after the voxel pass, before k_tail (which still holds the step's currentTime).
+__global__ void __launch_bounds__(VX3_BLOCK) k_secondary(Dev D) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= D.nvox) return;
+    const int sim = D.nsims == 1 ? 0 : D.vsim[v];
+    const SimC &S = D.simc[sim];
+    const SimD &dy = D.simd[sim];
+    if (!S.secondary_experiment || dy.status != VX3_SIM_RUNNING || dy.diverged || dy.dt == 0) return;
+    const double t = dy.t;
+    const VoxMatC &m = D.vmat_tab[D.vmat[v]];
+    const int flags = D.vflags[v];
+    if (!(flags & VXF_REMOVED) && m.remove_after > 0 && m.remove_after < t) {
+        D.vflags[v] = flags | VXF_REMOVED;
+        for (int k = 0; k < 6; k++) {
+            const int li = D.vlinks[6 * (size_t)v + k];
+            if (li < 0) continue;
+            D.lstate[li] |= LKS_REMOVED; // (a neighbour removed in the same step sets the same bit: benign)
+            const int2 e = D.lends[li];
+            const int nb = (e.x == v) ? e.y : e.x;
+            for (int q = 0; q < 6; q++)
+                if (D.vlinks[6 * (size_t)nb + q] == li) {
+                    D.vlinks[6 * (size_t)nb + q] = -1;
+                    break;
+                }
+            D.vlinks[6 * (size_t)v + k] = -1;
+        }
+    }
+    if (!dy.initpos_reinitialized && S.reinit_after < t) store3(D.initpos, v, load_pos(D.pose, v)); // saveInitialPosition()
+}
+
 // ------------------------------------------------------------------ reductions
 // updateCurrentCenterOfMass (:477-493) stage 1 + the per-voxel sums of collectResults
 // (VX3_SimulationManager.cu:455-466): one CTA per chunk of one simulation's voxels, fixed-order tree.
@@ -718,6 +751,10 @@ __global__ void __launch_bounds__(128) k_tail(Dev D, int com_ready, int check_st
         }
     }
     if (threadIdx.x == 0) {
+        if (S.secondary_experiment && !dy.initpos_reinitialized && S.reinit_after < dy.t) { // :344-348
+            dy.initpos_reinitialized = 1;
+            for (int k = 0; k < 3; k++) dy.com0[k] = dy.com[k]; // InitializeCenterOfMass()
+        }
         dy.t += dtF;
         if (check_stop && stop_condition_met(D, S, dy)) dy.status = VX3_SIM_STOPPED;
     }

@@ -30,6 +30,18 @@ struct PersistentPlan {
     int links_per_cta = 0, vox_per_cta = 0;
     unsigned int *barrier = nullptr; // [0] arrival counter, [1] divergence flag, [4..] phase cycle counters (debug)
     bool timing = false;
+    // point-to-point phase flags (replace the two grid-wide barriers): CTA c waits only for the CTAs that own the
+    // voxels its links touch / the links its voxels touch
+    bool p2p = false;
+    unsigned int *flags = nullptr; // [2][grid][32]: link phases done, voxel phases done (one 128-B line per counter)
+    int *deps = nullptr;           // [2][grid][VX3_PERSIST_MAX_DEPS]: producers of the link phase / of the voxel phase
+    int *ndeps = nullptr;          // [2][grid]
+};
+
+#define VX3_PERSIST_MAX_DEPS 32
+struct P2P {
+    unsigned int *flags;
+    const int *deps, *ndeps;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
@@ -63,9 +75,29 @@ __device__ __forceinline__ void grid_wait(const unsigned int *counter, unsigned 
     __syncthreads();
 }
 
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// publish "this CTA finished its phase number `value`": every thread's exchange stores precede the release store
+__device__ __forceinline__ void p2p_publish(unsigned int *flag, unsigned int value) {
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_u32(flag, value);
+}
+// wait until every producer CTA of my next phase has published `target`; returns the divergence flag (uniform)
+__device__ __forceinline__ unsigned int p2p_wait(const unsigned int *flags, int my_dep, unsigned int target, const unsigned int *divflag, int *s_div) {
+    if (my_dep >= 0) {
+        const unsigned int *f = flags + 32 * (size_t)my_dep;
+        while (ld_acquire_u32(f) < target) {}
+    }
+    if (threadIdx.x == 0) *s_div = (int)ld_relaxed_u32(divflag);
+    __syncthreads();
+    return (unsigned int)*s_div;
+}
+
 __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1)
-k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox_per_cta, unsigned int *bar, int timing) {
+k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox_per_cta, unsigned int *bar, int timing, P2P p2p) {
     __shared__ int s_stop;
+    __shared__ int s_div;
     __shared__ SimC sS; // per-simulation constants on chip: global loads would miss L1 after every barrier's fence
     for (int i = threadIdx.x; i < (int)(sizeof(SimC) / 4); i += blockDim.x) reinterpret_cast<int *>(&sS)[i] = reinterpret_cast<const int *>(&D.simc[0])[i];
     __syncthreads();
@@ -168,6 +200,19 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
     unsigned int phase_no = 0; // barriers passed
     long long done = 0;
     int status = VX3_SIM_RUNNING;
+    // point-to-point mode: thread k polls the k-th producer CTA of each phase
+    const bool use_p2p = p2p.flags != nullptr;
+    int dep_link = -1, dep_vox = -1; // producer (voxel-phase CTA) for my link phase / (link-phase CTA) for my voxel phase
+    unsigned int *my_lflag = nullptr, *my_vflag = nullptr;
+    const unsigned int *lflags = nullptr, *vflags = nullptr;
+    if (use_p2p) {
+        lflags = p2p.flags;
+        vflags = p2p.flags + 32 * (size_t)G;
+        my_lflag = p2p.flags + 32 * (size_t)blockIdx.x;
+        my_vflag = p2p.flags + 32 * (size_t)(G + blockIdx.x);
+        if ((int)threadIdx.x < p2p.ndeps[blockIdx.x]) dep_link = p2p.deps[(size_t)blockIdx.x * VX3_PERSIST_MAX_DEPS + threadIdx.x];
+        if ((int)threadIdx.x < p2p.ndeps[G + blockIdx.x]) dep_vox = p2p.deps[(size_t)(G + blockIdx.x) * VX3_PERSIST_MAX_DEPS + threadIdx.x];
+    }
 
     if (timing) c0 = clock64();
     for (long long s = 0; s < nsteps; s++) {
@@ -201,16 +246,22 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
             if (intP) pdP = dtF;
         }
         TICK(0);
-        grid_arrive(bar);
+        if (use_p2p) p2p_publish(my_lflag, (unsigned int)(s + 1));
+        else grid_arrive(bar);
         // --- while the arrivals propagate: the temperature the NEXT step starts with (gpu_update_temperature at t+dt) ---
         if (v >= 0) {
             tempe = tempe_next;
             if (vthermal && !(vm.thermal_on_after > t + dtF)) tempe_next = voxel_temperature(S, t + dtF, phase);
         }
         TICK(1);
-        grid_wait(bar, ++phase_no * G);
+        unsigned int div;
+        if (use_p2p) div = p2p_wait(lflags, dep_vox, (unsigned int)(s + 1), &bar[1], &s_div);
+        else {
+            grid_wait(bar, ++phase_no * G);
+            div = ld_relaxed_u32(&bar[1]);
+        }
         TICK(2);
-        if (ld_relaxed_u32(&bar[1])) { // a link diverged in this step: doTimeStep returns false before the voxel pass
+        if (div) { // a link diverged in this step: doTimeStep returns false before the voxel pass
             status = VX3_SIM_DIVERGED;
             done = s + 1;
             break;
@@ -249,7 +300,8 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
         t += dtF; // currentTime += dt (:352)
         done = s + 1;
         TICK(3);
-        grid_arrive(bar);
+        if (use_p2p) p2p_publish(my_vflag, (unsigned int)(s + 1));
+        else grid_arrive(bar);
         // --- while the arrivals propagate: the stop condition for the next step ---
         if (check_stop && threadIdx.x == 0) {
             s_stop = 0;
@@ -260,7 +312,13 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
                 s_stop = mt_eval<VX3_MAX_TOKENS>(D.tokens + S.prog_off[VX3_PROG_STOP], S.prog_n[VX3_PROG_STOP], vars, &ok) > 0;
             }
         }
-        grid_wait(bar, ++phase_no * G);
+        if (use_p2p) {
+            if (p2p_wait(vflags, dep_link, (unsigned int)(s + 1), &bar[1], &s_div)) { // someone diverged meanwhile
+                status = VX3_SIM_DIVERGED;
+                break;
+            }
+        } else
+            grid_wait(bar, ++phase_no * G);
         TICK(4);
         if (check_stop && s_stop) { // identical in every CTA: CoM, angle, ... only change on the streaming path's sampling steps
             status = VX3_SIM_STOPPED;
@@ -268,6 +326,13 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
         }
     }
 
+    if (use_p2p && status == VX3_SIM_DIVERGED) { // CTAs may leave at different steps: never let a neighbour wait for me
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st_release_u32(my_lflag, 0xFFFFFFFFu);
+            st_release_u32(my_vflag, 0xFFFFFFFFu);
+        }
+    }
     // ---- write the register-resident state back ----
     if (g >= 0) {
         double *hw = D.lhist + 9 * (size_t)g;
@@ -302,12 +367,17 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
 // host side ---------------------------------------------------------------------------------------------------
 inline void persistent_free(PersistentPlan &p) {
     if (p.barrier) cudaFree(p.barrier);
+    if (p.flags) cudaFree(p.flags);
+    if (p.deps) cudaFree(p.deps);
+    if (p.ndeps) cudaFree(p.ndeps);
     p.barrier = nullptr;
+    p.flags = nullptr;
+    p.deps = p.ndeps = nullptr;
     p.ok = false;
 }
 
 inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bool any_collide, bool any_detach, bool any_cilia,
-                            const cudaDeviceProp &prop) {
+                            const cudaDeviceProp &prop, const std::vector<int2> &lends, const std::vector<int32_t> &vlinks) {
     p.ok = false;
     if (simc.size() != 1 || any_collide || any_detach || any_cilia) return;
     if (!prop.cooperativeLaunch) return;
@@ -336,6 +406,46 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     p.links_per_cta = lpc;
     p.vox_per_cta = vpc;
     p.ok = true;
+    // ---- producer lists for the point-to-point phase flags ----
+    p.p2p = false;
+    if (getenv("VX3_PERSIST_GLOBAL_BARRIER")) return;
+    std::vector<int> deps(2 * (size_t)G * VX3_PERSIST_MAX_DEPS, -1), ndeps(2 * (size_t)G, 0);
+    auto add = [&](int which, int cta, int producer) -> bool {
+        if (producer == cta) return true; // own phases are ordered by program order
+        int *d = &deps[((size_t)which * G + cta) * VX3_PERSIST_MAX_DEPS];
+        int &n = ndeps[(size_t)which * G + cta];
+        for (int k = 0; k < n; k++)
+            if (d[k] == producer) return true;
+        if (n >= VX3_PERSIST_MAX_DEPS || n >= T) return false;
+        d[n++] = producer;
+        return true;
+    };
+    bool fits = true;
+    for (int g = 0; g < L && fits; g++) { // link phase of CTA g/lpc reads the poses owned by the voxel CTAs of its ends
+        const int2 e = lends[simc[0].loff + g];
+        if (e.x < 0) continue;
+        fits = add(0, g / lpc, (e.x - simc[0].voff) / vpc) && add(0, g / lpc, (e.y - simc[0].voff) / vpc);
+    }
+    for (int v = 0; v < V && fits; v++) // voxel phase of CTA v/vpc reads the forces owned by the link CTAs of its links
+        for (int i = 0; i < 6 && fits; i++) {
+            const int li = vlinks[6 * ((size_t)simc[0].voff + v) + i];
+            if (li >= 0) fits = add(1, v / vpc, (li - simc[0].loff) / lpc);
+        }
+    if (!fits) return; // too many neighbours for one poll per thread: keep the grid barrier
+    // symmetric closure: whoever reads my data must also be waited for before I overwrite it (WAR)
+    for (int c = 0; c < G && fits; c++) {
+        for (int k = 0; k < ndeps[c] && fits; k++) fits = add(1, deps[(size_t)c * VX3_PERSIST_MAX_DEPS + k], c);
+        for (int k = 0; k < ndeps[G + c] && fits; k++) fits = add(0, deps[((size_t)G + c) * VX3_PERSIST_MAX_DEPS + k], c);
+    }
+    if (!fits) return;
+    if (cudaMalloc((void **)&p.flags, 2 * (size_t)G * 32 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc((void **)&p.deps, deps.size() * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&p.ndeps, ndeps.size() * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaMemcpy(p.deps, deps.data(), deps.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.ndeps, ndeps.data(), ndeps.size() * sizeof(int), cudaMemcpyHostToDevice);
+    p.p2p = true;
 }
 
 inline int persistent_run(PersistentPlan &p, const Dev &D, cudaStream_t st, long long nsteps, bool check_stop, long long *launches) {
@@ -348,7 +458,12 @@ inline int persistent_run(PersistentPlan &p, const Dev &D, cudaStream_t st, long
         int cs = check_stop ? 1 : 0;
         Dev d = D;
         int tm = p.timing ? 1 : 0;
-        void *args[] = {(void *)&d, (void *)&n, (void *)&cs, (void *)&p.links_per_cta, (void *)&p.vox_per_cta, (void *)&p.barrier, (void *)&tm};
+        P2P pp;
+        pp.flags = p.p2p ? p.flags : nullptr;
+        pp.deps = p.deps;
+        pp.ndeps = p.ndeps;
+        if (p.p2p && cudaMemsetAsync(p.flags, 0, 2 * (size_t)p.grid * 32 * sizeof(unsigned int), st) != cudaSuccess) return -1;
+        void *args[] = {(void *)&d, (void *)&n, (void *)&cs, (void *)&p.links_per_cta, (void *)&p.vox_per_cta, (void *)&p.barrier, (void *)&tm, (void *)&pp};
         if (cudaLaunchCooperativeKernel((const void *)k_persistent, dim3(p.grid), dim3(p.block), args, 0, st) != cudaSuccess) return -1;
         if (launches) (*launches)++;
         if (p.timing) {
