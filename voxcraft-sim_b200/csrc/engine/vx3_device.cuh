@@ -46,6 +46,14 @@ struct VoxMatC {
     int32_t _pad;
 };
 
+// What the link pass needs of an end voxel's material (one record per VoxMatC entry, same index)
+struct VoxMatL {
+    double size[3];
+    double thermal_on_after;
+    float alphaCTE, dampMultNum;
+    int32_t fixed, _pad;
+};
+
 // Link material constants (VX3_MaterialLink + the VX3_Material stress model).
 struct LinkMatC {
     float E, nu, eHat, epsilonFail;
@@ -81,12 +89,26 @@ struct SimC {
     double dt_frac, optimal_dt;
 };
 
-// per-simulation dynamic scalars (VX3_VoxelyzeKernel members that change during the run)
-struct SimD {
+// bits of SimD::hot_flags (constants of the simulation mirrored next to the per-step scalars)
+#define SHF_THERMAL (1 << 0)     // VaryTempEnabled && TempPeriod > 0
+#define SHF_EXPANSION (1 << 1)   // EnableExpansion
+#define SHF_CILIA (1 << 2)
+#define SHF_FORCE_FIELD (1 << 3)
+#define SHF_ATTACH_COND (1 << 4)
+
+// per-simulation dynamic scalars (VX3_VoxelyzeKernel members that change during the run).  The first 48 bytes are the
+// "hot" block every link / voxel of the simulation needs each step; the streaming kernels prefetch it with three
+// 16-byte cp.async, so its layout and the 16-byte alignment matter.
+struct alignas(16) SimD {
     double t;          // currentTime
-    long long steps;   // CurStepCount
     int32_t status;    // vx3_status
     int32_t diverged;  // set by the link pass of the current step
+    float dt;          // step in use (float, VX3_VoxelyzeKernel.cu:237,253)
+    int32_t hot_flags; // SHF_* (constant)
+    double temp_amp;   // TempAmplitude (constant)
+    double temp_period; // TempPeriod (constant)
+    int32_t _hot_pad[2];
+    long long steps;   // CurStepCount
     int32_t link_cnt;  // d_v_links.size()
     int32_t collision_count;
     int32_t nsurface;
@@ -94,8 +116,6 @@ struct SimD {
     int32_t num_close_pairs;
     int32_t err;
     int32_t attach_events, detach_events;
-    float dt;          // step in use (float, VX3_VoxelyzeKernel.cu:237,253)
-    int32_t _pad;
     double com[3], com_hist[2][3], com0[3];
     double recent_angle, target_closeness, fitness;
     double total_dist;
@@ -111,26 +131,38 @@ struct Cand { // attach candidate (VX3_VoxelyzeKernel.cu:729-812), sorted by (hi
     int32_t _pad;
 };
 
+// Blocked SoA ("AoSoA") index maps of the three hot record arrays: the planes of 32 consecutive items are contiguous, so
+// a warp's access to one plane is one coalesced 512-byte run AND a tile's whole record is one contiguous block
+// (2.5 KB of link history, 3 KB of link end forces, 1.5 KB of momenta per 32 items).  Plain plane-major SoA coalesces just as
+// well but scatters every tile over as many DRAM pages / TLB entries as there are planes (measured: profiles/).
+VXHD size_t idx_lh(int p, size_t g) { return ((g >> 5) * 5 + p) * 32 + (g & 31); }
+VXHD size_t idx_mo(int p, size_t v) { return ((v >> 5) * 3 + p) * 32 + (v & 31); }
+VXHD size_t idx_lf(int k, size_t g) { return ((g >> 5) * 6 + k) * 32 + (g & 31); }
+
 // All device arrays of a batch (plain pointers; owned by the host Batch object).
 struct Dev {
     int32_t nsims, nvox, nlinkslots, nchunks;
     const SimC *simc;
     SimD *simd;
     const VoxMatC *vmat_tab;
+    const VoxMatL *vmatl_tab;
     const LinkMatC *lmat_tab;
+    int32_t n_vmats, n_lmats;
     const float *strain_pool, *stress_pool;
     const vx3_token *tokens;
     const ExtC *exts;
     const Chunk *chunks;
     const int32_t *targets;
     // voxels
-    double *pose;     // [nvox][8]: pos xyz, orient wxyz, pad
-    double *mom;      // [nvox][6]: linMom, angMom
+    int32_t vstride, lstride; // plane strides of the voxel / link-slot SoA planes (multiples of 32 elements)
+    double *pose;     // [nvox][8]: pos xyz, orient wxyz, {float temperature of the coming step, float previousDt}
+    double2 *mom2;    // [vstride/32][3][32] (idx_mo): {linMom.x, linMom.y}, {linMom.z, angMom.x}, {angMom.y, angMom.z}
     int32_t *vflags;  // boolStates | VXF_*
     const int32_t *vmat; // global voxel-material index
     const int32_t *vsim;
+    const int4 *vc4;     // {vmat, vsim, vext, 0}: the voxel's constant indices in one 16-byte record (streaming voxel pass)
     const double *phase;
-    float *tempe, *prevdt;
+    float *tempe;     // temperature the last executed step used (VX3_Voxel::temp)
     int32_t *vlinks;  // [nvox][6] global link slot or -1
     const int32_t *vext;
     const int16_t *ixyz; // [nvox][3]
@@ -141,11 +173,15 @@ struct Dev {
     int2 *lends;      // (vneg, vpos) global voxel indices; x<0 = empty pool slot
     int32_t *lstate;
     int32_t *lmat;
-    double *lhist;    // [slots][9]: pos2, angle1v, angle2v
-    double *lrest;
+    int4 *lc4;        // {vneg, vpos, lmat, sim}: the link's constant indices in one 16-byte record (streaming link pass)
+    double2 *lh2;     // [lstride/32][5][32] (idx_lh): {pos2.x, pos2.y}, {pos2.z, a1v.x}, {a1v.y, a1v.z}, {a2v.x, a2v.y}, {a2v.z, currentRestLength}
     float4 *lstrain;  // strain, maxStrain, strainOffset, _stress
     float2 *larea;    // currentTransverseArea, currentTransverseStrainSum
-    double *lforce;   // [slots][12]: forceNeg, momentNeg, forcePos, momentPos
+    // link end forces [lstride/32][6][32] (idx_lf): {Fneg.x, Fneg.y}, {Fneg.z, Mneg.x}, {Mneg.y, Mneg.z}, then the same three for
+    // the positive end.  Written coalesced by the link pass, gathered by the voxel pass through vlinks.  (Storing them by
+    // receiving voxel and direction instead makes the voxel pass stream, but a direction without a link leaves a 16-byte hole
+    // in its sector, and every partially written sector costs an ECC read-modify-write at eviction: measured 2.5x slower.)
+    double2 *lf2;
     // collision grid (hashed uniform grid)
     int32_t hmask;
     int32_t *cell_cnt, *cell_start, *cell_cursor, *cell_items;
@@ -155,6 +191,12 @@ struct Dev {
     int32_t cand_cap;
     // CoM partials [nchunks][6]: sum m*x, m*y, m*z, m, sum dist, n_measured
     double *com_part;
+#ifdef __CUDACC__
+    __device__ __forceinline__ double2 *lh(int p, int g) const { return lh2 + idx_lh(p, g); }
+    __device__ __forceinline__ double2 *mo(int p, int v) const { return mom2 + idx_mo(p, v); }
+    __device__ __forceinline__ double2 *lf(int k, int g) const { return lf2 + idx_lf(k, g); }
+    __device__ __forceinline__ double &lrest(int g) const { return lh2[idx_lh(4, g)].y; }
+#endif
 };
 
 } // namespace vx3

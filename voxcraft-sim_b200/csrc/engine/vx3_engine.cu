@@ -100,6 +100,8 @@ struct vx3_batch {
     double last_ms = 0;
     long long last_launches = 0;
     long long launches = 0;
+    bool link_smtab = true, vox_smtab = true; // material tables fit the kernels' shared-memory copies
+    int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     PersistentPlan pplan; // on-chip path for a single small collision-free body
     bool use_persistent = true;
 
@@ -129,6 +131,7 @@ struct vx3_batch {
 };
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop);
 
 // VX3_MaterialLink(mat, mat) for attach-created links between two voxels of the same material:
 // updateAll (src/VX3/VX3_MaterialLink.cu:53-127; only the linear model can be blended on the device,
@@ -188,6 +191,14 @@ static int validate_model(const vx3_model_desc &m, int idx) {
     }
     for (int i = 0; i < 6 * m.n_voxels; i++)
         if (m.vox_links[i] >= m.n_links) return bad("voxel link slot out of range");
+    // a link of axis a occupies direction slot 2a (+a) of its negative end and 2a+1 (-a) of its positive end
+    // (CVX_Voxel::addLinkInfo, src/old/VX_Voxel.cpp; VX3_Link ctor VX3_Link.cu:31-56): the engine stores each end's
+    // force by (voxel, direction)
+    for (int i = 0; i < m.n_links; i++) {
+        const int a = m.link_axis[i];
+        if (m.vox_links[6 * m.link_vneg[i] + 2 * a] != i || m.vox_links[6 * m.link_vpos[i] + 2 * a + 1] != i)
+            return bad("vox_links does not hold the link in slot 2*axis of its negative end and 2*axis+1 of its positive end");
+    }
     if (m.opt.enable_signals) return bad("EnableSignals is not supported by this engine yet");
     for (int s = 0; s < VX3_PROG_COUNT; s++) {
         if (m.prog[s].n < 0 || m.prog[s].n > VX3_MAX_TOKENS) return bad("token program too long");
@@ -290,9 +301,11 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         b->any_secondary |= m.opt.secondary_experiment != 0;
     }
 
-    std::vector<double> pose(nvox * 8, 0.0), mom(nvox * 6, 0.0), phase(nvox, 0.0), initpos(nvox * 3);
+    const size_t VS = (nvox + 31) / 32 * 32, LS = (std::max<size_t>(nslots, 1) + 31) / 32 * 32;
+    std::vector<double> pose(nvox * 8, 0.0), phase(nvox, 0.0), initpos(nvox * 3);
+    std::vector<double2> mom2(3 * VS, make_double2(0.0, 0.0));
     std::vector<int32_t> vflags(nvox), vmat(nvox), vsim(nvox), vlinks(nvox * 6), vext(nvox, -1);
-    std::vector<float> tempe(nvox, 0.0f), prevdt(nvox, 0.0f);
+    std::vector<float> tempe(nvox, 0.0f);
     std::vector<int16_t> ixyz(nvox * 3);
     std::vector<double> base_cilia, shift_cilia;
     bool any_cilia = false;
@@ -302,8 +315,9 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         shift_cilia.assign(nvox * 3, 0.0);
     }
     std::vector<int2> lends(nslots, make_int2(-1, -1));
+    std::vector<int4> lc4(nslots, make_int4(-1, -1, 0, 0)), vc4(nvox);
     std::vector<int32_t> lstate(nslots, 0), lmat(nslots, 0);
-    std::vector<double> lhist(nslots * 9, 0.0), lrest(nslots, 0.0);
+    std::vector<double2> lh2(5 * LS, make_double2(0.0, 0.0));
     std::vector<float4> lstrain(nslots, make_float4(0, 0, 0, 0));
     std::vector<float2> larea(nslots, make_float2(0, 0));
 
@@ -413,6 +427,10 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.pair_radius = m.opt.max_dist_in_voxel_lengths_to_count_as_pair * m.opt.vox_size;
         S.dt_frac = m.opt.dt_frac;
         S.optimal_dt = vx3_model_recommended_dt(&m);
+        dy.hot_flags = ((S.vary_temp && S.temp_period > 0) ? SHF_THERMAL : 0) | (S.enable_expansion ? SHF_EXPANSION : 0) | (S.enable_cilia ? SHF_CILIA : 0) |
+                       (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0);
+        dy.temp_amp = S.temp_amp;
+        dy.temp_period = S.temp_period;
         // voxels
         const int vo = S.voff;
         b->vmat_local[s].assign(m.vox_mat, m.vox_mat + m.n_voxels);
@@ -435,8 +453,14 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             else pose[8 * g + 3] = 1.0;
             for (int k = 0; k < 3; k++) {
                 initpos[3 * g + k] = m.pos[3 * i + k];
-                if (m.lin_mom) mom[6 * g + k] = m.lin_mom[3 * i + k];
-                if (m.ang_mom) mom[6 * g + 3 + k] = m.ang_mom[3 * i + k];
+            }
+            if (m.lin_mom) {
+                mom2[idx_mo(0, g)] = make_double2(m.lin_mom[3 * i], m.lin_mom[3 * i + 1]);
+                mom2[idx_mo(1, g)].x = m.lin_mom[3 * i + 2];
+            }
+            if (m.ang_mom) {
+                mom2[idx_mo(1, g)].y = m.ang_mom[3 * i];
+                mom2[idx_mo(2, g)] = make_double2(m.ang_mom[3 * i + 1], m.ang_mom[3 * i + 2]);
             }
             vflags[g] = (m.vox_flags[i] & VXF_BOOLSTATE_MASK) | VXF_ENABLE_ATTACH;
             vmat[g] = vm_global[m.vox_mat[i]];
@@ -471,20 +495,29 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             const int vn = m.link_vneg[i], vp = m.link_vpos[i], ax = m.link_axis[i];
             lends[g] = make_int2(vo + vn, vo + vp);
             lmat[g] = lg[m.link_mat[i]];
+            lc4[g] = make_int4(vo + vn, vo + vp, lmat[g], s);
             int st = (ax << LKS_AXIS_SHIFT);
             if (!m.link_small_angle || m.link_small_angle[i]) st |= LKS_SMALL;
             if (m.link_flags && (m.link_flags[i] & VX3_LINK_LOCAL_VELOCITY_VALID)) st |= LKS_VALID;
             lstate[g] = st;
-            for (int k = 0; k < 3; k++) {
-                if (m.link_pos2) lhist[9 * g + k] = m.link_pos2[3 * i + k];
-                if (m.link_angle1v) lhist[9 * g + 3 + k] = m.link_angle1v[3 * i + k];
-                if (m.link_angle2v) lhist[9 * g + 6 + k] = m.link_angle2v[3 * i + k];
+            {
+                double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int k = 0; k < 3; k++) {
+                    if (m.link_pos2) h[k] = m.link_pos2[3 * i + k];
+                    if (m.link_angle1v) h[3 + k] = m.link_angle1v[3 * i + k];
+                    if (m.link_angle2v) h[6 + k] = m.link_angle2v[3 * i + k];
+                }
+                lh2[idx_lh(0, g)] = make_double2(h[0], h[1]);
+                lh2[idx_lh(1, g)] = make_double2(h[2], h[3]);
+                lh2[idx_lh(2, g)] = make_double2(h[4], h[5]);
+                lh2[idx_lh(3, g)] = make_double2(h[6], h[7]);
+                lh2[idx_lh(4, g)].x = h[8];
             }
             const vx3_voxel_material &mn = m.voxel_mats[m.vox_mat[vn]], &mp = m.voxel_mats[m.vox_mat[vp]];
             const float tn = m.temp ? m.temp[vn] : 0.0f, tp = m.temp ? m.temp[vp] : 0.0f;
             // VX3_Link::reset() defaults (VX3_Link.cu:58-70) unless the model carries link state
-            if (m.link_rest_length) lrest[g] = m.link_rest_length[i];
-            else lrest[g] = 0.5 * ((mn.nomSize * mn.extScale[ax]) * (1 + tn * mn.alphaCTE) + (mp.nomSize * mp.extScale[ax]) * (1 + tp * mp.alphaCTE));
+            if (m.link_rest_length) lh2[idx_lh(4, g)].y = m.link_rest_length[i];
+            else lh2[idx_lh(4, g)].y = 0.5 * ((mn.nomSize * mn.extScale[ax]) * (1 + tn * mn.alphaCTE) + (mp.nomSize * mp.extScale[ax]) * (1 + tp * mp.alphaCTE));
             float4 sn = make_float4(0, 0, 0, 0);
             if (m.link_strain) sn.x = m.link_strain[i];
             if (m.link_max_strain) sn.y = m.link_max_strain[i];
@@ -510,6 +543,8 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     D.nvox = (int)nvox;
     D.nlinkslots = (int)nslots;
     D.nchunks = (int)chunks.size();
+    D.vstride = (int)VS;
+    D.lstride = (int)LS;
 #define UP(field, vec)                                                                                                  \
     do {                                                                                                                \
         std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type *p_ = nullptr;                            \
@@ -521,6 +556,20 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     UP(simd, simd);
     UP(vmat_tab, vmat_tab);
     UP(lmat_tab, lmat_tab);
+    {
+        std::vector<VoxMatL> vl(vmat_tab.size());
+        for (size_t i = 0; i < vmat_tab.size(); i++) {
+            memset(&vl[i], 0, sizeof(VoxMatL));
+            for (int k = 0; k < 3; k++) vl[i].size[k] = vmat_tab[i].size[k];
+            vl[i].thermal_on_after = vmat_tab[i].thermal_on_after;
+            vl[i].alphaCTE = vmat_tab[i].alphaCTE;
+            vl[i].dampMultNum = vmat_tab[i].dampMultNum;
+            vl[i].fixed = vmat_tab[i].fixed;
+        }
+        UP(vmatl_tab, vl);
+    }
+    D.n_vmats = (int)vmat_tab.size();
+    D.n_lmats = (int)lmat_tab.size();
     b->h_lmat_tab = lmat_tab;
     UP(strain_pool, strain_pool);
     UP(stress_pool, stress_pool);
@@ -529,13 +578,12 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     UP(chunks, chunks);
     UP(targets, targets);
     UP(pose, pose);
-    UP(mom, mom);
+    UP(mom2, mom2);
     UP(vflags, vflags);
     UP(vmat, vmat);
     UP(vsim, vsim);
     UP(phase, phase);
     UP(tempe, tempe);
-    UP(prevdt, prevdt);
     UP(vlinks, vlinks);
     UP(vext, vext);
     UP(ixyz, ixyz);
@@ -547,13 +595,15 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     UP(lends, lends);
     UP(lstate, lstate);
     UP(lmat, lmat);
-    UP(lhist, lhist);
-    UP(lrest, lrest);
+    for (size_t g = 0; g < nvox; g++) vc4[g] = make_int4(vmat[g], vsim[g], vext[g], 0);
+    UP(lc4, lc4);
+    UP(vc4, vc4);
+    UP(lh2, lh2);
     UP(lstrain, lstrain);
     UP(larea, larea);
 #undef UP
     int rc;
-    if ((rc = b->alloc(&D.lforce, nslots * 12))) return cleanup(rc);
+    if ((rc = b->alloc(&D.lf2, 6 * LS))) return cleanup(rc);
     if ((rc = b->alloc(&D.com_part, chunks.size() * 6))) return cleanup(rc);
     if (b->any_collide) {
         int H = 1024;
@@ -569,6 +619,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         if ((rc = b->alloc(&D.cands, (size_t)D.cand_cap))) return cleanup(rc);
         if ((rc = b->alloc(&D.cand_count, 1))) return cleanup(rc);
     }
+    if ((rc = setup_stream_kernels(b, prop))) return cleanup(rc);
     // device-side init at the top of CUDA_Simulation (VX3_SimulationManager.cu:20-24,54-55)
     run_com(b, 0);
     k_temp_init<<<cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, 0, b->stream>>>(D);
@@ -643,10 +694,38 @@ static long long next_com_step(const vx3_batch *b) {
         b->launches++;                                                                                                  \
     } while (0)
 
+#define LAUNCH_SM(cls, kern, grid, block, smem, ...)                                                                   \
+    do {                                                                                                                \
+        const bool p_ = b->prof.begin(cls, st);                                                                         \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                                                   \
+        if (p_) b->prof.end(st);                                                                                        \
+        b->launches++;                                                                                                  \
+    } while (0)
+
+// persistent tile loops: one wave of CTAs (SMs x resident CTAs per SM), each striding over the tiles
+static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
+    b->link_smtab = b->D.n_vmats <= VX3_SM_VMATS && b->D.n_lmats <= VX3_SM_LMATS;
+    b->vox_smtab = b->D.n_vmats <= VX3_SM_VMATS;
+    const void *kl = b->link_smtab ? (const void *)k_links<true> : (const void *)k_links<false>;
+    const void *kv = b->vox_smtab ? (const void *)k_voxels<true> : (const void *)k_voxels<false>;
+    int nl = 0, nv = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, kl, VX3_LINK_T, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nv, kv, VX3_VOX_T, 0));
+    if (nl < 1 || nv < 1) return fail(VX3_ERR_CUDA, "streaming kernels do not fit on this device");
+    b->link_tiles = cdiv(b->D.nlinkslots, VX3_LINK_T);
+    b->vox_tiles = cdiv(b->D.nvox, VX3_VOX_T);
+    b->link_grid = std::max(1, std::min(b->link_tiles, nl * prop.multiProcessorCount));
+    b->vox_grid = std::max(1, std::min(b->vox_tiles, nv * prop.multiProcessorCount));
+    return VX3_OK;
+}
+
 static void launch_step(vx3_batch *b, bool check_stop) {
     const Dev &D = b->D;
     cudaStream_t st = b->stream;
-    if (D.nlinkslots > 0) LAUNCH(KC_LINKS, k_links, cdiv(D.nlinkslots, VX3_BLOCK), VX3_BLOCK, D);
+    if (D.nlinkslots > 0) {
+        if (b->link_smtab) LAUNCH_SM(KC_LINKS, k_links<true>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        else LAUNCH_SM(KC_LINKS, k_links<false>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+    }
     if (b->any_collide) {
         LAUNCH(KC_GRID_COUNT, k_grid_count, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
         LAUNCH(KC_GRID_SCAN, k_grid_scan, 1, 1024, D);
@@ -657,11 +736,13 @@ static void launch_step(vx3_batch *b, bool check_stop) {
         LAUNCH(KC_SURFACE, k_surface, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     }
     if (b->any_detach && D.nlinkslots > 0) LAUNCH(KC_DETACH, k_detach, cdiv(D.nlinkslots, VX3_BLOCK), VX3_BLOCK, D);
-    LAUNCH(KC_VOXELS, k_voxels, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     const bool com = com_step(b, b->hsteps + 1);
+    if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
+    else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
-    LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, com ? 1 : 0, check_stop ? 1 : 0);
+    if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
+    else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
     b->hsteps++;
 }
 
@@ -884,13 +965,17 @@ extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
     w->n_voxels = nv;
     w->n_links = nl;
     const Dev &D = b->D;
-    std::vector<double> pose, mom, contact, lhist, lrest, lforce;
+    std::vector<double> pose, contact;
+    // blocked records: copy the 32-item blocks that cover the simulation's range; v0/l0 = first item of the first block
+    const size_t v0 = (size_t)S.voff / 32 * 32, v1 = ((size_t)S.voff + nv + 31) / 32 * 32;
+    const size_t l0 = (size_t)S.loff / 32 * 32, l1 = ((size_t)S.loff + nl + 31) / 32 * 32;
+    std::vector<double2> mom2, lh2, lf2;
     std::vector<int32_t> vflags, vlinks, lstate, lmat;
     std::vector<float> tempe;
     std::vector<int2> lends;
     std::vector<float4> lstrain;
     if ((rc = d2h(b, pose, D.pose, 8 * (size_t)S.voff, 8 * (size_t)nv))) return rc;
-    if ((rc = d2h(b, mom, D.mom, 6 * (size_t)S.voff, 6 * (size_t)nv))) return rc;
+    if ((rc = d2h(b, mom2, (const double2 *)D.mom2, 3 * v0, 3 * (v1 - v0)))) return rc;
     if ((rc = d2h(b, vflags, D.vflags, S.voff, nv))) return rc;
     if ((rc = d2h(b, tempe, D.tempe, S.voff, nv))) return rc;
     if ((rc = d2h(b, vlinks, D.vlinks, 6 * (size_t)S.voff, 6 * (size_t)nv))) return rc;
@@ -898,16 +983,17 @@ extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
     if ((rc = d2h(b, lends, D.lends, S.loff, nl))) return rc;
     if ((rc = d2h(b, lstate, D.lstate, S.loff, nl))) return rc;
     if ((rc = d2h(b, lmat, D.lmat, S.loff, nl))) return rc;
-    if ((rc = d2h(b, lhist, D.lhist, 9 * (size_t)S.loff, 9 * (size_t)nl))) return rc;
-    if ((rc = d2h(b, lrest, D.lrest, S.loff, nl))) return rc;
-    if ((rc = d2h(b, lforce, D.lforce, 12 * (size_t)S.loff, 12 * (size_t)nl))) return rc;
+    if (nl > 0 && (rc = d2h(b, lh2, (const double2 *)D.lh2, 5 * l0, 5 * (l1 - l0)))) return rc;
+    if (nl > 0 && (rc = d2h(b, lf2, (const double2 *)D.lf2, 6 * l0, 6 * (l1 - l0)))) return rc;
     if ((rc = d2h(b, lstrain, D.lstrain, S.loff, nl))) return rc;
     CK(cudaStreamSynchronize(b->stream));
     for (int i = 0; i < nv; i++) {
         for (int k = 0; k < 3; k++) {
             if (w->pos) w->pos[3 * i + k] = pose[8 * (size_t)i + k];
-            if (w->lin_mom) w->lin_mom[3 * i + k] = mom[6 * (size_t)i + k];
-            if (w->ang_mom) w->ang_mom[3 * i + k] = mom[6 * (size_t)i + 3 + k];
+            const size_t vb = (size_t)S.voff + i - v0; // index relative to the copied blocks
+            const double mo[6] = {mom2[idx_mo(0, vb)].x, mom2[idx_mo(0, vb)].y, mom2[idx_mo(1, vb)].x, mom2[idx_mo(1, vb)].y, mom2[idx_mo(2, vb)].x, mom2[idx_mo(2, vb)].y};
+            if (w->lin_mom) w->lin_mom[3 * i + k] = mo[k];
+            if (w->ang_mom) w->ang_mom[3 * i + k] = mo[3 + k];
             if (w->contact_force) w->contact_force[3 * i + k] = contact.empty() ? 0.0 : contact[3 * (size_t)i + k];
         }
         if (w->orient) for (int k = 0; k < 4; k++) w->orient[4 * i + k] = pose[8 * (size_t)i + 3 + k];
@@ -928,21 +1014,30 @@ extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
             if (it == lm_local.end()) it = lm_local.emplace(lmat[i], next_local++).first;
             w->link_mat[i] = it->second;
         }
+        const size_t lb = (size_t)S.loff + i - l0;
+        const double h[10] = {lh2[idx_lh(0, lb)].x, lh2[idx_lh(0, lb)].y, lh2[idx_lh(1, lb)].x, lh2[idx_lh(1, lb)].y, lh2[idx_lh(2, lb)].x, lh2[idx_lh(2, lb)].y,
+                              lh2[idx_lh(3, lb)].x, lh2[idx_lh(3, lb)].y, lh2[idx_lh(4, lb)].x, lh2[idx_lh(4, lb)].y};
+        double fn[6], fp[6];
+        for (int p = 0; p < 3; p++) {
+            const double2 a = lf2[idx_lf(p, lb)], c = lf2[idx_lf(3 + p, lb)];
+            fn[2 * p] = a.x; fn[2 * p + 1] = a.y;
+            fp[2 * p] = c.x; fp[2 * p + 1] = c.y;
+        }
         for (int k = 0; k < 3; k++) {
-            if (w->link_pos2) w->link_pos2[3 * i + k] = lhist[9 * (size_t)i + k];
-            if (w->link_angle1v) w->link_angle1v[3 * i + k] = lhist[9 * (size_t)i + 3 + k];
-            if (w->link_angle2v) w->link_angle2v[3 * i + k] = lhist[9 * (size_t)i + 6 + k];
-            if (w->link_force_neg) w->link_force_neg[3 * i + k] = lforce[12 * (size_t)i + k];
-            if (w->link_moment_neg) w->link_moment_neg[3 * i + k] = lforce[12 * (size_t)i + 3 + k];
-            if (w->link_force_pos) w->link_force_pos[3 * i + k] = lforce[12 * (size_t)i + 6 + k];
-            if (w->link_moment_pos) w->link_moment_pos[3 * i + k] = lforce[12 * (size_t)i + 9 + k];
+            if (w->link_pos2) w->link_pos2[3 * i + k] = h[k];
+            if (w->link_angle1v) w->link_angle1v[3 * i + k] = h[3 + k];
+            if (w->link_angle2v) w->link_angle2v[3 * i + k] = h[6 + k];
+            if (w->link_force_neg) w->link_force_neg[3 * i + k] = fn[k];
+            if (w->link_moment_neg) w->link_moment_neg[3 * i + k] = fn[3 + k];
+            if (w->link_force_pos) w->link_force_pos[3 * i + k] = fp[k];
+            if (w->link_moment_pos) w->link_moment_pos[3 * i + k] = fp[3 + k];
         }
         if (w->link_strain) w->link_strain[i] = lstrain[i].x;
         if (w->link_max_strain) w->link_max_strain[i] = lstrain[i].y;
         if (w->link_strain_offset) w->link_strain_offset[i] = lstrain[i].z;
         if (w->link_stress) w->link_stress[i] = lstrain[i].w;
         if (w->link_flags) w->link_flags[i] = lstate[i] & LKS_PUBLIC_MASK;
-        if (w->link_rest_length) w->link_rest_length[i] = lrest[i];
+        if (w->link_rest_length) w->link_rest_length[i] = h[9];
     }
     return VX3_OK;
 }

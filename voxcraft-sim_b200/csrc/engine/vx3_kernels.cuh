@@ -8,13 +8,28 @@
 namespace vx3 {
 
 #define VX3_BLOCK 256
-// occupancy targets of the two streaming hot kernels (CTAs of VX3_BLOCK threads per SM); tuned on B200, see DESIGN.md §4
+// Tile sizes (threads per CTA = items per tile) and occupancy targets of the two streaming hot kernels; tuned on
+// B200, see DESIGN.md §4.  Both are persistent tile loops that carry the next item's indices in registers (below).
+#ifndef VX3_LINK_T
+#define VX3_LINK_T 128
+#endif
 #ifndef VX3_LINKS_MIN_CTAS
-#define VX3_LINKS_MIN_CTAS 2
+#define VX3_LINKS_MIN_CTAS 4
+#endif
+#ifndef VX3_VOX_T
+#define VX3_VOX_T 128
 #endif
 #ifndef VX3_VOXELS_MIN_CTAS
-#define VX3_VOXELS_MIN_CTAS 2
+#define VX3_VOXELS_MIN_CTAS 4
 #endif
+
+// The 8th double of the pose record carries two floats: the voxel's temperature AT THE CURRENT SIMULATION TIME (what
+// gpu_update_temperature will set at the start of the next step — the voxel pass computes it once per voxel, the link
+// pass reads it with the pose instead of evaluating sin() for both ends of every link) and the voxel's previousDt
+// (VX3_Voxel.h:206-208 dampingMultiplier), so the link pass needs no second gather for it.
+__device__ __forceinline__ double pack_tp(float tempe, float prevdt) { return __hiloint2double(__float_as_int(prevdt), __float_as_int(tempe)); }
+__device__ __forceinline__ float unpack_t(double d) { return __int_as_float(__double2loint(d)); }
+__device__ __forceinline__ float unpack_pd(double d) { return __int_as_float(__double2hiint(d)); }
 
 __device__ __forceinline__ void load_pose(const double *__restrict__ pose, int v, V3 &p, Q4 &q) {
     const double2 *s = reinterpret_cast<const double2 *>(pose + 8 * (size_t)v);
@@ -27,98 +42,167 @@ __device__ __forceinline__ V3 load_pos(const double *__restrict__ pose, int v) {
     const double2 a = s[0];
     return V3(a.x, a.y, s[1].x);
 }
-// The 8th double of the pose record carries the voxel's temperature AT THE CURRENT SIMULATION TIME (what
-// gpu_update_temperature will set at the start of the next step): the voxel pass computes it once per voxel, the
-// link pass reads it with the pose instead of evaluating sin() for both ends of every link.
-__device__ __forceinline__ void load_pose_t(const double *__restrict__ pose, int v, V3 &p, Q4 &q, float &tempe) {
-    const double2 *s = reinterpret_cast<const double2 *>(pose + 8 * (size_t)v);
-    const double2 a = s[0], b = s[1], c = s[2], d = s[3];
-    p = V3(a.x, a.y, b.x);
-    q = Q4(b.y, c.x, c.y, d.x);
-    tempe = (float)d.y;
-}
-__device__ __forceinline__ void store_pose(double *pose, int v, const V3 &p, const Q4 &q, float tempe_next) {
+__device__ __forceinline__ void store_pose(double *pose, int v, const V3 &p, const Q4 &q, float tempe_next, float prevdt) {
     double2 *s = reinterpret_cast<double2 *>(pose + 8 * (size_t)v);
     s[0] = make_double2(p.x, p.y);
     s[1] = make_double2(p.z, q.w);
     s[2] = make_double2(q.x, q.y);
-    s[3] = make_double2(q.z, (double)tempe_next);
+    s[3] = make_double2(q.z, pack_tp(tempe_next, prevdt));
 }
 __device__ __forceinline__ V3 load3(const double *__restrict__ a, size_t i) { return V3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
 __device__ __forceinline__ void store3(double *a, size_t i, const V3 &v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
+__device__ __forceinline__ V3 load_linmom(const Dev &D, int v) {
+    const double2 a = *D.mo(0, v);
+    return V3(a.x, a.y, D.mo(1, v)->x);
+}
 
 // ------------------------------------------------------------------ links
 // gpu_update_links (VX3_VoxelyzeKernel.cu:566-581) with the temperature-driven rest-length refresh of
 // gpu_update_temperature (:625-650) folded in.
-__global__ void __launch_bounds__(VX3_BLOCK, VX3_LINKS_MIN_CTAS) k_links(Dev D) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= D.nlinkslots) return;
-    // Loads are issued in dependency LEVELS, each level before any branch that could separate it from the next:
-    // the kernel is latency bound (ncu: long-scoreboard stalls dominate), so the number of serialised DRAM round
-    // trips matters more than a few loads wasted on skipped links.
-    // ---- level 1: everything indexed by the link slot ----
-    const int2 e = D.lends[g];
-    LinkRegs L;
-    L.state = D.lstate[g];
-    const int lmi = D.lmat[g];
-    const double *h = D.lhist + 9 * (size_t)g;
-    L.pos2 = V3(h[0], h[1], h[2]);
-    L.angle1v = V3(h[3], h[4], h[5]);
-    L.angle2v = V3(h[6], h[7], h[8]);
-    const float4 sn = D.lstrain[g];
-    const float2 ar = D.larea[g];
-    L.rest = D.lrest[g];
-    if (e.x < 0) return;
-    // ---- level 2: everything indexed by the two end voxels (+ the link material) ----
-    V3 pN, pP;
-    Q4 qN, qP;
-    float tN, tP; // the ends' temperatures for this step (computed by the voxel pass of the previous step)
-    load_pose_t(D.pose, e.x, pN, qN, tN);
-    load_pose_t(D.pose, e.y, pP, qP, tP);
-    const int vmN = D.vmat[e.x], vmP = D.vmat[e.y];
-    const float pdN = D.prevdt[e.x], pdP = D.prevdt[e.y];
-    const int sim = D.nsims == 1 ? 0 : D.vsim[e.x];
-    const LinkMatC &lm = D.lmat_tab[lmi];
-    // ---- level 3: small tables (L1/L2 resident) ----
-    const SimC &S = D.simc[sim];
-    SimD &dy = D.simd[sim];
-    const VoxMatC &mN = D.vmat_tab[vmN], &mP = D.vmat_tab[vmP];
-    const int status = dy.status;
-    const float dt = dy.dt;
-    const bool fixedBoth = mN.fixed && mP.fixed;
-    const float numN = mN.dampMultNum, numP = mP.dampMultNum;
-    if (L.state & (LKS_DETACHED | LKS_REMOVED)) return;
-    if (status != VX3_SIM_RUNNING || dt == 0 || fixedBoth) return;
-    const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
-    L.state &= ~LKS_JUST_CREATED;
-    L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
-    L.area = ar.x; L.tsum = ar.y;
-    if (S.vary_temp && S.temp_period > 0) { // updateRestLength() from either end's setTemperature (VX3_Voxel.cu:107-113)
-        const double t = dy.t;
-        if (thermal_active(S, mN, 0, t) || thermal_active(S, mP, 0, t)) {
-            L.rest = 0.5 * (base_size_axis(mN, tN, axis) + base_size_axis(mP, tP, axis));
-            D.lrest[g] = L.rest;
-        }
+//
+// What the pass is bound by was established by A/B builds on config 3 (DESIGN.md §4 has the table): its bytes
+// (~250 MB per step there) move at HBM speed when the arithmetic is removed, so what is left is to overlap ~900-1500
+// instructions per link with them at 16 warps per SM.  The structure that measured best:
+//  * one memory level per link: a persistent tile loop in which every thread carries the constant index record
+//    {ends, material, simulation} of its NEXT link in registers, so that every load of the current link — slot record,
+//    both end poses, the simulation's hot scalars — is independent of every other.  They are issued back to back with
+//    volatile loads: ptxas otherwise sinks each load behind the early-out tests next to its first use and turns one
+//    exposed round trip per link into three dependent ones;
+//  * blocked SoA records (idx_lh / idx_lf): coalesced 16-byte accesses, full-sector writes;
+//  * the material tables live in shared memory, so the per-link constants cost an LDS, not a dependent global load.
+// Tried and dropped, each measured slower: cp.async staging of the next links' records (the LSU write wavefronts of the
+// gathers throttle the MIO queue), L1/L2 software prefetch, a class-sorted processing order that makes warps uniform in
+// small/large-angle mode (−34 % instructions, but the indirection costs more in sector efficiency than it saves), and
+// storing end forces by receiving voxel (streams for the voxel pass, but leaves partially written sectors -> ECC RMW).
+#define VX3_SM_VMATS 32
+#define VX3_SM_LMATS 64
+struct LinkSmem {
+    VoxMatL vm[VX3_SM_VMATS];
+    LinkMatC lm[VX3_SM_LMATS];
+};
+// Loads the compiler must not sink below a branch: the streaming kernels issue every load of an item back to back and
+// only then look at the values (nvcc otherwise moves each load next to its first use, behind the early-out tests, which
+// turns one memory round trip per item into three dependent ones — see profiles/).
+#define VX3_LDQ ".volatile"
+__device__ __forceinline__ double2 ldv(const double2 *p) {
+    double2 r;
+    asm volatile("ld" VX3_LDQ ".global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldv(const float4 *p) {
+    float4 r;
+    asm volatile("ld" VX3_LDQ ".global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int4 ldv(const int4 *p) {
+    int4 r;
+    asm volatile("ld" VX3_LDQ ".global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldv(const float2 *p) {
+    float2 r;
+    asm volatile("ld" VX3_LDQ ".global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int ldv(const int *p) {
+    int r;
+    asm volatile("ld" VX3_LDQ ".global.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ldv(const double *p) {
+    double r;
+    asm volatile("ld" VX3_LDQ ".global.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+// predicated 16-byte load (keeps the zero it is given when the predicate is off)
+__device__ __forceinline__ double2 ldv_if(const double2 *p, bool on) {
+    double2 r = make_double2(0.0, 0.0);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p ld" VX3_LDQ ".global.v2.f64 {%0, %1}, [%2];\n\t}" : "+d"(r.x), "+d"(r.y) : "l"(p), "r"((int)on));
+    return r;
+}
+
+__device__ __forceinline__ int4 link_c4(const Dev &D, long long g) { return g < D.nlinkslots ? __ldg(D.lc4 + g) : make_int4(-1, -1, 0, 0); }
+
+// SMTAB: the batch's material tables fit the shared-memory copies (the normal case); otherwise they are read from global
+template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles) {
+    __shared__ LinkSmem sm;
+    const int tid = threadIdx.x;
+    const long long G = gridDim.x;
+    if (SMTAB) {
+        for (int i = tid; i < D.n_vmats * (int)(sizeof(VoxMatL) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.vm)[i] = reinterpret_cast<const int *>(D.vmatl_tab)[i];
+        for (int i = tid; i < D.n_lmats * (int)(sizeof(LinkMatC) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.lm)[i] = reinterpret_cast<const int *>(D.lmat_tab)[i];
+        __syncthreads();
     }
-    // dampingMultiplier() = 2*_sqrtMass*zetaInternal/previousDt (float)
-    const float dmN = numN / pdN, dmP = numP / pdP;
-    LinkOut o;
-    link_update_forces(L, lm, D.strain_pool, D.stress_pool, pN, qN, pP, qP, dmN, dmP, o);
-    double *hw = D.lhist + 9 * (size_t)g;
-    hw[0] = L.pos2.x; hw[1] = L.pos2.y; hw[2] = L.pos2.z;
-    hw[3] = L.angle1v.x; hw[4] = L.angle1v.y; hw[5] = L.angle1v.z;
-    hw[6] = L.angle2v.x; hw[7] = L.angle2v.y; hw[8] = L.angle2v.z;
-    D.lstrain[g] = make_float4(L.strain, L.maxStrain, L.strainOffset, L.stress);
-    D.lstate[g] = L.state;
-    double2 *f = reinterpret_cast<double2 *>(D.lforce + 12 * (size_t)g);
-    f[0] = make_double2(o.forceNeg.x, o.forceNeg.y);
-    f[1] = make_double2(o.forceNeg.z, o.momentNeg.x);
-    f[2] = make_double2(o.momentNeg.y, o.momentNeg.z);
-    f[3] = make_double2(o.forcePos.x, o.forcePos.y);
-    f[4] = make_double2(o.forcePos.z, o.momentPos.x);
-    f[5] = make_double2(o.momentPos.y, o.momentPos.z);
-    // divergence: the reference samples one random link per step (:273-280); every link is checked here
-    if (L.strain > 100) dy.diverged = 1;
+    long long tile = blockIdx.x;
+    int4 c4 = link_c4(D, tile * VX3_LINK_T + tid);
+    for (; tile < ntiles; tile += G) {
+        // ---- the next item's constant indices (consumed by the next iteration) ----
+        const int4 c4n = link_c4(D, (tile + G) * VX3_LINK_T + tid);
+        const int gc = (int)(tile * VX3_LINK_T + tid);
+        const int4 c = c4;
+        c4 = c4n;
+        if (c.x < 0) continue; // empty pool slot / past the end
+        // ---- every load of this link, all independent ----
+        const double2 h0 = ldv(D.lh(0, gc)), h1 = ldv(D.lh(1, gc)), h2 = ldv(D.lh(2, gc)), h3 = ldv(D.lh(3, gc)), h4 = ldv(D.lh(4, gc));
+        const float4 sn = ldv(D.lstrain + gc);
+        const float2 ar = ldv(D.larea + gc);
+        LinkRegs L;
+        L.state = ldv(D.lstate + gc);
+        const double2 *pa = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.x), *pb = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.y);
+        const double2 a0 = ldv(pa), a1 = ldv(pa + 1), a2 = ldv(pa + 2), a3 = ldv(pa + 3);
+        const double2 b0 = ldv(pb), b1 = ldv(pb + 1), b2 = ldv(pb + 2), b3 = ldv(pb + 3);
+        const int vmN = ldv(D.vmat + c.x), vmP = ldv(D.vmat + c.y);
+        const int4 *hp = reinterpret_cast<const int4 *>(D.simd + c.w);
+        const int4 hot0 = ldv(hp), hot1 = ldv(hp + 1);
+        L.pos2 = V3(h0.x, h0.y, h1.x);
+        L.angle1v = V3(h1.y, h2.x, h2.y);
+        L.angle2v = V3(h3.x, h3.y, h4.x);
+        L.rest = h4.y;
+        const V3 pN(a0.x, a0.y, a1.x), pP(b0.x, b0.y, b1.x);
+        const Q4 qN(a1.y, a2.x, a2.y, a3.x), qP(b1.y, b2.x, b2.y, b3.x);
+        const float tN = unpack_t(a3.y), pdN = unpack_pd(a3.y), tP = unpack_t(b3.y), pdP = unpack_pd(b3.y);
+        const double t = __hiloint2double(hot0.y, hot0.x);
+        const int status = hot0.z;
+        const float dt = __int_as_float(hot1.x);
+        const int hot_flags = hot1.y;
+        const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+        const LinkMatC &lm = SMTAB ? sm.lm[c.z] : D.lmat_tab[c.z];
+        // the few end-material values, read up front so that their latencies overlap
+        struct { double size, on_after; float cte, dmn; int fixed; } mN, mP;
+        {
+            const VoxMatL &a = SMTAB ? sm.vm[vmN] : D.vmatl_tab[vmN], &b = SMTAB ? sm.vm[vmP] : D.vmatl_tab[vmP];
+            mN.size = a.size[axis]; mN.on_after = a.thermal_on_after; mN.cte = a.alphaCTE; mN.dmn = a.dampMultNum; mN.fixed = a.fixed;
+            mP.size = b.size[axis]; mP.on_after = b.thermal_on_after; mP.cte = b.alphaCTE; mP.dmn = b.dampMultNum; mP.fixed = b.fixed;
+        }
+        if (L.state & (LKS_DETACHED | LKS_REMOVED)) continue;
+        if (status != VX3_SIM_RUNNING || dt == 0 || (mN.fixed && mP.fixed)) continue;
+        L.state &= ~LKS_JUST_CREATED;
+        L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
+        L.area = ar.x; L.tsum = ar.y;
+        if (hot_flags & SHF_THERMAL) { // updateRestLength() from either end's setTemperature (VX3_Voxel.cu:107-113)
+            const bool actN = !mN.fixed && !(mN.on_after > t), actP = !mP.fixed && !(mP.on_after > t);
+            if (actN || actP) L.rest = 0.5 * (mN.size * (1 + tN * mN.cte) + mP.size * (1 + tP * mP.cte)); // VX3_Voxel.h:95-98
+        }
+        // dampingMultiplier() = 2*_sqrtMass*zetaInternal/previousDt (float)
+        const float dmN = mN.dmn / pdN, dmP = mP.dmn / pdP;
+        LinkOut o;
+        link_update_forces(L, lm, D.strain_pool, D.stress_pool, pN, qN, pP, qP, dmN, dmP, o);
+        *D.lh(0, gc) = make_double2(L.pos2.x, L.pos2.y);
+        *D.lh(1, gc) = make_double2(L.pos2.z, L.angle1v.x);
+        *D.lh(2, gc) = make_double2(L.angle1v.y, L.angle1v.z);
+        *D.lh(3, gc) = make_double2(L.angle2v.x, L.angle2v.y);
+        *D.lh(4, gc) = make_double2(L.angle2v.z, L.rest);
+        D.lstrain[gc] = make_float4(L.strain, L.maxStrain, L.strainOffset, L.stress);
+        D.lstate[gc] = L.state;
+        *D.lf(0, gc) = make_double2(o.forceNeg.x, o.forceNeg.y);
+        *D.lf(1, gc) = make_double2(o.forceNeg.z, o.momentNeg.x);
+        *D.lf(2, gc) = make_double2(o.momentNeg.y, o.momentNeg.z);
+        *D.lf(3, gc) = make_double2(o.forcePos.x, o.forcePos.y);
+        *D.lf(4, gc) = make_double2(o.forcePos.z, o.momentPos.x);
+        *D.lf(5, gc) = make_double2(o.momentPos.y, o.momentPos.z);
+        // divergence: the reference samples one random link per step (:273-280); every link is checked here
+        if (L.strain > 100) D.simd[c.w].diverged = 1;
+    }
 }
 
 // ------------------------------------------------------------------ voxels
@@ -134,93 +218,146 @@ __device__ __forceinline__ double eval_slot(const Dev &D, const SimC &S, int slo
 }
 
 // gpu_update_voxels (VX3_VoxelyzeKernel.cu:582-623) -> VX3_Voxel::timeStep
-__global__ void __launch_bounds__(VX3_BLOCK, VX3_VOXELS_MIN_CTAS) k_voxels(Dev D) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= D.nvox) return;
-    // loads in dependency levels (see k_links)
-    // ---- level 1: everything indexed by the voxel ----
-    VoxRegs r;
-    float tempe;
-    load_pose_t(D.pose, v, r.pos, r.orient, tempe); // this step's temperature (gpu_update_temperature at time t)
-    r.flags = D.vflags[v];
-    const int vmi = D.vmat[v];
-    const int sim = D.nsims == 1 ? 0 : D.vsim[v];
-    const double *mo = D.mom + 6 * (size_t)v;
-    r.linMom = V3(mo[0], mo[1], mo[2]);
-    r.angMom = V3(mo[3], mo[4], mo[5]);
-    int vl[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) vl[i] = D.vlinks[6 * (size_t)v + i];
-    const double phase = D.phase[v];
-    // ---- level 2: link end forces, tables ----
-    double2 fa[6], fb[6], fc[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        if (vl[i] >= 0) {
-            const double2 *f = reinterpret_cast<const double2 *>(D.lforce + 12 * (size_t)vl[i] + ((i & 1) ? 6 : 0));
-            fa[i] = f[0]; fb[i] = f[1]; fc[i] = f[2];
+//
+// Same idea as the link pass: a persistent tile loop in which the voxel's six link slots and constant indices
+// {material, simulation, external} are fetched one item ahead into registers, so that the pose, momenta, hot scalars of
+// the simulation and the end forces of exactly those directions whose slot holds a link are all issued together.
+struct VoxSmem {
+    VoxMatC vm[VX3_SM_VMATS];
+};
+struct VoxIdx {
+    int2 l0, l1, l2; // vlinks[0..5]
+    int4 c4;         // vmat, sim, ext
+};
+__device__ __forceinline__ VoxIdx vox_idx(const Dev &D, long long v) {
+    VoxIdx r;
+    r.l0 = r.l1 = r.l2 = make_int2(-1, -1);
+    r.c4 = make_int4(0, 0, -1, 0);
+    if (v < D.nvox) {
+        const int2 *src = reinterpret_cast<const int2 *>(D.vlinks + 6 * (size_t)v);
+        r.l0 = src[0]; r.l1 = src[1]; r.l2 = src[2];
+        r.c4 = __ldg(D.vc4 + v);
+    }
+    return r;
+}
+// the voxel is the negative end of the links in its even (+axis) slots and the positive end of those in its odd slots
+#define VX3_LOAD_END_FORCE(dir, slot)                                                                                   \
+    const double2 fa##dir = ldv_if(D.lf(3 * (dir & 1), slot), slot >= 0), fb##dir = ldv_if(D.lf(3 * (dir & 1) + 1, slot), slot >= 0),                \
+                  fc##dir = ldv_if(D.lf(3 * (dir & 1) + 2, slot), slot >= 0);
+#define VX3_ADD_END_FORCE(dir, cond)                                                                                    \
+    if (cond) {                                                                                                         \
+        F += V3(fa##dir.x, fa##dir.y, fb##dir.x);                                                                       \
+        M += V3(fb##dir.y, fc##dir.x, fc##dir.y);                                                                       \
+    }
+
+template <bool SMTAB> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MIN_CTAS) k_voxels(Dev D, int ntiles) {
+    __shared__ VoxSmem sm;
+    const int tid = threadIdx.x;
+    const long long G = gridDim.x;
+    if (SMTAB) { // material table -> shared memory
+        for (int i = tid; i < D.n_vmats * (int)(sizeof(VoxMatC) / 4); i += VX3_VOX_T) reinterpret_cast<int *>(sm.vm)[i] = reinterpret_cast<const int *>(D.vmat_tab)[i];
+        __syncthreads();
+    }
+    long long tile = blockIdx.x;
+    VoxIdx nx = vox_idx(D, tile * VX3_VOX_T + tid);
+    for (; tile < ntiles; tile += G) {
+        const VoxIdx id = nx;
+        nx = vox_idx(D, (tile + G) * VX3_VOX_T + tid);
+        const long long vv = tile * VX3_VOX_T + tid;
+        if (vv >= D.nvox) continue;
+        const int v = (int)vv;
+        // ---- every load of this voxel, all independent ----
+        const double2 *ps = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)v);
+        const double2 a = ldv(ps), b = ldv(ps + 1), c = ldv(ps + 2), d = ldv(ps + 3);
+        const double2 m0 = ldv(D.mo(0, v)), m1 = ldv(D.mo(1, v)), m2 = ldv(D.mo(2, v));
+        const int4 *hp = reinterpret_cast<const int4 *>(D.simd + id.c4.y);
+        const int4 hot0 = ldv(hp), hot1 = ldv(hp + 1), hot2 = ldv(hp + 2);
+        const double phase = ldv(D.phase + v);
+        VoxRegs r;
+        r.flags = ldv(D.vflags + v);
+        VX3_LOAD_END_FORCE(0, id.l0.x)
+        VX3_LOAD_END_FORCE(1, id.l0.y)
+        VX3_LOAD_END_FORCE(2, id.l1.x)
+        VX3_LOAD_END_FORCE(3, id.l1.y)
+        VX3_LOAD_END_FORCE(4, id.l2.x)
+        VX3_LOAD_END_FORCE(5, id.l2.y)
+        r.pos = V3(a.x, a.y, b.x);
+        r.orient = Q4(b.y, c.x, c.y, d.x);
+        const float tempe = unpack_t(d.y); // this step's temperature (gpu_update_temperature at time t)
+        const float pd_old = unpack_pd(d.y);
+        r.linMom = V3(m0.x, m0.y, m1.x);
+        r.angMom = V3(m1.y, m2.x, m2.y);
+        const int vmi = id.c4.x, sim = id.c4.y, ext = id.c4.z;
+        V3 F(0, 0, 0), M(0, 0, 0); // force()/moment() sum the links in direction order 0..5 (VX3_Voxel.cu:350-397)
+        VX3_ADD_END_FORCE(0, id.l0.x >= 0)
+        VX3_ADD_END_FORCE(1, id.l0.y >= 0)
+        VX3_ADD_END_FORCE(2, id.l1.x >= 0)
+        VX3_ADD_END_FORCE(3, id.l1.y >= 0)
+        VX3_ADD_END_FORCE(4, id.l2.x >= 0)
+        VX3_ADD_END_FORCE(5, id.l2.y >= 0)
+        const double t = __hiloint2double(hot0.y, hot0.x);
+        const int status = hot0.z, sdiverged = hot0.w;
+        const float dtF = __int_as_float(hot1.x);
+        const int hot_flags = hot1.y;
+        const double temp_amp = __hiloint2double(hot1.w, hot1.z), temp_period = __hiloint2double(hot2.y, hot2.x);
+        const VoxMatC &m = SMTAB ? sm.vm[vmi] : D.vmat_tab[vmi];
+        if (status != VX3_SIM_RUNNING || sdiverged) continue;
+        if (dtF == 0) continue;
+        const double dt = dtF;
+        D.tempe[v] = tempe;
+        // temperature the next step will start with (time t + dt), see pack_tp
+        const double tnext = t + dtF;
+        float tempe_next = tempe;
+        if ((hot_flags & SHF_THERMAL) && !(r.flags & VXF_REMOVED) && !(m.thermal_on_after > tnext) && !m.fixed)
+            tempe_next = voxel_temperature(temp_amp, temp_period, (hot_flags & SHF_EXPANSION) != 0, tnext, phase);
+        if ((r.flags & VXF_REMOVED) || m.fixed) {
+            if (tempe_next != tempe) D.pose[8 * (size_t)v + 7] = pack_tp(tempe_next, pd_old);
+            continue;
         }
-    }
-    const SimC &S = D.simc[sim];
-    const SimD &dy = D.simd[sim];
-    const VoxMatC &m = D.vmat_tab[vmi];
-    if (dy.status != VX3_SIM_RUNNING || dy.diverged) return;
-    const float dtF = dy.dt;
-    if (dtF == 0) return;
-    const double dt = dtF, t = dy.t;
-    D.tempe[v] = tempe;
-    // temperature the next step will start with (time t + dt), see store_pose
-    const double tnext = t + dtF;
-    const float tempe_next = thermal_active(S, m, r.flags, tnext) ? voxel_temperature(S, tnext, phase) : tempe;
-    if ((r.flags & VXF_REMOVED) || m.fixed) {
-        if (tempe_next != tempe) D.pose[8 * (size_t)v + 7] = (double)tempe_next;
-        return;
-    }
-    D.prevdt[v] = (float)dt;
-    V3 F(0, 0, 0), M(0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        if (vl[i] >= 0) {
-            F += V3(fa[i].x, fa[i].y, fb[i].x);
-            M += V3(fb[i].y, fc[i].x, fc[i].y);
+        V3 contact(0, 0, 0);
+        if (D.contact) {
+            contact = load3(D.contact, v);
+            store3(D.contact, v, V3());
         }
+        V3 cil(0, 0, 0);
+        if ((hot_flags & SHF_CILIA) && !(r.flags & VX3_VOX_SURFACE) && m.cilia != 0 && !(m.cilia_on_after > t)) { // gpu_update_cilia_force :846-859
+            cil = r.orient.RotateVec3D(load3(D.base_cilia, v)) * m.cilia;                                     // localSignal = 0 (signals are off)
+        }
+        V3 ff(0, 0, 0);
+        const ExtC *px = ext >= 0 ? &D.exts[ext] : nullptr;
+        const bool fixedAll = px && (px->dof & 0x3F) == 0x3F;
+        if ((hot_flags & SHF_FORCE_FIELD) && !fixedAll) {
+            const SimC &S = D.simc[sim];
+            const SimD &dy = D.simd[sim];
+            double vars[9];
+            prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
+            ff.x = eval_slot(D, S, VX3_PROG_FORCE_X, vars, 0.0);
+            ff.y = eval_slot(D, S, VX3_PROG_FORCE_Y, vars, 0.0);
+            ff.z = eval_slot(D, S, VX3_PROG_FORCE_Z, vars, 0.0);
+        }
+        int ix = 0, iy = 0, iz = 0;
+        if (px) {
+            const short *ic = D.ixyz + 3 * (size_t)v;
+            ix = ic[0]; iy = ic[1]; iz = ic[2];
+        }
+        voxel_time_step(r, m, px, ix, iy, iz, tempe, F, M, contact, cil, ff, dt);
+        // enableAttach = AND of the five attach conditions at the new position (:609-621)
+        if (hot_flags & SHF_ATTACH_COND) {
+            const SimC &S = D.simc[sim];
+            const SimD &dy = D.simd[sim];
+            double vars[9];
+            prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
+            bool all = true;
+            for (int c = 0; c < 5 && all; c++) all = eval_slot(D, S, VX3_PROG_ATTACH_0 + c, vars, 1.0) > 0;
+            if (all) r.flags |= VXF_ENABLE_ATTACH;
+            else r.flags &= ~VXF_ENABLE_ATTACH;
+        }
+        store_pose(D.pose, v, r.pos, r.orient, tempe_next, dtF);
+        *D.mo(0, v) = make_double2(r.linMom.x, r.linMom.y);
+        *D.mo(1, v) = make_double2(r.linMom.z, r.angMom.x);
+        *D.mo(2, v) = make_double2(r.angMom.y, r.angMom.z);
+        D.vflags[v] = r.flags;
     }
-    V3 contact(0, 0, 0);
-    if (D.contact) {
-        contact = load3(D.contact, v);
-        store3(D.contact, v, V3());
-    }
-    V3 cil(0, 0, 0);
-    if (S.enable_cilia && !(r.flags & VX3_VOX_SURFACE) && m.cilia != 0 && !(m.cilia_on_after > t)) { // gpu_update_cilia_force :846-859
-        cil = r.orient.RotateVec3D(load3(D.base_cilia, v)) * m.cilia;                                 // localSignal = 0 (signals are off)
-    }
-    V3 ff(0, 0, 0);
-    const int ext = D.vext[v];
-    const ExtC *px = ext >= 0 ? &D.exts[ext] : nullptr;
-    const bool fixedAll = px && (px->dof & 0x3F) == 0x3F;
-    if (S.has_ff && !fixedAll) {
-        double vars[9];
-        prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
-        ff.x = eval_slot(D, S, VX3_PROG_FORCE_X, vars, 0.0);
-        ff.y = eval_slot(D, S, VX3_PROG_FORCE_Y, vars, 0.0);
-        ff.z = eval_slot(D, S, VX3_PROG_FORCE_Z, vars, 0.0);
-    }
-    const short *ic = D.ixyz + 3 * (size_t)v;
-    voxel_time_step(r, m, px, ic[0], ic[1], ic[2], tempe, F, M, contact, cil, ff, dt);
-    // enableAttach = AND of the five attach conditions at the new position (:609-621)
-    if (S.has_attach_cond) {
-        double vars[9];
-        prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
-        bool all = true;
-        for (int c = 0; c < 5 && all; c++) all = eval_slot(D, S, VX3_PROG_ATTACH_0 + c, vars, 1.0) > 0;
-        if (all) r.flags |= VXF_ENABLE_ATTACH;
-        else r.flags &= ~VXF_ENABLE_ATTACH;
-    }
-    store_pose(D.pose, v, r.pos, r.orient, tempe_next);
-    double *mw = D.mom + 6 * (size_t)v;
-    mw[0] = r.linMom.x; mw[1] = r.linMom.y; mw[2] = r.linMom.z;
-    mw[3] = r.angMom.x; mw[4] = r.angMom.y; mw[5] = r.angMom.z;
-    D.vflags[v] = r.flags;
 }
 
 // ------------------------------------------------------------------ collision grid
@@ -240,7 +377,7 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_count(Dev D) {
     int4 vc = make_int4(0, 0, 0, -1);
     if (dy.status == VX3_SIM_RUNNING && !dy.diverged && dy.dt != 0 && sim_collides(S)) {
         int flags = D.vflags[v];
-        D.tempe[v] = (float)D.pose[8 * (size_t)v + 7]; // this step's temperature, for the contact phase
+        D.tempe[v] = unpack_t(D.pose[8 * (size_t)v + 7]); // this step's temperature, for the contact phase
         bool interior = true; // VX3_Voxel::updateSurface (VX3_Voxel.cu:515-524): the bit named SURFACE means interior
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -367,7 +504,7 @@ __device__ __forceinline__ V3 pair_contact_force(const Dev &D, int hi, int lo, c
     const double RelDist = NomDist - offset.Length();
     if (RelDist > 0) {
         const V3 unit = offset.Normalized();
-        const V3 vel1 = load3(D.mom, 2 * (size_t)hi) * m1.massInverse, vel2 = load3(D.mom, 2 * (size_t)lo) * m2.massInverse;
+        const V3 vel1 = load_linmom(D, hi) * m1.massInverse, vel2 = load_linmom(D, lo) * m2.massInverse;
         const double relativeVelocity = vel1.Dot(unit) - vel2.Dot(unit);
         return unit * (penetrationStiff * RelDist + dampingC * relativeVelocity);
     }
@@ -560,14 +697,13 @@ __global__ void __launch_bounds__(1024) k_resolve(Dev D) {
         D.vlinks[6 * (size_t)lo + dir2] = g;
         D.lends[g] = make_int2(vneg, vpos);
         D.lmat[g] = mh.self_lmat;
+        D.lc4[g] = make_int4(vneg, vpos, mh.self_lmat, sim);
         D.lstate[g] = (axis << LKS_AXIS_SHIFT) | LKS_SMALL | LKS_JUST_CREATED | (S.safety_guard << LKS_NEWLINK_SHIFT);
-        double *h = D.lhist + 9 * (size_t)g;
-        for (int k = 0; k < 9; k++) h[k] = 0.0;
-        double *f = D.lforce + 12 * (size_t)g;
-        for (int k = 0; k < 12; k++) f[k] = 0.0;
-        D.lstrain[g] = make_float4(0.f, 0.f, 0.f, 0.f);
         const VoxMatC &mn = D.vmat_tab[D.vmat[vneg]], &mp = D.vmat_tab[D.vmat[vpos]];
-        D.lrest[g] = 0.5 * (base_size_axis(mn, D.tempe[vneg], axis) + base_size_axis(mp, D.tempe[vpos], axis));
+        for (int k = 0; k < 4; k++) *D.lh(k, g) = make_double2(0.0, 0.0);
+        *D.lh(4, g) = make_double2(0.0, 0.5 * (base_size_axis(mn, D.tempe[vneg], axis) + base_size_axis(mp, D.tempe[vpos], axis)));
+        for (int k = 0; k < 6; k++) *D.lf(k, g) = make_double2(0.0, 0.0); // the new link's end forces start at zero (VX3_Link::reset)
+        D.lstrain[g] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float sn = (float)mn.nomSize, sp = (float)mp.nomSize; // transverseArea() with zero strain
         D.larea[g] = make_float2(0.5f * (sn * sn + sp * sp), 0.0f);
         dy.attach_events++;
@@ -760,6 +896,33 @@ __global__ void __launch_bounds__(128) k_tail(Dev D, int com_ready, int check_st
     }
 }
 
+// k_tail for a step on which NO simulation of the batch samples its centre of mass (the host knows the cadence): one
+// thread per simulation.  A simulation that nevertheless reaches a sampling step here reports VX3_ERR_INVALID.
+__device__ void tail_light(const Dev &D, int sim, int check_stop) {
+    const SimC &S = D.simc[sim];
+    SimD &dy = D.simd[sim];
+    if (dy.status != VX3_SIM_RUNNING) return;
+    const float dtF = dy.dt;
+    dy.steps += 1;
+    if (dtF == 0) return;
+    if (dy.diverged) {
+        dy.status = VX3_SIM_DIVERGED;
+        return;
+    }
+    const int CycleStep = (int)(S.temp_period / dtF);
+    if (CycleStep > 0 && dy.steps % CycleStep == 0) dy.err = VX3_ERR_INVALID;
+    if (S.secondary_experiment && !dy.initpos_reinitialized && S.reinit_after < dy.t) { // :344-348
+        dy.initpos_reinitialized = 1;
+        for (int k = 0; k < 3; k++) dy.com0[k] = dy.com[k]; // InitializeCenterOfMass()
+    }
+    dy.t += dtF;
+    if (check_stop && stop_condition_met(D, S, dy)) dy.status = VX3_SIM_STOPPED;
+}
+__global__ void __launch_bounds__(128) k_tail_light(Dev D, int check_stop) {
+    const int sim = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sim < D.nsims) tail_light(D, sim, check_stop);
+}
+
 // mode 0: initial state (saveInitialPosition is done on the host; InitializeCenterOfMass, VX3_SimulationManager.cu:54-55)
 // mode 1: results (updateCurrentCenterOfMass + computeFitness, :116-117)   mode 2: stop check before the first step (:63)
 __global__ void k_sim_update(Dev D, int mode) {
@@ -795,7 +958,7 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_temp_init(Dev D) {
     const double t = D.simd[sim].t;
     float tempe = D.tempe[v];
     if (thermal_active(S, m, D.vflags[v], t)) tempe = voxel_temperature(S, t, D.phase[v]);
-    D.pose[8 * (size_t)v + 7] = (double)tempe;
+    D.pose[8 * (size_t)v + 7] = pack_tp(tempe, 0.0f); // previousDt starts at 0 (VX3_Voxel.h:309)
 }
 
 __global__ void k_set_dt(Dev D, float dt) { // dt < 0: DtFrac * recommendedTimeStep() (:244-254)

@@ -143,17 +143,17 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
         else {
             const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
             lm = D.lmat_tab[D.lmat[g]];
-            const double *h = D.lhist + 9 * (size_t)g;
-            L.pos2 = V3(h[0], h[1], h[2]);
-            L.angle1v = V3(h[3], h[4], h[5]);
-            L.angle2v = V3(h[6], h[7], h[8]);
+            const double2 h0 = *D.lh(0, g), h1 = *D.lh(1, g), h2 = *D.lh(2, g), h3 = *D.lh(3, g), h4 = *D.lh(4, g);
+            L.pos2 = V3(h0.x, h0.y, h1.x);
+            L.angle1v = V3(h1.y, h2.x, h2.y);
+            L.angle2v = V3(h3.x, h3.y, h4.x);
+            L.rest = h4.y;
             const float4 sn = D.lstrain[g];
             L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
             const float2 ar = D.larea[g];
             L.area = ar.x; L.tsum = ar.y;
-            L.rest = D.lrest[g];
             L.state &= ~LKS_JUST_CREATED;
-            pdN = D.prevdt[ends.x]; pdP = D.prevdt[ends.y];
+            pdN = unpack_pd(D.pose[8 * (size_t)ends.x + 7]); pdP = unpack_pd(D.pose[8 * (size_t)ends.y + 7]);
             numN = mN.dampMultNum; numP = mP.dampMultNum;
             szN = mN.size[axis]; szP = mP.size[axis];
             cteN = mN.alphaCTE; cteP = mP.alphaCTE;
@@ -184,11 +184,12 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
         phase = D.phase[v];
         vthermal = vary && !(r.flags & VXF_REMOVED) && !vm.fixed;
         vint = !(r.flags & VXF_REMOVED) && !vm.fixed;
-        load_pose_t(D.pose, v, r.pos, r.orient, tempe_next);
+        load_pose(D.pose, v, r.pos, r.orient);
+        tempe_next = unpack_t(D.pose[8 * (size_t)v + 7]);
         tempe = D.tempe[v];
-        const double *mo = D.mom + 6 * (size_t)v;
-        r.linMom = V3(mo[0], mo[1], mo[2]);
-        r.angMom = V3(mo[3], mo[4], mo[5]);
+        const double2 m0 = *D.mo(0, v), m1 = *D.mo(1, v), m2 = *D.mo(2, v);
+        r.linMom = V3(m0.x, m0.y, m1.x);
+        r.angMom = V3(m1.y, m2.x, m2.y);
 #pragma unroll
         for (int i = 0; i < 6; i++) vl[i] = D.vlinks[6 * (size_t)v + i];
         const int ext = D.vext[v];
@@ -228,19 +229,18 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
                 pP = V3(b0.x, b0.y, b1.x); qP = Q4(b1.y, b2.x, b2.y, b3.x);
                 // updateRestLength() with the ends' temperatures for this step (published by their voxel passes)
                 if (vary && ((!fixN && !(onN > t)) || (!fixP && !(onP > t)))) {
-                    const float tN = (float)a3.y, tP = (float)b3.y;
+                    const float tN = unpack_t(a3.y), tP = unpack_t(b3.y);
                     L.rest = 0.5 * (szN * (1 + tN * cteN) + szP * (1 + tP * cteP));
                 }
             }
             LinkOut o;
             link_update_forces(L, lm, D.strain_pool, D.stress_pool, pN, qN, pP, qP, numN / pdN, numP / pdP, o);
-            double2 *f = reinterpret_cast<double2 *>(D.lforce + 12 * (size_t)g);
-            f[0] = make_double2(o.forceNeg.x, o.forceNeg.y);
-            f[1] = make_double2(o.forceNeg.z, o.momentNeg.x);
-            f[2] = make_double2(o.momentNeg.y, o.momentNeg.z);
-            f[3] = make_double2(o.forcePos.x, o.forcePos.y);
-            f[4] = make_double2(o.forcePos.z, o.momentPos.x);
-            f[5] = make_double2(o.momentPos.y, o.momentPos.z);
+            *D.lf(0, g) = make_double2(o.forceNeg.x, o.forceNeg.y);
+            *D.lf(1, g) = make_double2(o.forceNeg.z, o.momentNeg.x);
+            *D.lf(2, g) = make_double2(o.momentNeg.y, o.momentNeg.z);
+            *D.lf(3, g) = make_double2(o.forcePos.x, o.forcePos.y);
+            *D.lf(4, g) = make_double2(o.forcePos.z, o.momentPos.x);
+            *D.lf(5, g) = make_double2(o.momentPos.y, o.momentPos.z);
             if (L.strain > 100) atomicExch(&bar[1], 1u);
             if (intN) pdN = dtF;
             if (intP) pdP = dtF;
@@ -272,8 +272,8 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 if (vl[i] >= 0) {
-                    const double *f = D.lforce + 12 * (size_t)vl[i] + ((i & 1) ? 6 : 0);
-                    const double2 a = ldcg2(f), b = ldcg2(f + 2), c = ldcg2(f + 4);
+                    const int k0 = (i & 1) ? 3 : 0;
+                    const double2 a = __ldcg(D.lf(k0, vl[i])), b = __ldcg(D.lf(k0 + 1, vl[i])), c = __ldcg(D.lf(k0 + 2, vl[i]));
                     F += V3(a.x, a.y, b.x);
                     M += V3(b.y, c.x, c.y);
                 }
@@ -295,7 +295,7 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
                 if (all) r.flags |= VXF_ENABLE_ATTACH;
                 else r.flags &= ~VXF_ENABLE_ATTACH;
             }
-            store_pose(D.pose, v, r.pos, r.orient, tempe_next);
+            store_pose(D.pose, v, r.pos, r.orient, tempe_next, dtF);
         }
         t += dtF; // currentTime += dt (:352)
         done = s + 1;
@@ -335,21 +335,20 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
     }
     // ---- write the register-resident state back ----
     if (g >= 0) {
-        double *hw = D.lhist + 9 * (size_t)g;
-        hw[0] = L.pos2.x; hw[1] = L.pos2.y; hw[2] = L.pos2.z;
-        hw[3] = L.angle1v.x; hw[4] = L.angle1v.y; hw[5] = L.angle1v.z;
-        hw[6] = L.angle2v.x; hw[7] = L.angle2v.y; hw[8] = L.angle2v.z;
+        *D.lh(0, g) = make_double2(L.pos2.x, L.pos2.y);
+        *D.lh(1, g) = make_double2(L.pos2.z, L.angle1v.x);
+        *D.lh(2, g) = make_double2(L.angle1v.y, L.angle1v.z);
+        *D.lh(3, g) = make_double2(L.angle2v.x, L.angle2v.y);
+        *D.lh(4, g) = make_double2(L.angle2v.z, L.rest);
         D.lstrain[g] = make_float4(L.strain, L.maxStrain, L.strainOffset, L.stress);
         D.lstate[g] = L.state;
-        D.lrest[g] = L.rest;
     }
     if (v >= 0) {
-        double *mw = D.mom + 6 * (size_t)v;
-        mw[0] = r.linMom.x; mw[1] = r.linMom.y; mw[2] = r.linMom.z;
-        mw[3] = r.angMom.x; mw[4] = r.angMom.y; mw[5] = r.angMom.z;
+        *D.mo(0, v) = make_double2(r.linMom.x, r.linMom.y);
+        *D.mo(1, v) = make_double2(r.linMom.z, r.angMom.x);
+        *D.mo(2, v) = make_double2(r.angMom.y, r.angMom.z);
         D.vflags[v] = r.flags;
         D.tempe[v] = tempe;
-        if (vint && done > 0 && !(status == VX3_SIM_DIVERGED && done == 1)) D.prevdt[v] = dtF;
     }
     if (timing && threadIdx.x == 0) {
         unsigned long long *o = reinterpret_cast<unsigned long long *>(bar + 4) + 8 * blockIdx.x;

@@ -84,6 +84,13 @@ __device__ __forceinline__ float voxel_temperature(const SimC &S, double t, doub
     }
     return (float)cur;
 }
+__device__ __forceinline__ float voxel_temperature(double temp_amp, double temp_period, bool enable_expansion, double t, double phase) {
+    double cur = temp_amp * sin(2 * 3.1415926f * (t / temp_period + phase));
+    if (!enable_expansion) {
+        if (cur > 0) cur = 0;
+    }
+    return (float)cur;
+}
 __device__ __forceinline__ double base_size_axis(const VoxMatC &m, float tempe, int axis) { // VX3_Voxel.h:95-98
     return m.size[axis] * (1 + tempe * m.alphaCTE);
 }
