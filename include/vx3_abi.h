@@ -36,6 +36,9 @@ enum vx3_op {
 #define VX3_VOX_FLOOR_ENABLED         (1 << 2)
 #define VX3_VOX_FLOOR_STATIC_FRICTION (1 << 3)
 #define VX3_VOX_COLLISIONS_ENABLED    (1 << 5)
+/* not a reference bit: halo copy of a voxel another rank owns (slab decomposition of one body, vx3_batch_halo_*):
+ * never integrated, not counted in the centre of mass, its pose record is overwritten by the halo exchange */
+#define VX3_VOX_GHOST                 (1 << 7)
 
 /* src/old/types.h:6-8 (linkFlags) */
 #define VX3_LINK_LOCAL_VELOCITY_VALID (1 << 0)
@@ -332,6 +335,28 @@ int vx3_batch_last_timing(vx3_batch *b, double *ms, int64_t *launches);
  * milliseconds and launch count of kernel `index` (0, 1, ...); returns 1 past the last kernel. */
 int vx3_batch_set_profiling(vx3_batch *b, int on, int use_persistent);
 int vx3_batch_kernel_stats(vx3_batch *b, int index, char *name, int name_cap, double *total_ms, int64_t *launches);
+
+/* --- slab decomposition of ONE body over the GPUs of a box (BASELINE config 5; no reference twin: the reference only
+ * spreads independent files over devices, src/Executables/vx3_node_worker.cu:88-93).  Each rank creates a batch of one
+ * sub-model: the voxels of its slab, VX3_VOX_GHOST copies of the neighbour slabs' face voxels and every link with an
+ * owned end (host logic: voxcraft-sim_b200/parallel.py).  side 0 = lower neighbour, 1 = upper neighbour.
+ *   halo_setup    the face voxels this rank sends to that neighbour and the ghost voxels it receives from it (voxel
+ *                 indices of the sub-model; both ranks list them in the same order)
+ *   halo_export   64-byte CUDA IPC handle of this rank's receive block for that side
+ *   halo_connect  the handle the neighbour exported for its side facing this rank (+ its n_recv as a consistency check)
+ * After connect, every step ends with the exchange of the face voxels' 64-byte pose records inside the step stream
+ * (peer stores over NVLink + step-number flags, no host round trip).  All ranks must step in lock step with the same
+ * explicit dt (vx3_batch_step_dt).  com_sums: raw centre-of-mass sums over OWNED voxels, to be added across ranks. */
+int vx3_batch_halo_setup(vx3_batch *b, int side, int n_send, const int32_t *send_vox, int n_recv, const int32_t *recv_vox);
+int vx3_batch_halo_export(vx3_batch *b, int side, void *handle64);
+int vx3_batch_halo_connect(vx3_batch *b, int side, const void *peer_handle64, int peer_n_recv);
+int vx3_batch_halo_connect_local(vx3_batch *b, int side, vx3_batch *peer); /* both slabs driven by this process */
+int vx3_batch_com_sums(vx3_batch *b, int sim, double *out6);
+/* Queue k steps (explicit dt, or dt < 0 like vx3_batch_step) without waiting; vx3_batch_sync waits.  For one host thread
+ * that drives several batches whose step streams wait for each other (slabs of a decomposed body): queue the slabs in
+ * rounds of a few dozen steps — a round that overflows the driver's launch queue (~1000 launches) blocks the host on one
+ * slab while that slab waits for a neighbour whose round has not been queued yet. */
+int vx3_batch_step_async(vx3_batch *b, int64_t k, float dt);
 
 /* Sort results like sortResults (src/VX3/VX3_SimulationManager.cu:472,
  * VX3_SimulationResult.h:26-33): fitness descending, NaN last.  Host-only. */

@@ -5,6 +5,7 @@ the compiled library by ``vx3_abi_sizeof`` in tests/test_abi.py).  No physics li
 """
 import ctypes as C
 
+VOX_GHOST = 1 << 7  # include/vx3_abi.h VX3_VOX_GHOST
 VX3_PROG_COUNT = 10
 (PROG_STOP, PROG_FITNESS, PROG_FORCE_X, PROG_FORCE_Y, PROG_FORCE_Z, PROG_ATTACH_0, PROG_ATTACH_1, PROG_ATTACH_2,
  PROG_ATTACH_3, PROG_ATTACH_4) = range(10)
@@ -184,6 +185,12 @@ def declare_engine_api(lib):
     lib.vx3_batch_last_timing.argtypes = [vp, P(f64), P(i64)]
     lib.vx3_batch_set_profiling.argtypes = [vp, C.c_int, C.c_int]
     lib.vx3_batch_kernel_stats.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, P(f64), P(i64)]
+    lib.vx3_batch_halo_setup.argtypes = [vp, C.c_int, C.c_int, P(i32), C.c_int, P(i32)]
+    lib.vx3_batch_halo_export.argtypes = [vp, C.c_int, vp]
+    lib.vx3_batch_halo_connect.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.vx3_batch_com_sums.argtypes = [vp, C.c_int, P(f64)]
+    lib.vx3_batch_halo_connect_local.argtypes = [vp, C.c_int, vp]
+    lib.vx3_batch_step_async.argtypes = [vp, i64, f32]
     lib.vx3_abi_sizeof.argtypes = [C.c_char_p]
     lib.vx3_abi_sizeof.restype = C.c_size_t
     lib.vx3_sort_results.argtypes = [P(Result), C.c_int]
@@ -197,7 +204,9 @@ def declare_engine_api(lib):
 
 ENGINE_SYMBOLS = ["vx3_batch_create", "vx3_batch_run", "vx3_batch_step", "vx3_batch_step_dt", "vx3_batch_sync",
                   "vx3_batch_state", "vx3_batch_results", "vx3_batch_positions", "vx3_batch_recommended_dt",
-                  "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_last_error", "vx3_abi_version"]
+                  "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_batch_halo_setup",
+                  "vx3_batch_halo_export", "vx3_batch_halo_connect", "vx3_batch_halo_connect_local", "vx3_batch_com_sums",
+                  "vx3_batch_step_async", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_last_error", "vx3_abi_version"]
 WORKER_SYMBOLS = ["vx3_worker_run_vxt", "vx3_worker_run_files", "vx3_write_report"]
 MODEL_SYMBOLS = ["vx3_material_params_default", "vx3_env_params_default", "vx3_sim_options_default", "vx3_builder_create",
                  "vx3_builder_destroy", "vx3_builder_add_material", "vx3_builder_set_env", "vx3_builder_set_options",

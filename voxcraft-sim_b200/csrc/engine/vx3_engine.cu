@@ -15,6 +15,7 @@
 #include "../../../include/vx3_model.h"
 #include "vx3_kernels.cuh"
 #include "vx3_persistent.cuh"
+#include "vx3_halo.cuh"
 #include "vx3_history.h"
 
 using namespace vx3;
@@ -42,9 +43,9 @@ extern "C" size_t vx3_abi_sizeof(const char *name) {
 }
 
 // ------------------------------------------------------------------ per-kernel timing (bench hook)
-enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_COM, KC_TAIL, KC_PERSISTENT, KC_COUNT };
+enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_COM, KC_TAIL, KC_PERSISTENT, KC_HALO, KC_COUNT };
 static const char *const kKernelNames[KC_COUNT] = {"k_links", "k_voxels", "k_grid_count", "k_grid_scan", "k_grid_fill", "k_contact", "k_resolve",
-                                                   "k_detach", "k_surface", "k_secondary", "k_com_partial", "k_tail", "k_persistent"};
+                                                   "k_detach", "k_surface", "k_secondary", "k_com_partial", "k_tail", "k_persistent", "k_halo"};
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> ev; // pairs
@@ -102,6 +103,8 @@ struct vx3_batch {
     long long launches = 0;
     bool link_smtab = true, vox_smtab = true; // material tables fit the kernels' shared-memory copies
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
+    Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
+    bool any_ghost = false;
     PersistentPlan pplan; // on-chip path for a single small collision-free body
     bool use_persistent = true;
 
@@ -463,6 +466,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 mom2[idx_mo(2, g)] = make_double2(m.ang_mom[3 * i + 1], m.ang_mom[3 * i + 2]);
             }
             vflags[g] = (m.vox_flags[i] & VXF_BOOLSTATE_MASK) | VXF_ENABLE_ATTACH;
+            b->any_ghost |= (m.vox_flags[i] & VX3_VOX_GHOST) != 0;
             vmat[g] = vm_global[m.vox_mat[i]];
             vsim[g] = s;
             if (m.phase_offset) phase[g] = m.phase_offset[i];
@@ -629,7 +633,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         if (od < 1e-10) od = 1e-10;
         b->hdt[s] = (float)(b->simc[s].dt_frac * od);
     }
-    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary, any_cilia, prop, lends, vlinks);
+    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost, any_cilia, prop, lends, vlinks);
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaGetLastError());
     *out = b;
@@ -641,6 +645,8 @@ extern "C" void vx3_batch_destroy(vx3_batch *b) {
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     persistent_free(b->pplan);
+    for (int sd = 0; sd < 2; sd++)
+        if (b->halo.side[sd].peer_open) cudaIpcCloseMemHandle(b->halo.side[sd].peer_flag);
     for (auto &e : b->prof.ev) cudaEventDestroy(e);
     for (void *p : b->allocs) cudaFree(p);
     if (b->ev0) cudaEventDestroy(b->ev0);
@@ -743,6 +749,22 @@ static void launch_step(vx3_batch *b, bool check_stop) {
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
     else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
+    if (b->halo.on) { // face poses to the neighbour slabs, ghost poses from them (vx3_halo.cuh)
+        const unsigned int step1 = (unsigned int)(b->hsteps + 1);
+        const int parity = (int)(b->hsteps & 1);
+        for (int sd = 0; sd < 2; sd++) {
+            HaloSide &h = b->halo.side[sd];
+            if (h.n_send > 0 && (h.peer_open || h.peer_local))
+                LAUNCH(KC_HALO, k_halo_send, std::min(64, cdiv(4 * h.n_send, VX3_HALO_BLOCK)), VX3_HALO_BLOCK, D.pose, h.send_idx, h.n_send, h.peer_buf, h.peer_flag,
+                       h.send_count, step1, parity);
+        }
+        for (int sd = 0; sd < 2; sd++) {
+            HaloSide &h = b->halo.side[sd];
+            if (h.n_recv > 0 && (h.peer_open || h.peer_local))
+                LAUNCH(KC_HALO, k_halo_recv, std::min(64, cdiv(4 * h.n_recv, VX3_HALO_BLOCK)), VX3_HALO_BLOCK, D.pose, h.recv_idx, h.n_recv, h.recv_buf, h.recv_flag, step1,
+                       parity, b->halo.err);
+        }
+    }
     b->hsteps++;
 }
 
@@ -775,6 +797,11 @@ static int check_device_errors(vx3_batch *b) {
     CK(cudaStreamSynchronize(b->stream));
     for (int s = 0; s < b->nsims; s++)
         if (h[s].err) return fail(h[s].err, "simulation " + std::to_string(s) + ": device-side capacity/consistency error (link pool, partner list or attach candidates)");
+    if (b->halo.on) {
+        int herr = 0;
+        CK(cudaMemcpy(&herr, b->halo.err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) return fail(VX3_ERR_CUDA, "halo exchange: a neighbour rank did not publish its face poses in time");
+    }
     return VX3_OK;
 }
 
@@ -799,10 +826,23 @@ extern "C" int vx3_batch_step_dt(vx3_batch *b, int64_t k, float dt) {
 
 extern "C" int vx3_batch_step(vx3_batch *b, int64_t k) { return vx3_batch_step_dt(b, k, -1.0f); }
 
+// queue k steps without waiting for them (vx3_batch_sync waits): lets one host thread drive several batches whose
+// step streams depend on each other (slabs of a decomposed body)
+extern "C" int vx3_batch_step_async(vx3_batch *b, int64_t k, float dt) {
+    if (!b || k < 0) return fail(VX3_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(b->device));
+    set_dt(b, dt);
+    int rc = advance(b, k, false);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return VX3_OK;
+}
+
 extern "C" int vx3_batch_sync(vx3_batch *b) {
     if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
     CK(cudaSetDevice(b->device));
     CK(cudaStreamSynchronize(b->stream));
+    if (b->halo.on) return check_device_errors(b); // a halo wait that ran into its spin limit must not pass silently
     return VX3_OK;
 }
 
@@ -1105,6 +1145,107 @@ extern "C" void vx3_sort_results(vx3_result *r, int n) {
         if (bn) return true;
         return a.fitness_score > b.fitness_score;
     });
+}
+
+// ------------------------------------------------------------------ slab decomposition (vx3_halo.cuh)
+// One receive block per side: [2 flags, 128 bytes apart][2 parities][n_recv][8] doubles, one cudaMalloc, one IPC handle.
+static const size_t kHaloFlagBytes = 256;
+
+extern "C" int vx3_batch_halo_setup(vx3_batch *b, int side, int n_send, const int32_t *send_vox, int n_recv, const int32_t *recv_vox) {
+    if (!b || side < 0 || side > 1 || n_send < 0 || n_recv < 0) return fail(VX3_ERR_INVALID, "bad arguments");
+    if (b->nsims != 1) return fail(VX3_ERR_INVALID, "halo exchange applies to a batch of ONE decomposed body");
+    if (b->any_collide) return fail(VX3_ERR_INVALID, "halo exchange: collisions / attach are not supported across slabs");
+    CK(cudaSetDevice(b->device));
+    HaloSide &h = b->halo.side[side];
+    if (h.recv_flag) return fail(VX3_ERR_INVALID, "halo side already set up");
+    const int nv = b->simc[0].nvox;
+    std::vector<int32_t> si(send_vox, send_vox + n_send), ri(recv_vox, recv_vox + n_recv);
+    for (int v : si) if (v < 0 || v >= nv) return fail(VX3_ERR_INVALID, "halo send index out of range");
+    for (int v : ri) if (v < 0 || v >= nv) return fail(VX3_ERR_INVALID, "halo receive index out of range");
+    int rc;
+    if ((rc = b->upload(&h.send_idx, si))) return rc;
+    if ((rc = b->upload(&h.recv_idx, ri))) return rc;
+    if ((rc = b->alloc(&h.send_count, 1))) return rc;
+    unsigned char *blk = nullptr;
+    if ((rc = b->alloc(&blk, kHaloFlagBytes + sizeof(double) * 16 * (size_t)std::max(n_recv, 1)))) return rc;
+    h.recv_flag = reinterpret_cast<unsigned int *>(blk);
+    h.recv_buf = reinterpret_cast<double *>(blk + kHaloFlagBytes);
+    h.n_send = n_send;
+    h.n_recv = n_recv;
+    if (!b->halo.err && (rc = b->alloc(&b->halo.err, 1))) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_halo_export(vx3_batch *b, int side, void *handle64) {
+    if (!b || side < 0 || side > 1 || !handle64) return fail(VX3_ERR_INVALID, "bad arguments");
+    HaloSide &h = b->halo.side[side];
+    if (!h.recv_flag) return fail(VX3_ERR_INVALID, "halo side not set up");
+    CK(cudaSetDevice(b->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, h.recv_flag));
+    memcpy(handle64, &hd, 64);
+    return VX3_OK;
+}
+
+// peer_handle64: what the neighbour on this side exported for ITS side facing me; peer_n_recv must equal my n_send
+extern "C" int vx3_batch_halo_connect(vx3_batch *b, int side, const void *peer_handle64, int peer_n_recv) {
+    if (!b || side < 0 || side > 1 || !peer_handle64) return fail(VX3_ERR_INVALID, "bad arguments");
+    HaloSide &h = b->halo.side[side];
+    if (!h.recv_flag) return fail(VX3_ERR_INVALID, "halo side not set up");
+    if (peer_n_recv != h.n_send) return fail(VX3_ERR_INVALID, "halo: the neighbour expects a different number of face voxels than this rank sends");
+    CK(cudaSetDevice(b->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, peer_handle64, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h.peer_flag = reinterpret_cast<unsigned int *>(p);
+    h.peer_buf = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(p) + kHaloFlagBytes);
+    h.peer_open = true;
+    b->halo.on = true;
+    b->use_persistent = false;
+    return VX3_OK;
+}
+
+// same-process variant of halo_connect (one host process driving both slabs, e.g. two batches on one device in the tests)
+extern "C" int vx3_batch_halo_connect_local(vx3_batch *b, int side, vx3_batch *peer) {
+    if (!b || !peer || side < 0 || side > 1) return fail(VX3_ERR_INVALID, "bad arguments");
+    HaloSide &h = b->halo.side[side];
+    HaloSide &ph = peer->halo.side[1 - side];
+    if (!h.recv_flag || !ph.recv_flag) return fail(VX3_ERR_INVALID, "halo side not set up");
+    if (ph.n_recv != h.n_send) return fail(VX3_ERR_INVALID, "halo: the neighbour expects a different number of face voxels than this rank sends");
+    if (b->device != peer->device) {
+        CK(cudaSetDevice(b->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(VX3_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    h.peer_flag = ph.recv_flag;
+    h.peer_buf = ph.recv_buf;
+    h.peer_open = false; // nothing to close
+    h.peer_local = true;
+    b->halo.on = true;
+    b->use_persistent = false;
+    return VX3_OK;
+}
+
+// raw centre-of-mass sums of one simulation over its OWNED voxels: sum m*x, m*y, m*z, sum m, sum |pos - initial pos|, count
+// (a decomposed body's ranks add these up before dividing, updateCurrentCenterOfMass VX3_VoxelyzeKernel.cu:477-493)
+extern "C" int vx3_batch_com_sums(vx3_batch *b, int sim, double *out6) {
+    if (!b || sim < 0 || sim >= b->nsims || !out6) return fail(VX3_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(b->device));
+    k_com_partial<<<b->D.nchunks, VX3_BLOCK, 0, b->stream>>>(b->D);
+    b->launches++;
+    const SimC &S = b->simc[sim];
+    std::vector<double> part;
+    int rc = d2h(b, part, (const double *)b->D.com_part, 6 * (size_t)S.chunk_off, 6 * (size_t)S.nchunks);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    for (int k = 0; k < 6; k++) out6[k] = 0;
+    for (int c = 0; c < S.nchunks; c++)
+        for (int k = 0; k < 6; k++) out6[k] += part[6 * (size_t)c + k];
+    return VX3_OK;
 }
 
 #include "vx3_history.inl"

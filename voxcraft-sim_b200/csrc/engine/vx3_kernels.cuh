@@ -310,6 +310,7 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MI
         float tempe_next = tempe;
         if ((hot_flags & SHF_THERMAL) && !(r.flags & VXF_REMOVED) && !(m.thermal_on_after > tnext) && !m.fixed)
             tempe_next = voxel_temperature(temp_amp, temp_period, (hot_flags & SHF_EXPANSION) != 0, tnext, phase);
+        if (r.flags & VX3_VOX_GHOST) continue; // a neighbour slab owns this voxel: its pose record arrives with the halo exchange
         if ((r.flags & VXF_REMOVED) || m.fixed) {
             if (tempe_next != tempe) D.pose[8 * (size_t)v + 7] = pack_tp(tempe_next, pd_old);
             continue;
@@ -780,7 +781,7 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_com_partial(Dev D) {
     for (int i = threadIdx.x; i < ck.vcount; i += blockDim.x) {
         const int v = ck.vstart + i;
         const VoxMatC &m = D.vmat_tab[D.vmat[v]];
-        if (!m.is_measured) continue;
+        if (!m.is_measured || (D.vflags[v] & VX3_VOX_GHOST)) continue;
         const V3 p = load_pos(D.pose, v);
         const double mass = m.mass;
         a[0] += p.x * mass; a[1] += p.y * mass; a[2] += p.z * mass; a[3] += mass;

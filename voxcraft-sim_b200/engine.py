@@ -94,6 +94,34 @@ class Batch:
             i += 1
         return out
 
+    # ---- slab decomposition of one body (include/vx3_abi.h vx3_batch_halo_*) ----
+    def halo_setup(self, side, send_vox, recv_vox):
+        import numpy as np
+        sv = np.ascontiguousarray(send_vox, dtype=np.int32)
+        rv = np.ascontiguousarray(recv_vox, dtype=np.int32)
+        self._check(self.lib.vx3_batch_halo_setup(self.h, side, len(sv), sv.ctypes.data_as(C.POINTER(C.c_int32)), len(rv),
+                                                  rv.ctypes.data_as(C.POINTER(C.c_int32))), "vx3_batch_halo_setup")
+
+    def halo_export(self, side):
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.vx3_batch_halo_export(self.h, side, C.cast(buf, C.c_void_p)), "vx3_batch_halo_export")
+        return bytes(buf)
+
+    def halo_connect(self, side, handle, peer_n_recv):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._check(self.lib.vx3_batch_halo_connect(self.h, side, C.cast(buf, C.c_void_p), peer_n_recv), "vx3_batch_halo_connect")
+
+    def halo_connect_local(self, side, peer):
+        self._check(self.lib.vx3_batch_halo_connect_local(self.h, side, peer.h), "vx3_batch_halo_connect_local")
+
+    def step_async(self, k, dt=-1.0):
+        self._check(self.lib.vx3_batch_step_async(self.h, k, dt), "vx3_batch_step_async")
+
+    def com_sums(self, sim=0):
+        out = (C.c_double * 6)()
+        self._check(self.lib.vx3_batch_com_sums(self.h, sim, out), "vx3_batch_com_sums")
+        return list(out)
+
     def close(self):
         if self.h:
             self.lib.vx3_batch_destroy(self.h)
