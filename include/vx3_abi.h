@@ -262,6 +262,8 @@ typedef struct vx3_state_view {
     int32_t *link_flags;    /* bit0 LOCAL_VELOCITY_VALID, bit1 smallAngle, bit2 isDetached,
                                bit3 removed, bits 8.. isNewLink countdown */
     double *link_rest_length;
+    double *signal;         /* [n_voxels][6]: localSignal, localSignaldt, inactiveUntil, packmakerNextPulse,
+                               d_signal.value, d_signal.activeTime (VX3_Voxel.h:304-309); zeros when EnableSignals=0 */
 } vx3_state_view;
 
 #define VX3_LINKSTATE_LOCAL_VELOCITY_VALID (1 << 0)
@@ -362,7 +364,13 @@ int vx3_batch_step_async(vx3_batch *b, int64_t k, float dt);
  * VX3_SimulationResult.h:26-33): fitness descending, NaN last.  Host-only. */
 void vx3_sort_results(vx3_result *r, int n);
 
+/* Destroying a batch returns its device arena, pinned staging buffer, stream and events to a small per-process cache
+ * (at most two idle sets per device) that the next vx3_batch_create on that device reuses: a worker that evaluates one
+ * batch after another pays cudaMalloc / cudaMallocHost / cudaFree once.  (The reference leaks by design instead:
+ * src/old/VX3_MemoryCleaner.h:14-18, src/VX3/VX3_VoxelyzeKernel.cu:522.) */
 void vx3_batch_destroy(vx3_batch *b);
+/* Frees every idle cached arena / staging buffer / stream now. */
+void vx3_engine_trim(void);
 
 /* Thread-local description of the last error returned on this thread. */
 const char *vx3_last_error(void);

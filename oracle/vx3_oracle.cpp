@@ -300,7 +300,9 @@ struct OVoxel {
     V3 contactForce, baseCiliaForce, shiftCiliaForce, CiliaForce;
     bool enableAttach = true;
     bool removed = false;
-    double localSignal = 0;
+    // signals (VX3_Voxel.h:304-309): d_signal {value, activeTime}, localSignal(+dt), inactiveUntil, packmakerNextPulse
+    double localSignal = 0, localSignaldt = 0, inactiveUntil = 0, packmakerNextPulse = 0;
+    double sigValue = 0, sigActiveTime = 0;
 };
 
 struct OLink {
@@ -663,6 +665,59 @@ struct vx3o_sim {
         }
     }
 
+    // ---- signals (VX3_Voxel.cu:279-348).  The reference runs these at the end of every voxel's timeStep with the
+    // voxels in parallel (racy: a voxel writes its neighbours' state).  Canonical order here and on the GPU: the
+    // voxels take their turns in ascending voxel index.
+    void receiveSignal(OVoxel &v, double signalValue, double activeTime, bool force) { // :315-335
+        const OMat &m = vm(v);
+        if (!force) {
+            if (v.inactiveUntil > activeTime) return;
+        }
+        if (signalValue < 0.1) return;
+        v.inactiveUntil = activeTime + m.m.inactive_period;
+        v.localSignal = signalValue;
+        v.sigValue = signalValue * m.m.signal_value_decay;
+        if (v.sigValue < 0.1) v.sigValue = 0;
+        v.sigActiveTime = activeTime;
+    }
+    void propagateSignal(int vi, double t) { // :336-362
+        OVoxel &v = vox[vi];
+        const OMat &m = vm(v);
+        if (v.sigActiveTime > t) return;
+        if (v.sigValue < 0.1) return;
+        for (int i = 0; i < 6; i++) {
+            if (v.links[i] >= 0) {
+                const OLink &l = links[v.links[i]];
+                const int other = (l.vNeg == vi) ? l.vPos : l.vNeg;
+                receiveSignal(vox[other], v.sigValue, t + m.m.signal_time_delay, false);
+            }
+        }
+        v.sigValue = 0;
+        v.sigActiveTime = 0;
+        v.inactiveUntil = t + 2 * m.m.signal_time_delay + m.m.inactive_period;
+    }
+    void packMaker(OVoxel &v, double t) { // :304-313
+        const OMat &m = vm(v);
+        if (!m.m.is_pacemaker) return;
+        if (v.packmakerNextPulse > t) return;
+        receiveSignal(v, 100, t, true);
+        v.packmakerNextPulse = t + m.m.pacemaker_period;
+    }
+    void localSignalDecay(OVoxel &v, double t) { // :291-302
+        if (v.localSignaldt > t) return;
+        if (v.localSignal < 0.1) v.localSignal = 0;
+        else {
+            v.localSignal = v.localSignal * 0.9;
+            v.localSignaldt = t + 0.01;
+        }
+    }
+    // does timeStep reach its end for this voxel (:162-174 early returns; gpu_update_voxels :586-589 skips)?
+    bool runsSignals(const OVoxel &v, double dt) const {
+        if (v.removed || vm(v).m.fixed || dt == 0.0) return false;
+        if (v.ext >= 0 && exts[v.ext].isFixedAll()) return false;
+        return true;
+    }
+
     // ---- kernel-level ----
     double recommendedTimeStep() { // VX3_VoxelyzeKernel.cu:184-217
         double MaxFreq2 = 0.0f;
@@ -874,6 +929,12 @@ struct vx3o_sim {
             bool all = true;
             for (int c = 0; c < 5 && all; c++) all = evalProg(VX3_PROG_ATTACH_0 + c, v.pos.x, v.pos.y, v.pos.z, 1.0) > 0;
             if (all) v.enableAttach = true;
+            if (opt.enable_signals && runsSignals(v, dtD)) { // VX3_Voxel.cu:270-275
+                const int vi = (int)(&v - &vox[0]);
+                propagateSignal(vi, currentTime);
+                packMaker(v, currentTime);
+                localSignalDecay(v, currentTime);
+            }
         }
         if (!cpu_lib_mode) {
             int CycleStep = int(opt.temp_period / dt);
@@ -1004,7 +1065,13 @@ void vx3o_sim::handle_collision_attachment(int i1, int i2) {
         cache2 = -force;
         voxel1.contactForce += cache1;
         voxel2.contactForce += cache2;
-        if ((m1.m.is_target && !m2.m.is_target) || (m2.m.is_target && !m1.m.is_target)) collisionCount++;
+        if ((m1.m.is_target && !m2.m.is_target) || (m2.m.is_target && !m1.m.is_target)) {
+            collisionCount++;
+            if (opt.enable_signals) { // :719-725: the non-target voxel of the pair fires
+                if (m1.m.is_target) receiveSignal(voxel2, 100, currentTime, true);
+                else receiveSignal(voxel1, 100, currentTime, true);
+            }
+        }
     }
     if (!voxel1.enableAttach || !voxel2.enableAttach) return;
     if (m1.m.fixed || m2.m.fixed) return;
@@ -1215,6 +1282,10 @@ int vx3o_state(vx3o_sim *s, vx3_state_view *w) {
         if (w->vox_flags) w->vox_flags[i] = v.boolStates;
         if (w->temp) w->temp[i] = v.tempe;
         if (w->vox_links) for (int k = 0; k < 6; k++) w->vox_links[6 * i + k] = v.links[k];
+        if (w->signal) {
+            double *o = w->signal + 6 * (size_t)i;
+            o[0] = v.localSignal; o[1] = v.localSignaldt; o[2] = v.inactiveUntil; o[3] = v.packmakerNextPulse; o[4] = v.sigValue; o[5] = v.sigActiveTime;
+        }
     }
     for (int i = 0; i < nl; i++) {
         const OLink &l = s->links[i];

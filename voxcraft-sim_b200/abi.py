@@ -107,7 +107,7 @@ class StateView(C.Structure):
                 ("link_pos2", P(f64)), ("link_angle1v", P(f64)), ("link_angle2v", P(f64)),
                 ("link_force_neg", P(f64)), ("link_force_pos", P(f64)), ("link_moment_neg", P(f64)), ("link_moment_pos", P(f64)),
                 ("link_strain", P(f32)), ("link_max_strain", P(f32)), ("link_strain_offset", P(f32)), ("link_stress", P(f32)),
-                ("link_flags", P(i32)), ("link_rest_length", P(f64))]
+                ("link_flags", P(i32)), ("link_rest_length", P(f64)), ("signal", P(f64))]
 
 
 class RunOpts(C.Structure):
@@ -197,6 +197,8 @@ def declare_engine_api(lib):
     lib.vx3_sort_results.restype = None
     lib.vx3_batch_destroy.argtypes = [vp]
     lib.vx3_batch_destroy.restype = None
+    lib.vx3_engine_trim.argtypes = []
+    lib.vx3_engine_trim.restype = None
     lib.vx3_last_error.restype = C.c_char_p
     lib.vx3_abi_version.restype = C.c_int
     return lib
@@ -206,7 +208,8 @@ ENGINE_SYMBOLS = ["vx3_batch_create", "vx3_batch_run", "vx3_batch_step", "vx3_ba
                   "vx3_batch_state", "vx3_batch_results", "vx3_batch_positions", "vx3_batch_recommended_dt",
                   "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_batch_halo_setup",
                   "vx3_batch_halo_export", "vx3_batch_halo_connect", "vx3_batch_halo_connect_local", "vx3_batch_com_sums",
-                  "vx3_batch_step_async", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_last_error", "vx3_abi_version"]
+                  "vx3_batch_step_async", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_engine_trim", "vx3_last_error",
+                  "vx3_abi_version"]
 WORKER_SYMBOLS = ["vx3_worker_run_vxt", "vx3_worker_run_files", "vx3_write_report"]
 MODEL_SYMBOLS = ["vx3_material_params_default", "vx3_env_params_default", "vx3_sim_options_default", "vx3_builder_create",
                  "vx3_builder_destroy", "vx3_builder_add_material", "vx3_builder_set_env", "vx3_builder_set_options",

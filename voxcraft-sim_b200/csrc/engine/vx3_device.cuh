@@ -64,6 +64,12 @@ struct LinkMatC {
     int32_t _pad;
 };
 
+// Signal constants of a voxel material (VX3_Material.h:151-161), same index as VoxMatC
+struct SigMatC {
+    double pacemaker_period, value_decay, time_delay, inactive_period;
+    int32_t is_pacemaker, _pad;
+};
+
 struct ExtC { // VX3_External
     int32_t dof;
     float force[3], moment[3];
@@ -81,7 +87,7 @@ struct SimC {
     int32_t prog_off[VX3_PROG_COUNT], prog_n[VX3_PROG_COUNT];
     int32_t tgt_off, ntgt;
     int32_t chunk_off, nchunks; // CoM reduction chunks
-    int32_t secondary_experiment, _pad0;
+    int32_t secondary_experiment, enable_signals;
     double reinit_after; // ReinitializeInitialPositionAfterThisManySeconds
     double temp_amp, temp_period;
     double vox_size, pair_radius; // MaxDistInVoxelLengthsToCountAsPair * voxSize (0 = closeness off)
@@ -95,6 +101,7 @@ struct SimC {
 #define SHF_CILIA (1 << 2)
 #define SHF_FORCE_FIELD (1 << 3)
 #define SHF_ATTACH_COND (1 << 4)
+#define SHF_SIGNALS (1 << 5)
 
 // per-simulation dynamic scalars (VX3_VoxelyzeKernel members that change during the run).  The first 48 bytes are the
 // "hot" block every link / voxel of the simulation needs each step; the streaming kernels prefetch it with three
@@ -169,6 +176,12 @@ struct Dev {
     double *contact;  // [nvox][3] (NULL if no sim collides)
     const double *base_cilia, *shift_cilia; // [nvox][3] or NULL
     double *initpos;  // [nvox][3]
+    // signals (NULL unless a simulation has EnableSignals): [nvox][6] = localSignal, localSignaldt, inactiveUntil,
+    // packmakerNextPulse, d_signal.value, d_signal.activeTime (VX3_Voxel.h:304-309); sprop[nvox] = the value a voxel
+    // propagates to its neighbours in the current step (0 = none), see k_signals
+    double *sig;
+    double *sprop;
+    const SigMatC *smat_tab;
     // links
     int2 *lends;      // (vneg, vpos) global voxel indices; x<0 = empty pool slot
     int32_t *lstate;

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -43,9 +44,9 @@ extern "C" size_t vx3_abi_sizeof(const char *name) {
 }
 
 // ------------------------------------------------------------------ per-kernel timing (bench hook)
-enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_COM, KC_TAIL, KC_PERSISTENT, KC_HALO, KC_COUNT };
+enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_SIGNALS, KC_COM, KC_TAIL, KC_PERSISTENT, KC_HALO, KC_COUNT };
 static const char *const kKernelNames[KC_COUNT] = {"k_links", "k_voxels", "k_grid_count", "k_grid_scan", "k_grid_fill", "k_contact", "k_resolve",
-                                                   "k_detach", "k_surface", "k_secondary", "k_com_partial", "k_tail", "k_persistent", "k_halo"};
+                                                   "k_detach", "k_surface", "k_secondary", "k_signals", "k_com_partial", "k_tail", "k_persistent", "k_halo"};
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> ev; // pairs
@@ -76,13 +77,159 @@ struct Profiler {
     }
 };
 
+// ------------------------------------------------------------------ device arena + resource cache
+// One batch = ONE device allocation and ONE host->device copy: every array of the batch is a 256-byte aligned slice of
+// an arena, staged in one pinned host buffer and uploaded with a single cudaMemcpyAsync (the reference pays one
+// cudaMalloc + one blocking cudaMemcpy per voxel/link/material object, VX3_VoxelyzeKernel.cu:107-160).  Arenas, their
+// pinned staging buffers, streams and events are kept in a small per-process cache when a batch is destroyed, so that a
+// worker which evaluates one batch after another (vx3_node_worker) pays cudaMalloc/cudaFree/cudaMallocHost once.
+struct Resources {
+    int device = -1;
+    char *d = nullptr; // device arena
+    char *h = nullptr; // pinned staging
+    size_t dcap = 0, hcap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+static std::mutex g_res_mu;
+static std::vector<Resources> g_res_idle;
+static const size_t kMaxIdlePerDevice = 2;
+
+static void resources_free(Resources &r) {
+    if (r.d) cudaFree(r.d);
+    if (r.h) cudaFreeHost(r.h);
+    if (r.ev0) cudaEventDestroy(r.ev0);
+    if (r.ev1) cudaEventDestroy(r.ev1);
+    if (r.stream) cudaStreamDestroy(r.stream);
+    r = Resources();
+}
+
+// the current device must be `device`
+static int resources_acquire(int device, size_t dbytes, size_t hbytes, Resources &out) {
+    out = Resources();
+    {
+        std::lock_guard<std::mutex> lk(g_res_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_res_idle.size(); i++) {
+            const Resources &r = g_res_idle[i];
+            if (r.device != device) continue;
+            if (best < 0) best = (int)i;
+            else { // prefer one that already fits, then the smallest such; otherwise the largest (least to regrow)
+                const Resources &q = g_res_idle[best];
+                const bool rf = r.dcap >= dbytes && r.hcap >= hbytes, qf = q.dcap >= dbytes && q.hcap >= hbytes;
+                if ((rf && !qf) || (rf == qf && (rf ? r.dcap < q.dcap : r.dcap > q.dcap))) best = (int)i;
+            }
+        }
+        if (best >= 0) {
+            out = g_res_idle[best];
+            g_res_idle.erase(g_res_idle.begin() + best);
+        }
+    }
+    out.device = device;
+    if (!out.stream) {
+        CK(cudaStreamCreateWithFlags(&out.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&out.ev0));
+        CK(cudaEventCreate(&out.ev1));
+    }
+    if (out.dcap < dbytes) {
+        if (out.d) cudaFree(out.d);
+        out.d = nullptr;
+        out.dcap = 0;
+        const size_t want = (dbytes + (dbytes >> 3) + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1); // headroom so similar batches reuse it
+        cudaError_t e = cudaMalloc((void **)&out.d, want);
+        if (e != cudaSuccess) {
+            resources_free(out);
+            return fail(VX3_ERR_CUDA, std::string("cudaMalloc (batch arena): ") + cudaGetErrorString(e));
+        }
+        out.dcap = want;
+    }
+    if (out.hcap < hbytes) {
+        if (out.h) cudaFreeHost(out.h);
+        out.h = nullptr;
+        out.hcap = 0;
+        const size_t want = (hbytes + (hbytes >> 3) + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+        cudaError_t e = cudaMallocHost((void **)&out.h, want);
+        if (e != cudaSuccess) {
+            resources_free(out);
+            return fail(VX3_ERR_CUDA, std::string("cudaMallocHost (staging): ") + cudaGetErrorString(e));
+        }
+        out.hcap = want;
+    }
+    return VX3_OK;
+}
+
+static void resources_release(Resources &r) {
+    if (!r.stream && !r.d && !r.h) return;
+    std::vector<Resources> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_res_mu);
+        g_res_idle.push_back(r);
+        size_t same = 0;
+        for (const Resources &q : g_res_idle) same += q.device == r.device;
+        while (same > kMaxIdlePerDevice) { // drop the smallest idle arena of this device
+            int worst = -1;
+            for (size_t i = 0; i < g_res_idle.size(); i++)
+                if (g_res_idle[i].device == r.device && (worst < 0 || g_res_idle[i].dcap < g_res_idle[worst].dcap)) worst = (int)i;
+            drop.push_back(g_res_idle[worst]);
+            g_res_idle.erase(g_res_idle.begin() + worst);
+            same--;
+        }
+    }
+    r = Resources();
+    for (Resources &q : drop) {
+        cudaSetDevice(q.device);
+        resources_free(q);
+    }
+}
+
+// frees every cached arena / staging buffer / stream (idle ones only; live batches keep theirs)
+extern "C" void vx3_engine_trim(void) {
+    std::vector<Resources> all;
+    {
+        std::lock_guard<std::mutex> lk(g_res_mu);
+        all.swap(g_res_idle);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (Resources &q : all) {
+        cudaSetDevice(q.device);
+        resources_free(q);
+    }
+    cudaSetDevice(cur);
+}
+
+// slices of the arena, planned first (sizes), then staged + uploaded in one go
+struct ArenaPlan {
+    struct Item {
+        void **field;
+        const void *src;
+        size_t bytes, off;
+    };
+    std::vector<Item> up, zero;
+    template <class T, class U> void upload(T **field, const std::vector<U> &h) {
+        static_assert(sizeof(T) == sizeof(U), "element size");
+        if (h.empty()) zero.push_back(Item{(void **)field, nullptr, sizeof(T), 0});
+        else up.push_back(Item{(void **)field, h.data(), h.size() * sizeof(U), 0});
+    }
+    template <class T> void zeroed(T **field, size_t n) { zero.push_back(Item{(void **)field, nullptr, std::max<size_t>(n, 1) * sizeof(T), 0}); }
+    size_t up_bytes = 0, total = 0;
+    void layout() {
+        size_t o = 0;
+        for (Item &i : up) { i.off = o; o += (i.bytes + 255) & ~(size_t)255; }
+        up_bytes = o;
+        for (Item &i : zero) { i.off = o; o += (i.bytes + 255) & ~(size_t)255; }
+        total = std::max<size_t>(o, 256);
+    }
+};
+
 // ------------------------------------------------------------------ batch object
 struct vx3_batch {
     Profiler prof;
     int device = 0;
+    Resources res; // arena, pinned staging, stream, events (returned to the cache on destroy)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<void *> allocs;
+    std::vector<void *> allocs; // allocations made after construction (halo buffers)
     Dev D;
     int nsims = 0;
     std::vector<SimC> simc;
@@ -95,7 +242,7 @@ struct vx3_batch {
     std::vector<vx3_sim_options> opts;
     std::vector<std::vector<vx3_voxel_material>> h_vmats; // per sim host copy (data pointers cleared) for the history writer
     std::vector<LinkMatC> h_lmat_tab;
-    bool any_collide = false, any_sticky = false, any_detach = false, any_secondary = false;
+    bool any_collide = false, any_sticky = false, any_detach = false, any_secondary = false, any_signals = false;
     long long hsteps = 0; // doTimeStep calls issued so far (all running simulations advance together)
     std::vector<float> hdt; // per-sim dt in use
     double last_ms = 0;
@@ -202,7 +349,6 @@ static int validate_model(const vx3_model_desc &m, int idx) {
         if (m.vox_links[6 * m.link_vneg[i] + 2 * a] != i || m.vox_links[6 * m.link_vpos[i] + 2 * a + 1] != i)
             return bad("vox_links does not hold the link in slot 2*axis of its negative end and 2*axis+1 of its positive end");
     }
-    if (m.opt.enable_signals) return bad("EnableSignals is not supported by this engine yet");
     for (int s = 0; s < VX3_PROG_COUNT; s++) {
         if (m.prog[s].n < 0 || m.prog[s].n > VX3_MAX_TOKENS) return bad("token program too long");
         if (m.prog[s].n > 0 && !m.prog[s].tok) return bad("token program pointer missing");
@@ -242,12 +388,10 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         vx3_batch_destroy(b);
         return rc;
     };
-    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail(VX3_ERR_CUDA, "cudaStreamCreate failed"));
-    cudaEventCreate(&b->ev0);
-    cudaEventCreate(&b->ev1);
 
     // ---- global tables ----
     std::vector<VoxMatC> vmat_tab;
+    std::vector<SigMatC> smat_tab; // same index as vmat_tab
     std::vector<LinkMatC> lmat_tab;
     std::vector<float> strain_pool, stress_pool;
     std::map<std::string, int> vmat_index, lmat_index;
@@ -302,6 +446,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         b->any_sticky |= collide && sticky;
         b->any_detach |= m.opt.enable_detach != 0;
         b->any_secondary |= m.opt.secondary_experiment != 0;
+        b->any_signals |= m.opt.enable_signals != 0;
     }
 
     const size_t VS = (nvox + 31) / 32 * 32, LS = (std::max<size_t>(nslots, 1) + 31) / 32 * 32;
@@ -391,10 +536,19 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 }
                 vm.self_lmat = found;
             }
+            SigMatC sg;
+            memset(&sg, 0, sizeof(sg));
+            sg.pacemaker_period = in.pacemaker_period;
+            sg.value_decay = in.signal_value_decay;
+            sg.time_delay = in.signal_time_delay;
+            sg.inactive_period = in.inactive_period;
+            sg.is_pacemaker = in.is_pacemaker != 0;
             std::string key = blob(&vm, sizeof(vm));
+            if (m.opt.enable_signals) key += blob(&sg, sizeof(sg));
             auto it = vmat_index.find(key);
             if (it == vmat_index.end()) {
                 vmat_tab.push_back(vm);
+                smat_tab.push_back(sg);
                 it = vmat_index.emplace(key, (int)vmat_tab.size() - 1).first;
             }
             vm_global[i] = it->second;
@@ -423,6 +577,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.enable_cilia = m.opt.enable_cilia != 0;
         S.safety_guard = m.opt.safety_guard;
         S.secondary_experiment = m.opt.secondary_experiment != 0;
+        S.enable_signals = m.opt.enable_signals != 0;
         S.reinit_after = m.opt.reinit_initial_position_after_s;
         S.temp_amp = m.opt.temp_amplitude;
         S.temp_period = m.opt.temp_period;
@@ -431,7 +586,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.dt_frac = m.opt.dt_frac;
         S.optimal_dt = vx3_model_recommended_dt(&m);
         dy.hot_flags = ((S.vary_temp && S.temp_period > 0) ? SHF_THERMAL : 0) | (S.enable_expansion ? SHF_EXPANSION : 0) | (S.enable_cilia ? SHF_CILIA : 0) |
-                       (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0);
+                       (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0);
         dy.temp_amp = S.temp_amp;
         dy.temp_period = S.temp_period;
         // voxels
@@ -549,29 +704,23 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     D.nchunks = (int)chunks.size();
     D.vstride = (int)VS;
     D.lstride = (int)LS;
-#define UP(field, vec)                                                                                                  \
-    do {                                                                                                                \
-        std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type *p_ = nullptr;                            \
-        int rc_ = b->upload(&p_, vec);                                                                                  \
-        if (rc_) return cleanup(rc_);                                                                                   \
-        D.field = p_;                                                                                                   \
-    } while (0)
+    // ---- plan the arena: every array is a slice; uploaded slices first, zero-initialised ones after ----
+    ArenaPlan plan;
+#define UP(field, vec) plan.upload(const_cast<std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type **>(&D.field), vec)
     UP(simc, b->simc);
     UP(simd, simd);
     UP(vmat_tab, vmat_tab);
     UP(lmat_tab, lmat_tab);
-    {
-        std::vector<VoxMatL> vl(vmat_tab.size());
-        for (size_t i = 0; i < vmat_tab.size(); i++) {
-            memset(&vl[i], 0, sizeof(VoxMatL));
-            for (int k = 0; k < 3; k++) vl[i].size[k] = vmat_tab[i].size[k];
-            vl[i].thermal_on_after = vmat_tab[i].thermal_on_after;
-            vl[i].alphaCTE = vmat_tab[i].alphaCTE;
-            vl[i].dampMultNum = vmat_tab[i].dampMultNum;
-            vl[i].fixed = vmat_tab[i].fixed;
-        }
-        UP(vmatl_tab, vl);
+    std::vector<VoxMatL> vl(vmat_tab.size());
+    for (size_t i = 0; i < vmat_tab.size(); i++) {
+        memset(&vl[i], 0, sizeof(VoxMatL));
+        for (int k = 0; k < 3; k++) vl[i].size[k] = vmat_tab[i].size[k];
+        vl[i].thermal_on_after = vmat_tab[i].thermal_on_after;
+        vl[i].alphaCTE = vmat_tab[i].alphaCTE;
+        vl[i].dampMultNum = vmat_tab[i].dampMultNum;
+        vl[i].fixed = vmat_tab[i].fixed;
     }
+    UP(vmatl_tab, vl);
     D.n_vmats = (int)vmat_tab.size();
     D.n_lmats = (int)lmat_tab.size();
     b->h_lmat_tab = lmat_tab;
@@ -596,6 +745,11 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         UP(base_cilia, base_cilia);
         UP(shift_cilia, shift_cilia);
     }
+    if (b->any_signals) {
+        UP(smat_tab, smat_tab);
+        plan.zeroed(&D.sig, 6 * nvox);
+        plan.zeroed(&D.sprop, nvox);
+    }
     UP(lends, lends);
     UP(lstate, lstate);
     UP(lmat, lmat);
@@ -606,23 +760,48 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     UP(lstrain, lstrain);
     UP(larea, larea);
 #undef UP
-    int rc;
-    if ((rc = b->alloc(&D.lf2, 6 * LS))) return cleanup(rc);
-    if ((rc = b->alloc(&D.com_part, chunks.size() * 6))) return cleanup(rc);
+    plan.zeroed(&D.lf2, 6 * LS);
+    plan.zeroed(&D.com_part, chunks.size() * 6);
     if (b->any_collide) {
         int H = 1024;
         while (H < 2 * (int)nvox && H < (1 << 24)) H <<= 1;
         D.hmask = H - 1;
-        if ((rc = b->alloc(&D.contact, nvox * 3))) return cleanup(rc);
-        if ((rc = b->alloc(&D.cell_cnt, (size_t)H))) return cleanup(rc);
-        if ((rc = b->alloc(&D.cell_start, (size_t)H + 1))) return cleanup(rc);
-        if ((rc = b->alloc(&D.cell_cursor, (size_t)H))) return cleanup(rc);
-        if ((rc = b->alloc(&D.cell_items, nvox))) return cleanup(rc);
-        if ((rc = b->alloc(&D.vcell, nvox))) return cleanup(rc);
+        plan.zeroed(&D.contact, nvox * 3);
+        plan.zeroed(&D.cell_cnt, (size_t)H);
+        plan.zeroed(&D.cell_start, (size_t)H + 1);
+        plan.zeroed(&D.cell_cursor, (size_t)H);
+        plan.zeroed(&D.cell_items, nvox);
+        plan.zeroed(&D.vcell, nvox);
         D.cand_cap = 2048;
-        if ((rc = b->alloc(&D.cands, (size_t)D.cand_cap))) return cleanup(rc);
-        if ((rc = b->alloc(&D.cand_count, 1))) return cleanup(rc);
+        plan.zeroed(&D.cands, (size_t)D.cand_cap);
+        plan.zeroed(&D.cand_count, 1);
     }
+    // on-chip path for a single small collision-free body: its barrier / flag / producer-list arrays are arena slices too
+    std::vector<int> pdeps, pndeps;
+    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost || b->any_signals, any_cilia, prop, lends, vlinks, pdeps, pndeps);
+    if (b->pplan.ok) {
+        plan.zeroed(&b->pplan.barrier, 4 + 2 * 8 * (size_t)b->pplan.grid);
+        if (b->pplan.p2p) {
+            plan.upload(&b->pplan.deps, pdeps);
+            plan.upload(&b->pplan.ndeps, pndeps);
+            plan.zeroed(&b->pplan.flags, 2 * (size_t)b->pplan.grid * 32);
+        }
+    }
+    plan.layout();
+    int rc;
+    if ((rc = resources_acquire(device, plan.total, plan.up_bytes, b->res))) return cleanup(rc);
+    b->stream = b->res.stream;
+    b->ev0 = b->res.ev0;
+    b->ev1 = b->res.ev1;
+    for (const ArenaPlan::Item &it : plan.up) {
+        memcpy(b->res.h + it.off, it.src, it.bytes);
+        *it.field = b->res.d + it.off;
+    }
+    for (const ArenaPlan::Item &it : plan.zero) *it.field = b->res.d + it.off;
+    cudaError_t ce = cudaSuccess;
+    if (plan.up_bytes) ce = cudaMemcpyAsync(b->res.d, b->res.h, plan.up_bytes, cudaMemcpyHostToDevice, b->stream);
+    if (ce == cudaSuccess && plan.total > plan.up_bytes) ce = cudaMemsetAsync(b->res.d + plan.up_bytes, 0, plan.total - plan.up_bytes, b->stream);
+    if (ce != cudaSuccess) return cleanup(fail(VX3_ERR_CUDA, std::string("batch upload: ") + cudaGetErrorString(ce)));
     if ((rc = setup_stream_kernels(b, prop))) return cleanup(rc);
     // device-side init at the top of CUDA_Simulation (VX3_SimulationManager.cu:20-24,54-55)
     run_com(b, 0);
@@ -633,9 +812,9 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         if (od < 1e-10) od = 1e-10;
         b->hdt[s] = (float)(b->simc[s].dt_frac * od);
     }
-    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost, any_cilia, prop, lends, vlinks);
-    CK(cudaStreamSynchronize(b->stream));
-    CK(cudaGetLastError());
+    ce = cudaStreamSynchronize(b->stream);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce != cudaSuccess) return cleanup(fail(VX3_ERR_CUDA, std::string("batch init: ") + cudaGetErrorString(ce)));
     *out = b;
     return VX3_OK;
 }
@@ -644,14 +823,11 @@ extern "C" void vx3_batch_destroy(vx3_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    persistent_free(b->pplan);
     for (int sd = 0; sd < 2; sd++)
         if (b->halo.side[sd].peer_open) cudaIpcCloseMemHandle(b->halo.side[sd].peer_flag);
     for (auto &e : b->prof.ev) cudaEventDestroy(e);
     for (void *p : b->allocs) cudaFree(p);
-    if (b->ev0) cudaEventDestroy(b->ev0);
-    if (b->ev1) cudaEventDestroy(b->ev1);
-    if (b->stream) cudaStreamDestroy(b->stream);
+    resources_release(b->res); // arena, staging, stream and events go back to the cache
     delete b;
 }
 
@@ -745,6 +921,7 @@ static void launch_step(vx3_batch *b, bool check_stop) {
     const bool com = com_step(b, b->hsteps + 1);
     if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
     else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
+    if (b->any_signals) LAUNCH(KC_SIGNALS, k_signals, b->nsims, 256, D); // end of timeStep (VX3_Voxel.cu:270-275), before removeVoxels
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
@@ -1020,6 +1197,8 @@ extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
     if ((rc = d2h(b, tempe, D.tempe, S.voff, nv))) return rc;
     if ((rc = d2h(b, vlinks, D.vlinks, 6 * (size_t)S.voff, 6 * (size_t)nv))) return rc;
     if (D.contact && (rc = d2h(b, contact, D.contact, 3 * (size_t)S.voff, 3 * (size_t)nv))) return rc;
+    std::vector<double> sig;
+    if (D.sig && w->signal && (rc = d2h(b, sig, D.sig, 6 * (size_t)S.voff, 6 * (size_t)nv))) return rc;
     if ((rc = d2h(b, lends, D.lends, S.loff, nl))) return rc;
     if ((rc = d2h(b, lstate, D.lstate, S.loff, nl))) return rc;
     if ((rc = d2h(b, lmat, D.lmat, S.loff, nl))) return rc;
@@ -1039,6 +1218,7 @@ extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
         if (w->orient) for (int k = 0; k < 4; k++) w->orient[4 * i + k] = pose[8 * (size_t)i + 3 + k];
         if (w->vox_flags) w->vox_flags[i] = vflags[i] & VXF_BOOLSTATE_MASK;
         if (w->temp) w->temp[i] = tempe[i];
+        if (w->signal) for (int k = 0; k < 6; k++) w->signal[6 * i + k] = sig.empty() ? 0.0 : sig[6 * (size_t)i + k];
         if (w->vox_links) for (int k = 0; k < 6; k++) w->vox_links[6 * i + k] = vlinks[6 * (size_t)i + k] >= 0 ? vlinks[6 * (size_t)i + k] - S.loff : -1;
     }
     // global link-material index -> the simulation's local index (attach-created materials follow the model's)

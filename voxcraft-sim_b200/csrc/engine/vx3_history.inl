@@ -38,6 +38,8 @@ static int history_frame(vx3_batch *b, int sim, long long j, double t, const vx3
     if ((rc = d2h(b, lstate, D.lstate, S.loff, nl))) return rc;
     if ((rc = d2h(b, lmat, D.lmat, S.loff, nl))) return rc;
     if ((rc = d2h(b, lstrain, D.lstrain, S.loff, nl))) return rc;
+    std::vector<double> sig;
+    if (D.sig && b->simc[sim].enable_signals && (rc = d2h(b, sig, D.sig, 6 * (size_t)S.voff, 6 * (size_t)nv))) return rc;
     CK(cudaStreamSynchronize(b->stream));
     const double vs = 1 / 0.001;
     char buf[512];
@@ -82,7 +84,7 @@ static int history_frame(vx3_batch *b, int sim, long long j, double t, const vx3
             out += buf;
             snprintf(buf, sizeof(buf), "%d,", m.matid);
             out += buf;
-            snprintf(buf, sizeof(buf), "%.1f,", 0.0); // localSignal (signals are not simulated)
+            snprintf(buf, sizeof(buf), "%.1f,", sig.empty() ? 0.0 : sig[6 * (size_t)i]); // localSignal (VX3_SimulationManager.cu:88)
             out += buf;
             out += ";";
         }

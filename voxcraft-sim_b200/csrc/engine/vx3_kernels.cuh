@@ -322,7 +322,9 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MI
         }
         V3 cil(0, 0, 0);
         if ((hot_flags & SHF_CILIA) && !(r.flags & VX3_VOX_SURFACE) && m.cilia != 0 && !(m.cilia_on_after > t)) { // gpu_update_cilia_force :846-859
-            cil = r.orient.RotateVec3D(load3(D.base_cilia, v)) * m.cilia;                                     // localSignal = 0 (signals are off)
+            V3 cf = load3(D.base_cilia, v);
+            if (hot_flags & SHF_SIGNALS) cf += D.sig[6 * (size_t)v] * load3(D.shift_cilia, v); // baseCiliaForce + localSignal * shiftCiliaForce
+            cil = r.orient.RotateVec3D(cf) * m.cilia;
         }
         V3 ff(0, 0, 0);
         const ExtC *px = ext >= 0 ? &D.exts[ext] : nullptr;
@@ -583,6 +585,7 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
     }
     V3 c(0, 0, 0);
     int hits = 0;
+    bool fire = false; // EnableSignals: a non-target voxel touching a target voxel fires (:719-725)
     for (int i = 0; i < np; i++) {
         const int u = partner[i] & 0x3FFFFFFF;
         const bool fresh = (partner[i] >> 30) & 1;
@@ -593,7 +596,10 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
             if (v != hi) f = -f;
             c += f;
             if (fresh) c -= f; // a link was created for this pair: its contact force is taken back (:827-830)
-            if (v == hi && ((m1.is_target && !m2.is_target) || (m2.is_target && !m1.is_target))) hits++;
+            if ((m1.is_target && !m2.is_target) || (m2.is_target && !m1.is_target)) {
+                if (v == hi) hits++;
+                if (!mv.is_target) fire = true;
+            }
         }
         if (!emit || v != hi || fresh) continue;
         // ---- attach candidate test (:729-812) on the step-start link graph ----
@@ -635,6 +641,17 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
     if (S.enable_collision) {
         store3(D.contact, v, c);
         if (emit && hits) atomicAdd(&dy.collision_count, hits);
+        if (emit && fire && S.enable_signals) { // receiveSignal(100, currentTime, force = true) (VX3_Voxel.cu:315-335)
+            const SigMatC &sm = D.smat_tab[matv];
+            double *sg = D.sig + 6 * (size_t)v;
+            const double t = dy.t;
+            sg[2] = t + sm.inactive_period;
+            sg[0] = 100.0;
+            double val = 100.0 * sm.value_decay;
+            if (val < 0.1) val = 0;
+            sg[4] = val;
+            sg[5] = t;
+        }
     }
 }
 
@@ -769,6 +786,165 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_secondary(Dev D) {
         }
     }
     if (!dy.initpos_reinitialized && S.reinit_after < t) store3(D.initpos, v, load_pos(D.pose, v)); // saveInitialPosition()
+}
+
+// ------------------------------------------------------------------ signals
+// VX3_Voxel::propagateSignal / packMaker / localSignalDecay / receiveSignal (VX3_Voxel.cu:279-348), which the reference
+// runs at the end of every voxel's timeStep with all voxels in parallel: a voxel writes its NEIGHBOURS' signal state, so
+// the reference result depends on thread timing.  Defined behaviour here (and in the oracle): the voxels take their turns
+// in ascending voxel index.  That order is reproduced in parallel:
+//   1. sprop[i] = the value voxel i propagates AT ITS TURN.  It depends only on i's start state and on what its
+//      LOWER-index neighbours propagate, so iterating sprop[i] = f(sprop[lower neighbours]) from any start converges to
+//      the one assignment the sequential order produces (induction over the index); the loop runs until nothing changes
+//      (one or two rounds unless many adjacent voxels are active at once).
+//   2. every voxel then replays its own history of the step: receives from lower-index senders, its own
+//      propagate / pacemaker / decay, receives from higher-index senders.
+// One CTA per simulation (a simulation's voxels only talk to each other).
+struct SigState {
+    double ls, lsdt, inact, next, val, act;
+};
+__device__ __forceinline__ void sig_receive(SigState &s, const SigMatC &m, double value, double activeTime, bool force) { // :315-335
+    if (!force && s.inact > activeTime) return;
+    if (value < 0.1) return;
+    s.inact = activeTime + m.inactive_period;
+    s.ls = value;
+    s.val = value * m.value_decay;
+    if (s.val < 0.1) s.val = 0;
+    s.act = activeTime;
+}
+// the ≤6 link neighbours of voxel v, ascending by voxel index (-1 = none, sorted last as INT_MAX)
+__device__ __forceinline__ void sig_neighbours(const Dev &D, int v, int nb[6]) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int li = D.vlinks[6 * (size_t)v + k];
+        int o = 0x7FFFFFFF;
+        if (li >= 0) {
+            const int2 e = D.lends[li];
+            o = (e.x == v) ? e.y : e.x;
+        }
+        nb[k] = o;
+    }
+#pragma unroll
+    for (int i = 1; i < 6; i++) { // insertion sort
+        const int key = nb[i];
+        int j = i - 1;
+        while (j >= 0 && nb[j] > key) {
+            nb[j + 1] = nb[j];
+            j--;
+        }
+        nb[j + 1] = key;
+    }
+}
+__device__ __forceinline__ bool sig_runs(const Dev &D, int v) { // does timeStep reach its end for this voxel (:162-174, :586-589)?
+    if (D.vflags[v] & VXF_REMOVED) return false;
+    if (D.vmat_tab[D.vmat[v]].fixed) return false;
+    const int ext = D.vext[v];
+    if (ext >= 0 && (D.exts[ext].dof & 0x3F) == 0x3F) return false;
+    return true;
+}
+__global__ void __launch_bounds__(256) k_signals(Dev D) {
+    __shared__ int s_any;
+    const int sim = blockIdx.x;
+    const SimC &S = D.simc[sim];
+    const SimD &dy = D.simd[sim];
+    if (!S.enable_signals || dy.status != VX3_SIM_RUNNING || dy.diverged || dy.dt == 0) return;
+    const double t = dy.t;
+    const int v0 = S.voff, v1 = S.voff + S.nvox;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    // ---- 1a. start value: what the voxel would propagate if nothing reached it before its turn ----
+    bool any = false;
+    for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+        const double *sg = D.sig + 6 * (size_t)v;
+        double pv = 0;
+        if (sig_runs(D, v) && !(sg[5] > t) && !(sg[4] < 0.1)) pv = sg[4];
+        D.sprop[v] = pv;
+        any |= pv > 0;
+    }
+    if (any) s_any = 1;
+    __syncthreads();
+    const bool senders = s_any != 0;
+    // ---- 1b. fixpoint over the lower-index senders ----
+    if (senders) {
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_any = 0;
+            __syncthreads();
+            bool changed = false;
+            for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+                if (!sig_runs(D, v)) continue;
+                int nb[6];
+                sig_neighbours(D, v, nb);
+                const double *sg = D.sig + 6 * (size_t)v;
+                SigState s{sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]};
+                const SigMatC &m = D.smat_tab[D.vmat[v]];
+                int prev = -1;
+                for (int k = 0; k < 6; k++) {
+                    const int n = nb[k];
+                    if (n >= v) break;
+                    if (n == prev) continue;
+                    prev = n;
+                    const double pn = *(volatile double *)(D.sprop + n);
+                    if (pn > 0) sig_receive(s, m, pn, t + D.smat_tab[D.vmat[n]].time_delay, false);
+                }
+                const double pv = (!(s.act > t) && !(s.val < 0.1)) ? s.val : 0.0;
+                if (pv != *(volatile double *)(D.sprop + v)) {
+                    D.sprop[v] = pv;
+                    changed = true;
+                }
+            }
+            if (changed) s_any = 1;
+            __syncthreads();
+            if (!s_any) break;
+        }
+    }
+    // ---- 2. replay ----
+    for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+        double *sg = D.sig + 6 * (size_t)v;
+        SigState s{sg[0], sg[1], sg[2], sg[3], sg[4], sg[5]};
+        const SigMatC &m = D.smat_tab[D.vmat[v]];
+        int nb[6];
+        int k = 0, prev = -1;
+        if (senders) {
+            sig_neighbours(D, v, nb);
+            for (; k < 6; k++) {
+                const int n = nb[k];
+                if (n >= v) break;
+                if (n == prev) continue;
+                prev = n;
+                const double pn = D.sprop[n];
+                if (pn > 0) sig_receive(s, m, pn, t + D.smat_tab[D.vmat[n]].time_delay, false);
+            }
+        }
+        if (sig_runs(D, v)) {
+            if (!(s.act > t) && !(s.val < 0.1)) { // propagateSignal (:336-362): the sends are replayed by the receivers
+                s.val = 0;
+                s.act = 0;
+                s.inact = t + 2 * m.time_delay + m.inactive_period;
+            }
+            if (m.is_pacemaker && !(s.next > t)) { // packMaker (:304-313)
+                sig_receive(s, m, 100.0, t, true);
+                s.next = t + m.pacemaker_period;
+            }
+            if (!(s.lsdt > t)) { // localSignalDecay (:291-302)
+                if (s.ls < 0.1) s.ls = 0;
+                else {
+                    s.ls = s.ls * 0.9;
+                    s.lsdt = t + 0.01;
+                }
+            }
+        }
+        if (senders)
+            for (; k < 6; k++) {
+                const int n = nb[k];
+                if (n == 0x7FFFFFFF) break;
+                if (n == prev || n == v) continue;
+                prev = n;
+                const double pn = D.sprop[n];
+                if (pn > 0) sig_receive(s, m, pn, t + D.smat_tab[D.vmat[n]].time_delay, false);
+            }
+        sg[0] = s.ls; sg[1] = s.lsdt; sg[2] = s.inact; sg[3] = s.next; sg[4] = s.val; sg[5] = s.act;
+    }
 }
 
 // ------------------------------------------------------------------ reductions

@@ -364,20 +364,13 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
 }
 
 // host side ---------------------------------------------------------------------------------------------------
-inline void persistent_free(PersistentPlan &p) {
-    if (p.barrier) cudaFree(p.barrier);
-    if (p.flags) cudaFree(p.flags);
-    if (p.deps) cudaFree(p.deps);
-    if (p.ndeps) cudaFree(p.ndeps);
-    p.barrier = nullptr;
-    p.flags = nullptr;
-    p.deps = p.ndeps = nullptr;
-    p.ok = false;
-}
-
+// Decides whether the batch qualifies and sizes the launch; fills the producer lists of the point-to-point phase flags.
+// The device arrays (barrier, flags, deps, ndeps) are slices of the batch arena, placed by the caller (vx3_engine.cu).
 inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bool any_collide, bool any_detach, bool any_cilia,
-                            const cudaDeviceProp &prop, const std::vector<int2> &lends, const std::vector<int32_t> &vlinks) {
+                            const cudaDeviceProp &prop, const std::vector<int2> &lends, const std::vector<int32_t> &vlinks,
+                            std::vector<int> &deps, std::vector<int> &ndeps) {
     p.ok = false;
+    p.p2p = false;
     if (simc.size() != 1 || any_collide || any_detach || any_cilia) return;
     if (!prop.cooperativeLaunch) return;
     const int L = simc[0].lcap, V = simc[0].nvox;
@@ -396,19 +389,15 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
         return;
     }
     p.timing = getenv("VX3_PERSIST_TIMING") != nullptr;
-    if (cudaMalloc((void **)&p.barrier, 4 * sizeof(unsigned int) + 8 * (size_t)G * sizeof(unsigned long long)) != cudaSuccess) {
-        cudaGetLastError();
-        return;
-    }
     p.grid = G;
     p.block = T;
     p.links_per_cta = lpc;
     p.vox_per_cta = vpc;
     p.ok = true;
     // ---- producer lists for the point-to-point phase flags ----
-    p.p2p = false;
     if (getenv("VX3_PERSIST_GLOBAL_BARRIER")) return;
-    std::vector<int> deps(2 * (size_t)G * VX3_PERSIST_MAX_DEPS, -1), ndeps(2 * (size_t)G, 0);
+    deps.assign(2 * (size_t)G * VX3_PERSIST_MAX_DEPS, -1);
+    ndeps.assign(2 * (size_t)G, 0);
     auto add = [&](int which, int cta, int producer) -> bool {
         if (producer == cta) return true; // own phases are ordered by program order
         int *d = &deps[((size_t)which * G + cta) * VX3_PERSIST_MAX_DEPS];
@@ -437,13 +426,6 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
         for (int k = 0; k < ndeps[G + c] && fits; k++) fits = add(0, deps[((size_t)G + c) * VX3_PERSIST_MAX_DEPS + k], c);
     }
     if (!fits) return;
-    if (cudaMalloc((void **)&p.flags, 2 * (size_t)G * 32 * sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc((void **)&p.deps, deps.size() * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&p.ndeps, ndeps.size() * sizeof(int)) != cudaSuccess) {
-        cudaGetLastError();
-        return;
-    }
-    cudaMemcpy(p.deps, deps.data(), deps.size() * sizeof(int), cudaMemcpyHostToDevice);
-    cudaMemcpy(p.ndeps, ndeps.data(), ndeps.size() * sizeof(int), cudaMemcpyHostToDevice);
     p.p2p = true;
 }
 

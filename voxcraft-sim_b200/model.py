@@ -298,6 +298,7 @@ class StateBuffers:
         for k in ("link_strain", "link_max_strain", "link_strain_offset", "link_stress"):
             self.a[k] = np.zeros(nl, np.float32)
         self.a["link_rest_length"] = np.zeros(nl)
+        self.a["signal"] = np.zeros((nv, 6))
         self.view = abi.StateView()
         self.view.n_voxels, self.view.n_links = n_voxels, n_links
         for name, ctype in abi.StateView._fields_:
