@@ -147,6 +147,39 @@ def test_passive_large_angle():
         lib.vx3_builder_destroy(b)
 
 
+@pytest.mark.parametrize("persistent", [True, False])
+def test_divergence_stops_at_the_reference_step(persistent):
+    """A bar torn apart by a huge end load: some link's strain passes 100, doTimeStep returns false in that step
+    (VX3_VoxelyzeKernel.cu:273-281) — CurStepCount counts it, currentTime does not, the fitness reads NaN.  Both GPU paths
+    must stop at the oracle's step."""
+    spec = ModelSpec(0.01, "tear")
+    spec.add_material(elastic_mod=1e6, density=1e3, u_static=1.0, u_dynamic=0.5)
+    spec.set_env(bond_damping_z=1.0, col_damping_z=0.8, slow_damping_z=0.01, floor_enabled=0, grav_enabled=0)
+    spec.set_options(enable_collision=0)
+    spec.set_structure(np.ones((2, 3, 12), np.uint8))
+    for i in range(6):
+        spec.set_external(12 * i, dof_fixed=0x3F)
+        spec.set_external(12 * i + 11, force=(6e3, 0.0, 0.0))  # diverges after ~130 steps
+    lib, b, d = build(spec)
+    try:
+        eng = EngineBatch([d])
+        eng.set_profiling(False, use_persistent=persistent)
+        orc = OracleSim(d)
+        dt = float(np.float32(0.9 * orc.recommended_dt()))
+        eng.step(5000, dt)
+        done = orc.step(5000, dt)
+        assert done < 5000, "scenario must diverge"
+        re, ro = eng.results()[0], orc.result()
+        assert ro.status == abi.SIM_DIVERGED and re.status == abi.SIM_DIVERGED
+        assert re.steps == ro.steps == done + 1
+        assert re.current_time == ro.current_time
+        assert np.isnan(re.fitness_score)
+        eng.step(10, dt)  # a finished simulation does not move
+        assert eng.results()[0].steps == ro.steps
+    finally:
+        lib.vx3_builder_destroy(b)
+
+
 def test_batch_of_different_bodies():
     """Several simulations in one batch advance independently and equal their single runs."""
     specs = [cube_spec((3, 3, 3), seed=21, name="b0"), cube_spec((4, 2, 3), seed=22, holes=0.2, name="b1"),

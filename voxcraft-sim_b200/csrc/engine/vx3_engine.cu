@@ -776,16 +776,19 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         plan.zeroed(&D.cands, (size_t)D.cand_cap);
         plan.zeroed(&D.cand_count, 1);
     }
-    // on-chip path for a single small collision-free body: its barrier / flag / producer-list arrays are arena slices too
-    std::vector<int> pdeps, pndeps;
-    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost || b->any_signals, any_cilia, prop, lends, vlinks, pdeps, pndeps);
+    // on-chip path for a single small collision-free body: its control words, flags, lane tables and the odd-parity pose
+    // buffer are arena slices too
+    PersistentTables ptab;
+    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost || b->any_signals, any_cilia, prop, lends, vlinks, ixyz, ptab);
     if (b->pplan.ok) {
-        plan.zeroed(&b->pplan.barrier, 4 + 2 * 8 * (size_t)b->pplan.grid);
-        if (b->pplan.p2p) {
-            plan.upload(&b->pplan.deps, pdeps);
-            plan.upload(&b->pplan.ndeps, pndeps);
-            plan.zeroed(&b->pplan.flags, 2 * (size_t)b->pplan.grid * 32);
-        }
+        plan.zeroed(&b->pplan.ctl, 4 + 2 * 8 * (size_t)b->pplan.grid);
+        plan.zeroed(&b->pplan.flags, (size_t)b->pplan.grid * 32);
+        plan.zeroed(&b->pplan.pose_alt, 8 * nvox);
+        plan.upload(&b->pplan.lk_slot, ptab.lk_slot);
+        plan.upload(&b->pplan.vx_id, ptab.vx_id);
+        plan.upload(&b->pplan.vx_lane, ptab.vx_lane);
+        plan.upload(&b->pplan.deps, ptab.deps);
+        plan.upload(&b->pplan.ndeps, ptab.ndeps);
     }
     plan.layout();
     int rc;

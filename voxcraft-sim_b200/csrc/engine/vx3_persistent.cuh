@@ -1,19 +1,27 @@
 // On-chip persistent step kernel for ONE small collision-free body (BASELINE config 2 class).
 //
-// The streaming path pays three dependent kernel launches per doTimeStep, which is launch/latency bound for a
-// body whose whole state (a few MB) fits on chip.  Here one cooperative grid (one CTA per SM) runs many steps per
-// launch: every thread permanently owns at most one link and one voxel whose private state (link history,
-// strain, momenta, flags) stays in REGISTERS for the whole launch; only what the other phase needs crosses the
-// chip through L2 — the voxel pose (56 B) and the link's end forces/moments (96 B) — in the same global arrays
-// the streaming kernels use, so the two paths can alternate freely.  Two grid barriers per step separate the
-// link phase from the voxel phase exactly like the reference's two child grids
-// (src/VX3/VX3_VoxelyzeKernel.cu:259-269 gpu_update_links, :306-312 gpu_update_voxels); temperature / each voxel's
-// temperature for the next step is computed between a barrier's arrive and its wait and travels in its pose record.
-// The physics is the same code as the streaming kernels (vx3_physics.cuh).
+// The streaming path pays three dependent kernel launches per doTimeStep, which is launch/latency bound for a body
+// whose whole state (a few MB) fits on chip.  Here one cooperative grid (one CTA per SM) runs many steps per launch.
+//
+// Decomposition: the host cuts the body into one compact spatial block of voxels per CTA (recursive coordinate
+// bisection of the lattice coordinates).  A CTA owns its block's voxels and evaluates EVERY link that touches one of
+// them — a link across a block face is evaluated by both neighbours, from the same inputs with the same code, hence
+// to the same bits — so the end forces a voxel gathers never leave the SM: they go through shared memory.  Every
+// thread permanently owns at most one link and one voxel whose private state (link history, strain, momenta, flags)
+// stays in REGISTERS for the whole launch.  The only data that crosses the chip is the voxel pose record (64 B), ONCE
+// per step: poses are double-buffered by step parity (no write-after-read hazard, hence no second synchronisation),
+// and a CTA starts step s as soon as the CTAs that own the far ends of its face links have published step s-1
+// (point-to-point flags, release/acquire).  The reference orders the same two phases with two device-wide child-grid
+// syncs per step (src/VX3/VX3_VoxelyzeKernel.cu:259-269 gpu_update_links, :306-312 gpu_update_voxels).
+//
+// Temperature: each voxel's temperature for the next step is computed by its owner and travels in its pose record.
+// The physics is the same code as the streaming kernels (vx3_physics.cuh), so the two paths alternate freely (the
+// streaming path takes the CoM-sampling steps) and are bit-identical.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -23,25 +31,28 @@
 namespace vx3 {
 
 #define VX3_PERSIST_MAX_BLOCK 256
+#define VX3_PERSIST_MAX_DEPS 32
 
 struct PersistentPlan {
     bool ok = false;
     int grid = 0, block = 0;
-    int links_per_cta = 0, vox_per_cta = 0;
-    unsigned int *barrier = nullptr; // [0] arrival counter, [1] divergence flag, [4..] phase cycle counters (debug)
     bool timing = false;
-    // point-to-point phase flags (replace the two grid-wide barriers): CTA c waits only for the CTAs that own the
-    // voxels its links touch / the links its voxels touch
-    bool p2p = false;
-    unsigned int *flags = nullptr; // [2][grid][32]: link phases done, voxel phases done (one 128-B line per counter)
-    int *deps = nullptr;           // [2][grid][VX3_PERSIST_MAX_DEPS]: producers of the link phase / of the voxel phase
-    int *ndeps = nullptr;          // [2][grid]
+    // arena slices (placed by vx3_engine.cu)
+    unsigned int *ctl = nullptr;   // [0] divergence word, [1] exit counter, [4..] phase cycle counters (debug)
+    unsigned int *flags = nullptr; // [grid][32]: steps completed by the CTA in this launch (one 128-B line per counter)
+    int *lk_slot = nullptr;        // [grid][block]: global link slot of the lane (-1 none); bit 30 set = evaluated here for a neighbour's benefit only (not written back)
+    int *vx_id = nullptr;          // [grid][block]: global voxel of the lane (-1 none)
+    int *vx_lane = nullptr;        // [grid][block][6]: lane (in this CTA) of the voxel's link in each direction, -1 none
+    int *deps = nullptr;           // [grid][VX3_PERSIST_MAX_DEPS]: CTAs whose poses this CTA's links read
+    int *ndeps = nullptr;          // [grid]
+    double *pose_alt = nullptr;    // [nvox][8]: odd-parity pose buffer
 };
+#define VX3_PERSIST_DUP (1 << 30)
 
-#define VX3_PERSIST_MAX_DEPS 32
-struct P2P {
-    unsigned int *flags;
-    const int *deps, *ndeps;
+struct PersistArgs {
+    unsigned int *ctl, *flags;
+    const int *lk_slot, *vx_id, *vx_lane, *deps, *ndeps;
+    double *pose_alt;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
@@ -49,57 +60,23 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_add(unsigned int *p, unsigned int v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ double2 ldcg2(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
-
-// grid barrier split in two halves so independent work can run while the arrivals propagate
-__device__ __forceinline__ void grid_arrive(unsigned int *counter) {
-    __syncthreads(); // every thread's exchange stores are issued (and ordered before thread 0's release)
-    if (threadIdx.x == 0) red_release_add(counter, 1u);
-}
 __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Spin with relaxed loads (an acquire load would invalidate L1 on every poll), then ONE acquire fence.
-__device__ __forceinline__ void grid_wait(const unsigned int *counter, unsigned int target) {
-    if (threadIdx.x == 0) {
-        while (ld_relaxed_u32(counter) < target) {}
-#ifndef VX3_PERSIST_NO_ACQ_FENCE
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-#endif
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// publish "this CTA finished its phase number `value`": every thread's exchange stores precede the release store
-__device__ __forceinline__ void p2p_publish(unsigned int *flag, unsigned int value) {
-    __syncthreads();
-    if (threadIdx.x == 0) st_release_u32(flag, value);
-}
-// wait until every producer CTA of my next phase has published `target`; returns the divergence flag (uniform)
-__device__ __forceinline__ unsigned int p2p_wait(const unsigned int *flags, int my_dep, unsigned int target, const unsigned int *divflag, int *s_div) {
-    if (my_dep >= 0) {
-        const unsigned int *f = flags + 32 * (size_t)my_dep;
-        while (ld_acquire_u32(f) < target) {}
-    }
-    if (threadIdx.x == 0) *s_div = (int)ld_relaxed_u32(divflag);
-    __syncthreads();
-    return (unsigned int)*s_div;
-}
+__device__ __forceinline__ double2 ldcg2(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ void stcg2(double *p, double a, double b) { __stcg(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
 
-__global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1)
-k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox_per_cta, unsigned int *bar, int timing, P2P p2p) {
-    __shared__ int s_stop;
-    __shared__ int s_div;
-    __shared__ SimC sS; // per-simulation constants on chip: global loads would miss L1 after every barrier's fence
-    for (int i = threadIdx.x; i < (int)(sizeof(SimC) / 4); i += blockDim.x) reinterpret_cast<int *>(&sS)[i] = reinterpret_cast<const int *>(&D.simc[0])[i];
+__global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, long long nsteps, int check_stop, int timing, PersistArgs A) {
+    __shared__ int s_stop, s_div;
+    __shared__ SimC sS;                                    // per-simulation constants on chip
+    __shared__ double sF[VX3_PERSIST_MAX_BLOCK][12];       // end forces of the CTA's links: Fneg, Mneg, Fpos, Mpos
+    const int T = blockDim.x, tid = threadIdx.x;
+    for (int i = tid; i < (int)(sizeof(SimC) / 4); i += T) reinterpret_cast<int *>(&sS)[i] = reinterpret_cast<const int *>(&D.simc[0])[i];
     __syncthreads();
     long long tk[5] = {0, 0, 0, 0, 0}, c0 = 0;
 #define TICK(i)                                                                                                         \
@@ -114,16 +91,16 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
     const float dtF = dy.dt;
     if (dtF == 0) return;
     const double dt = dtF;
-    double t = dy.t;
+    const double t0 = dy.t;
+    double t = t0;
     const unsigned int G = gridDim.x;
     const bool vary = S.vary_temp && S.temp_period > 0;
+    double *const P0 = D.pose, *const P1 = A.pose_alt;
 
     // ---- my link ----
-    int g = -1;
-    if ((int)threadIdx.x < links_per_cta) {
-        g = blockIdx.x * links_per_cta + threadIdx.x;
-        if (g >= D.nlinkslots) g = -1;
-    }
+    int g = A.lk_slot[(size_t)blockIdx.x * T + tid];
+    const bool dup = g >= 0 && (g & VX3_PERSIST_DUP);
+    if (g >= 0) g &= ~VX3_PERSIST_DUP;
     LinkRegs L;
     int2 ends = make_int2(-1, -1);
     LinkMatC lm;
@@ -153,7 +130,7 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
             const float2 ar = D.larea[g];
             L.area = ar.x; L.tsum = ar.y;
             L.state &= ~LKS_JUST_CREATED;
-            pdN = unpack_pd(D.pose[8 * (size_t)ends.x + 7]); pdP = unpack_pd(D.pose[8 * (size_t)ends.y + 7]);
+            pdN = unpack_pd(P0[8 * (size_t)ends.x + 7]); pdP = unpack_pd(P0[8 * (size_t)ends.y + 7]);
             numN = mN.dampMultNum; numP = mP.dampMultNum;
             szN = mN.size[axis]; szP = mP.size[axis];
             cteN = mN.alphaCTE; cteP = mP.alphaCTE;
@@ -164,17 +141,18 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
             intP = !mP.fixed && !(D.vflags[ends.y] & VXF_REMOVED);
         }
     }
+    // a lane without a live link still owns a force record that voxels may index: keep it zero
+#pragma unroll
+    for (int k = 0; k < 12; k++) sF[tid][k] = 0.0;
+
     // ---- my voxel ----
-    int v = -1;
-    if ((int)threadIdx.x < vox_per_cta) {
-        v = blockIdx.x * vox_per_cta + threadIdx.x;
-        if (v >= D.nvox) v = -1;
-    }
+    const int v = A.vx_id[(size_t)blockIdx.x * T + tid];
     VoxRegs r;
     VoxMatC vm;
     float tempe = 0, tempe_next = 0; // this step's temperature / the next step's (published in the pose record)
+    float pd_cur = 0;
     double phase = 0;
-    int vl[6] = {-1, -1, -1, -1, -1, -1};
+    int vl[6] = {-1, -1, -1, -1, -1, -1}; // lane of the link in each direction
     const ExtC *px = nullptr;
     short ic[3] = {0, 0, 0};
     bool vthermal = false, vint = false;
@@ -184,45 +162,61 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
         phase = D.phase[v];
         vthermal = vary && !(r.flags & VXF_REMOVED) && !vm.fixed;
         vint = !(r.flags & VXF_REMOVED) && !vm.fixed;
-        load_pose(D.pose, v, r.pos, r.orient);
-        tempe_next = unpack_t(D.pose[8 * (size_t)v + 7]);
+        load_pose(P0, v, r.pos, r.orient);
+        const double tp = P0[8 * (size_t)v + 7];
+        tempe_next = unpack_t(tp);
+        pd_cur = unpack_pd(tp);
         tempe = D.tempe[v];
         const double2 m0 = *D.mo(0, v), m1 = *D.mo(1, v), m2 = *D.mo(2, v);
         r.linMom = V3(m0.x, m0.y, m1.x);
         r.angMom = V3(m1.y, m2.x, m2.y);
 #pragma unroll
-        for (int i = 0; i < 6; i++) vl[i] = D.vlinks[6 * (size_t)v + i];
+        for (int i = 0; i < 6; i++) {
+            vl[i] = A.vx_lane[((size_t)blockIdx.x * T + tid) * 6 + i];
+            if (D.vlinks[6 * (size_t)v + i] < 0) vl[i] = -1;
+        }
         const int ext = D.vext[v];
         px = ext >= 0 ? &D.exts[ext] : nullptr;
         ic[0] = D.ixyz[3 * (size_t)v]; ic[1] = D.ixyz[3 * (size_t)v + 1]; ic[2] = D.ixyz[3 * (size_t)v + 2];
+        // the odd-parity buffer starts as a copy: voxels that are never integrated keep their record in both
+        store_pose(P1, v, r.pos, r.orient, tempe_next, pd_cur);
     }
     const bool fixedAll = px && (px->dof & 0x3F) == 0x3F;
 
-    unsigned int phase_no = 0; // barriers passed
+    // point-to-point: thread k polls the k-th neighbour CTA
+    int dep = -1;
+    if (tid < A.ndeps[blockIdx.x]) dep = A.deps[(size_t)blockIdx.x * VX3_PERSIST_MAX_DEPS + tid];
+    unsigned int *my_flag = A.flags + 32 * (size_t)blockIdx.x;
+    const unsigned int *dep_flag = dep >= 0 ? A.flags + 32 * (size_t)dep : nullptr;
+    unsigned int *divword = A.ctl; // 0 = no divergence; otherwise nsteps - s of the EARLIEST diverging step s (atomicMax)
+
     long long done = 0;
     int status = VX3_SIM_RUNNING;
-    // point-to-point mode: thread k polls the k-th producer CTA of each phase
-    const bool use_p2p = p2p.flags != nullptr;
-    int dep_link = -1, dep_vox = -1; // producer (voxel-phase CTA) for my link phase / (link-phase CTA) for my voxel phase
-    unsigned int *my_lflag = nullptr, *my_vflag = nullptr;
-    const unsigned int *lflags = nullptr, *vflags = nullptr;
-    if (use_p2p) {
-        lflags = p2p.flags;
-        vflags = p2p.flags + 32 * (size_t)G;
-        my_lflag = p2p.flags + 32 * (size_t)blockIdx.x;
-        my_vflag = p2p.flags + 32 * (size_t)(G + blockIdx.x);
-        if ((int)threadIdx.x < p2p.ndeps[blockIdx.x]) dep_link = p2p.deps[(size_t)blockIdx.x * VX3_PERSIST_MAX_DEPS + threadIdx.x];
-        if ((int)threadIdx.x < p2p.ndeps[G + blockIdx.x]) dep_vox = p2p.deps[(size_t)(G + blockIdx.x) * VX3_PERSIST_MAX_DEPS + threadIdx.x];
-    }
-
     if (timing) c0 = clock64();
-    for (long long s = 0; s < nsteps; s++) {
+    long long s = 0;
+    for (; s < nsteps; s++) {
+        // ================= wait: the poses of step s are published by every CTA my links reach into =================
+        const double *Pr = (s & 1) ? P1 : P0;
+        double *Pw = (s & 1) ? P0 : P1;
+        if (dep_flag) {
+            while (ld_acquire_u32(dep_flag) < (unsigned int)s) {
+                if (ld_relaxed_u32(divword)) break; // the producer may have left: the simulation is over
+            }
+        }
+        if (tid == 0) s_div = (int)ld_relaxed_u32(divword);
+        __syncthreads();
+        if (s_div) { // somebody's link diverged at a step <= s: doTimeStep returned false there
+            status = VX3_SIM_DIVERGED;
+            break;
+        }
+        TICK(0);
         // ================= link phase (gpu_update_links) =================
+        bool mydiv = false;
         if (g >= 0) {
             V3 pN, pP;
             Q4 qN, qP;
             {
-                const double *a = D.pose + 8 * (size_t)ends.x, *b = D.pose + 8 * (size_t)ends.y;
+                const double *a = Pr + 8 * (size_t)ends.x, *b = Pr + 8 * (size_t)ends.y;
                 const double2 a0 = ldcg2(a), a1 = ldcg2(a + 2), a2 = ldcg2(a + 4), a3 = ldcg2(a + 6);
                 const double2 b0 = ldcg2(b), b1 = ldcg2(b + 2), b2 = ldcg2(b + 4), b3 = ldcg2(b + 6);
                 pN = V3(a0.x, a0.y, a1.x); qN = Q4(a1.y, a2.x, a2.y, a3.x);
@@ -235,47 +229,42 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
             }
             LinkOut o;
             link_update_forces(L, lm, D.strain_pool, D.stress_pool, pN, qN, pP, qP, numN / pdN, numP / pdP, o);
-            *D.lf(0, g) = make_double2(o.forceNeg.x, o.forceNeg.y);
-            *D.lf(1, g) = make_double2(o.forceNeg.z, o.momentNeg.x);
-            *D.lf(2, g) = make_double2(o.momentNeg.y, o.momentNeg.z);
-            *D.lf(3, g) = make_double2(o.forcePos.x, o.forcePos.y);
-            *D.lf(4, g) = make_double2(o.forcePos.z, o.momentPos.x);
-            *D.lf(5, g) = make_double2(o.momentPos.y, o.momentPos.z);
-            if (L.strain > 100) atomicExch(&bar[1], 1u);
+            double *f = sF[tid];
+            f[0] = o.forceNeg.x; f[1] = o.forceNeg.y; f[2] = o.forceNeg.z; f[3] = o.momentNeg.x; f[4] = o.momentNeg.y; f[5] = o.momentNeg.z;
+            f[6] = o.forcePos.x; f[7] = o.forcePos.y; f[8] = o.forcePos.z; f[9] = o.momentPos.x; f[10] = o.momentPos.y; f[11] = o.momentPos.z;
+            if (!dup) { // the streaming path and the state read-back see the end forces in global memory
+                *D.lf(0, g) = make_double2(o.forceNeg.x, o.forceNeg.y);
+                *D.lf(1, g) = make_double2(o.forceNeg.z, o.momentNeg.x);
+                *D.lf(2, g) = make_double2(o.momentNeg.y, o.momentNeg.z);
+                *D.lf(3, g) = make_double2(o.forcePos.x, o.forcePos.y);
+                *D.lf(4, g) = make_double2(o.forcePos.z, o.momentPos.x);
+                *D.lf(5, g) = make_double2(o.momentPos.y, o.momentPos.z);
+            }
+            mydiv = L.strain > 100;
             if (intN) pdN = dtF;
             if (intP) pdP = dtF;
         }
-        TICK(0);
-        if (use_p2p) p2p_publish(my_lflag, (unsigned int)(s + 1));
-        else grid_arrive(bar);
-        // --- while the arrivals propagate: the temperature the NEXT step starts with (gpu_update_temperature at t+dt) ---
+        TICK(1);
+        // --- the temperature the NEXT step starts with (gpu_update_temperature at t+dt) ---
         if (v >= 0) {
             tempe = tempe_next;
             if (vthermal && !(vm.thermal_on_after > t + dtF)) tempe_next = voxel_temperature(S, t + dtF, phase);
         }
-        TICK(1);
-        unsigned int div;
-        if (use_p2p) div = p2p_wait(lflags, dep_vox, (unsigned int)(s + 1), &bar[1], &s_div);
-        else {
-            grid_wait(bar, ++phase_no * G);
-            div = ld_relaxed_u32(&bar[1]);
-        }
-        TICK(2);
-        if (div) { // a link diverged in this step: doTimeStep returns false before the voxel pass
+        if (__syncthreads_or(mydiv)) { // a link of this CTA diverged in this step: doTimeStep returns false before the voxel pass
+            if (tid == 0) atomicMax(divword, (unsigned int)(nsteps - s));
             status = VX3_SIM_DIVERGED;
-            done = s + 1;
             break;
         }
+        TICK(2);
         // ================= voxel phase (gpu_update_voxels) =================
         if (v >= 0 && vint) {
             V3 F(0, 0, 0), M(0, 0, 0);
 #pragma unroll
             for (int i = 0; i < 6; i++) {
                 if (vl[i] >= 0) {
-                    const int k0 = (i & 1) ? 3 : 0;
-                    const double2 a = __ldcg(D.lf(k0, vl[i])), b = __ldcg(D.lf(k0 + 1, vl[i])), c = __ldcg(D.lf(k0 + 2, vl[i]));
-                    F += V3(a.x, a.y, b.x);
-                    M += V3(b.y, c.x, c.y);
+                    const double *f = sF[vl[i]] + ((i & 1) ? 6 : 0);
+                    F += V3(f[0], f[1], f[2]);
+                    M += V3(f[3], f[4], f[5]);
                 }
             }
             V3 ff(0, 0, 0);
@@ -295,46 +284,42 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
                 if (all) r.flags |= VXF_ENABLE_ATTACH;
                 else r.flags &= ~VXF_ENABLE_ATTACH;
             }
-            store_pose(D.pose, v, r.pos, r.orient, tempe_next, dtF);
+            pd_cur = dtF;
+            double *w = Pw + 8 * (size_t)v;
+            stcg2(w, r.pos.x, r.pos.y);
+            stcg2(w + 2, r.pos.z, r.orient.w);
+            stcg2(w + 4, r.orient.x, r.orient.y);
+            stcg2(w + 6, r.orient.z, pack_tp(tempe_next, dtF));
         }
         t += dtF; // currentTime += dt (:352)
         done = s + 1;
         TICK(3);
-        if (use_p2p) p2p_publish(my_vflag, (unsigned int)(s + 1));
-        else grid_arrive(bar);
-        // --- while the arrivals propagate: the stop condition for the next step ---
-        if (check_stop && threadIdx.x == 0) {
-            s_stop = 0;
-            if (S.prog_n[VX3_PROG_STOP] > 0) {
-                double vars[9];
-                prog_vars(S, dy, t, dy.com[0], dy.com[1], dy.com[2], vars);
-                bool ok;
-                s_stop = mt_eval<VX3_MAX_TOKENS>(D.tokens + S.prog_off[VX3_PROG_STOP], S.prog_n[VX3_PROG_STOP], vars, &ok) > 0;
+        // ================= publish step s+1 =================
+        __syncthreads(); // every thread's pose stores are issued (and ordered before thread 0's release)
+        if (tid == 0) {
+            st_release_u32(my_flag, (unsigned int)(s + 1));
+            if (check_stop) { // the stop condition for the next step: identical in every CTA (CoM, angle, ... only change on the streaming path's sampling steps)
+                s_stop = 0;
+                if (S.prog_n[VX3_PROG_STOP] > 0) {
+                    double vars[9];
+                    prog_vars(S, dy, t, dy.com[0], dy.com[1], dy.com[2], vars);
+                    bool ok;
+                    s_stop = mt_eval<VX3_MAX_TOKENS>(D.tokens + S.prog_off[VX3_PROG_STOP], S.prog_n[VX3_PROG_STOP], vars, &ok) > 0;
+                }
             }
         }
-        if (use_p2p) {
-            if (p2p_wait(vflags, dep_link, (unsigned int)(s + 1), &bar[1], &s_div)) { // someone diverged meanwhile
-                status = VX3_SIM_DIVERGED;
+        if (check_stop) {
+            __syncthreads();
+            if (s_stop) {
+                status = VX3_SIM_STOPPED;
                 break;
             }
-        } else
-            grid_wait(bar, ++phase_no * G);
-        TICK(4);
-        if (check_stop && s_stop) { // identical in every CTA: CoM, angle, ... only change on the streaming path's sampling steps
-            status = VX3_SIM_STOPPED;
-            break;
         }
+        TICK(4);
     }
 
-    if (use_p2p && status == VX3_SIM_DIVERGED) { // CTAs may leave at different steps: never let a neighbour wait for me
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            st_release_u32(my_lflag, 0xFFFFFFFFu);
-            st_release_u32(my_vflag, 0xFFFFFFFFu);
-        }
-    }
     // ---- write the register-resident state back ----
-    if (g >= 0) {
+    if (g >= 0 && !dup) {
         *D.lh(0, g) = make_double2(L.pos2.x, L.pos2.y);
         *D.lh(1, g) = make_double2(L.pos2.z, L.angle1v.x);
         *D.lh(2, g) = make_double2(L.angle1v.y, L.angle1v.z);
@@ -350,109 +335,168 @@ k_persistent(Dev D, long long nsteps, int check_stop, int links_per_cta, int vox
         D.vflags[v] = r.flags;
         D.tempe[v] = tempe;
     }
-    if (timing && threadIdx.x == 0) {
-        unsigned long long *o = reinterpret_cast<unsigned long long *>(bar + 4) + 8 * blockIdx.x;
+    if (timing && tid == 0) {
+        unsigned long long *o = reinterpret_cast<unsigned long long *>(A.ctl + 4) + 8 * blockIdx.x;
         for (int i = 0; i < 5; i++) o[i] = (unsigned long long)tk[i];
         o[5] = (unsigned long long)done;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        dy.t = t;
-        dy.steps += done;
-        dy.status = status;
-        if (status == VX3_SIM_DIVERGED) dy.diverged = 1;
+    // ---- the last CTA to leave writes the simulation's scalars; every CTA then restores its voxels' records in the
+    // batch's pose array (the even buffer) — only after ALL CTAs have left their loops, because a slower neighbour may
+    // still be reading the even buffer ----
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int left = atomicAdd(A.ctl + 1, 1u);
+        if (left == G - 1) {
+            __threadfence();
+            const unsigned int dv = ld_relaxed_u32(divword);
+            if (dv) { // diverged in the link pass of step sd: CurStepCount was incremented, time was not (:241-281)
+                const long long sd = nsteps - (long long)dv;
+                double td = t0;
+                for (long long i = 0; i < sd; i++) td += dtF;
+                dy.t = td;
+                dy.steps += sd + 1;
+                dy.status = VX3_SIM_DIVERGED;
+                dy.diverged = 1;
+            } else {
+                dy.t = t;
+                dy.steps += done;
+                dy.status = status;
+            }
+        }
+        while (ld_acquire_u32(A.ctl + 1) < G) {}
     }
+    __syncthreads();
+    if (v >= 0) store_pose(P0, v, r.pos, r.orient, tempe_next, pd_cur);
 }
 
 // host side ---------------------------------------------------------------------------------------------------
-// Decides whether the batch qualifies and sizes the launch; fills the producer lists of the point-to-point phase flags.
-// The device arrays (barrier, flags, deps, ndeps) are slices of the batch arena, placed by the caller (vx3_engine.cu).
-inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bool any_collide, bool any_detach, bool any_cilia,
+struct PersistentTables {
+    std::vector<int> lk_slot, vx_id, vx_lane, deps, ndeps;
+};
+
+// recursive coordinate bisection: voxels idx[lo, hi) go to CTAs [c0, c0 + nc)
+inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, const int16_t *ixyz, int voff, std::vector<int> &cta_of) {
+    if (nc == 1) {
+        for (int i = lo; i < hi; i++) cta_of[idx[i]] = c0;
+        return;
+    }
+    int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+    for (int i = lo; i < hi; i++)
+        for (int a = 0; a < 3; a++) {
+            const int c = ixyz[3 * ((size_t)voff + idx[i]) + a];
+            mn[a] = std::min(mn[a], c);
+            mx[a] = std::max(mx[a], c);
+        }
+    int ax = 0;
+    for (int a = 1; a < 3; a++)
+        if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
+    std::sort(idx.begin() + lo, idx.begin() + hi, [&](int p, int q) {
+        const int cp = ixyz[3 * ((size_t)voff + p) + ax], cq = ixyz[3 * ((size_t)voff + q) + ax];
+        return cp != cq ? cp < cq : p < q;
+    });
+    const int ncl = nc / 2;
+    const int mid = lo + (int)((long long)(hi - lo) * ncl / nc);
+    persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of);
+    persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of);
+}
+
+// Decides whether the batch qualifies, cuts the body into blocks and builds the per-CTA lane tables.  The device arrays
+// are slices of the batch arena, placed by the caller (vx3_engine.cu).
+inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bool any_collide, bool any_dynamic_topology, bool any_cilia,
                             const cudaDeviceProp &prop, const std::vector<int2> &lends, const std::vector<int32_t> &vlinks,
-                            std::vector<int> &deps, std::vector<int> &ndeps) {
+                            const std::vector<int16_t> &ixyz, PersistentTables &tb) {
     p.ok = false;
-    p.p2p = false;
-    if (simc.size() != 1 || any_collide || any_detach || any_cilia) return;
+    if (simc.size() != 1 || any_collide || any_dynamic_topology || any_cilia) return;
     if (!prop.cooperativeLaunch) return;
-    const int L = simc[0].lcap, V = simc[0].nvox;
+    const int L = simc[0].lcap, V = simc[0].nvox, voff = simc[0].voff, loff = simc[0].loff;
+    if (V < 1) return;
     int G = prop.multiProcessorCount;
-    const int most = L > V ? L : V;
-    if ((most + 31) / 32 < G) G = (most + 31) / 32;
+    if ((V + 15) / 16 < G) G = (V + 15) / 16; // at least ~16 voxels per CTA
     if (G < 1) G = 1;
-    const int lpc = (L + G - 1) / G, vpc = (V + G - 1) / G;
-    int T = lpc > vpc ? lpc : vpc;
-    T = (T + 31) / 32 * 32;
-    if (T < 32) T = 32;
-    if (T > VX3_PERSIST_MAX_BLOCK) return; // body too large for one item per thread: streaming path
+    std::vector<int> idx(V), cta_of(V, 0);
+    for (int i = 0; i < V; i++) idx[i] = i;
+    persist_rcb(idx, 0, V, 0, G, ixyz.data(), voff, cta_of);
+    std::vector<std::vector<int>> vox(G), lnk(G);
+    for (int i = 0; i < V; i++) vox[cta_of[i]].push_back(i);
+    for (int l = 0; l < L; l++) {
+        const int2 e = lends[(size_t)loff + l];
+        if (e.x < 0) continue;
+        const int ca = cta_of[e.x - voff], cb = cta_of[e.y - voff];
+        lnk[ca].push_back(l);
+        if (cb != ca) lnk[cb].push_back(l | VX3_PERSIST_DUP); // owner = the CTA of the negative end
+    }
+    int most = 1;
+    for (int c = 0; c < G; c++) most = std::max(most, (int)std::max(vox[c].size(), lnk[c].size()));
+    int T = (most + 31) / 32 * 32;
+    if (T > VX3_PERSIST_MAX_BLOCK) return; // blocks too large for one item per thread: streaming path
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_persistent, T, 0) != cudaSuccess || nb < 1) {
         cudaGetLastError();
         return;
     }
+    tb.lk_slot.assign((size_t)G * T, -1);
+    tb.vx_id.assign((size_t)G * T, -1);
+    tb.vx_lane.assign((size_t)G * T * 6, -1);
+    tb.deps.assign((size_t)G * VX3_PERSIST_MAX_DEPS, -1);
+    tb.ndeps.assign(G, 0);
+    std::vector<int> lane_of(L, -1);
+    for (int c = 0; c < G; c++) {
+        for (size_t k = 0; k < lnk[c].size(); k++) {
+            const int l = lnk[c][k] & ~VX3_PERSIST_DUP;
+            tb.lk_slot[(size_t)c * T + k] = (loff + l) | (lnk[c][k] & VX3_PERSIST_DUP);
+            lane_of[l] = (int)k;
+            const int2 e = lends[(size_t)loff + l];
+            for (int other : {cta_of[e.x - voff], cta_of[e.y - voff]}) {
+                if (other == c) continue;
+                int *d = &tb.deps[(size_t)c * VX3_PERSIST_MAX_DEPS];
+                int &n = tb.ndeps[c];
+                bool have = false;
+                for (int q = 0; q < n; q++) have |= d[q] == other;
+                if (have) continue;
+                if (n >= VX3_PERSIST_MAX_DEPS || n >= T) return; // too many neighbours for one poll per thread
+                d[n++] = other;
+            }
+        }
+        for (size_t k = 0; k < vox[c].size(); k++) {
+            const int vi = vox[c][k];
+            tb.vx_id[(size_t)c * T + k] = voff + vi;
+            for (int dir = 0; dir < 6; dir++) {
+                const int li = vlinks[6 * ((size_t)voff + vi) + dir];
+                if (li < 0) continue;
+                const int l = li - loff;
+                if (l < 0 || l >= L || lane_of[l] < 0) return; // inconsistent adjacency: leave it to the streaming path
+                tb.vx_lane[((size_t)c * T + k) * 6 + dir] = lane_of[l];
+            }
+        }
+        for (size_t k = 0; k < lnk[c].size(); k++) lane_of[lnk[c][k] & ~VX3_PERSIST_DUP] = -1;
+    }
     p.timing = getenv("VX3_PERSIST_TIMING") != nullptr;
     p.grid = G;
     p.block = T;
-    p.links_per_cta = lpc;
-    p.vox_per_cta = vpc;
     p.ok = true;
-    // ---- producer lists for the point-to-point phase flags ----
-    if (getenv("VX3_PERSIST_GLOBAL_BARRIER")) return;
-    deps.assign(2 * (size_t)G * VX3_PERSIST_MAX_DEPS, -1);
-    ndeps.assign(2 * (size_t)G, 0);
-    auto add = [&](int which, int cta, int producer) -> bool {
-        if (producer == cta) return true; // own phases are ordered by program order
-        int *d = &deps[((size_t)which * G + cta) * VX3_PERSIST_MAX_DEPS];
-        int &n = ndeps[(size_t)which * G + cta];
-        for (int k = 0; k < n; k++)
-            if (d[k] == producer) return true;
-        if (n >= VX3_PERSIST_MAX_DEPS || n >= T) return false;
-        d[n++] = producer;
-        return true;
-    };
-    bool fits = true;
-    for (int g = 0; g < L && fits; g++) { // link phase of CTA g/lpc reads the poses owned by the voxel CTAs of its ends
-        const int2 e = lends[simc[0].loff + g];
-        if (e.x < 0) continue;
-        fits = add(0, g / lpc, (e.x - simc[0].voff) / vpc) && add(0, g / lpc, (e.y - simc[0].voff) / vpc);
-    }
-    for (int v = 0; v < V && fits; v++) // voxel phase of CTA v/vpc reads the forces owned by the link CTAs of its links
-        for (int i = 0; i < 6 && fits; i++) {
-            const int li = vlinks[6 * ((size_t)simc[0].voff + v) + i];
-            if (li >= 0) fits = add(1, v / vpc, (li - simc[0].loff) / lpc);
-        }
-    if (!fits) return; // too many neighbours for one poll per thread: keep the grid barrier
-    // symmetric closure: whoever reads my data must also be waited for before I overwrite it (WAR)
-    for (int c = 0; c < G && fits; c++) {
-        for (int k = 0; k < ndeps[c] && fits; k++) fits = add(1, deps[(size_t)c * VX3_PERSIST_MAX_DEPS + k], c);
-        for (int k = 0; k < ndeps[G + c] && fits; k++) fits = add(0, deps[((size_t)G + c) * VX3_PERSIST_MAX_DEPS + k], c);
-    }
-    if (!fits) return;
-    p.p2p = true;
 }
 
 inline int persistent_run(PersistentPlan &p, const Dev &D, cudaStream_t st, long long nsteps, bool check_stop, long long *launches) {
     if (!p.ok) return -1;
-    if (cudaMemsetAsync(p.barrier, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) return -1;
-    // the arrival counter is 32-bit: 2 barriers per step, grid arrivals each
-    const long long max_chunk = 0x7FFFFFFFll / (2ll * p.grid) - 4;
+    const long long max_chunk = 0x3FFFFFFFll; // the flags and the divergence word are 32-bit step counts
     while (nsteps > 0) {
         long long n = nsteps < max_chunk ? nsteps : max_chunk;
         int cs = check_stop ? 1 : 0;
         Dev d = D;
         int tm = p.timing ? 1 : 0;
-        P2P pp;
-        pp.flags = p.p2p ? p.flags : nullptr;
-        pp.deps = p.deps;
-        pp.ndeps = p.ndeps;
-        if (p.p2p && cudaMemsetAsync(p.flags, 0, 2 * (size_t)p.grid * 32 * sizeof(unsigned int), st) != cudaSuccess) return -1;
-        void *args[] = {(void *)&d, (void *)&n, (void *)&cs, (void *)&p.links_per_cta, (void *)&p.vox_per_cta, (void *)&p.barrier, (void *)&tm, (void *)&pp};
+        PersistArgs a{p.ctl, p.flags, p.lk_slot, p.vx_id, p.vx_lane, p.deps, p.ndeps, p.pose_alt};
+        if (cudaMemsetAsync(p.ctl, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) return -1;
+        if (cudaMemsetAsync(p.flags, 0, (size_t)p.grid * 32 * sizeof(unsigned int), st) != cudaSuccess) return -1;
+        void *args[] = {(void *)&d, (void *)&n, (void *)&cs, (void *)&tm, (void *)&a};
         if (cudaLaunchCooperativeKernel((const void *)k_persistent, dim3(p.grid), dim3(p.block), args, 0, st) != cudaSuccess) return -1;
         if (launches) (*launches)++;
         if (p.timing) {
             std::vector<unsigned long long> h(8 * (size_t)p.grid);
             cudaStreamSynchronize(st);
-            cudaMemcpy(h.data(), p.barrier + 4, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-            const char *nm[5] = {"link", "arrive1+temp", "wait1", "voxel", "arrive2+wait2"};
-            fprintf(stderr, "[persist timing] %llu steps, cycles/step over %d CTAs (min / mean / max):", h[5], p.grid);
+            cudaMemcpy(h.data(), p.ctl + 4, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            const char *nm[5] = {"wait", "link", "temp+sync", "voxel", "publish"};
+            fprintf(stderr, "[persist timing] %llu steps, block %d, cycles/step over %d CTAs (min / mean / max):", h[5], p.block, p.grid);
             for (int k = 0; k < 5; k++) {
                 double mn = 1e30, mx = 0, sum = 0;
                 for (int c = 0; c < p.grid; c++) {
@@ -466,7 +510,6 @@ inline int persistent_run(PersistentPlan &p, const Dev &D, cudaStream_t st, long
             fprintf(stderr, "\n");
         }
         nsteps -= n;
-        if (nsteps > 0 && cudaMemsetAsync(p.barrier, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) return -1;
     }
     return 0;
 }
