@@ -355,8 +355,7 @@ def main():
                 bt.set_profiling(False, use_persistent=False)
             bt.step(S)
             bt.results()
-            for i in range(len(descs)):
-                bt.positions(i)
+            bt.positions(None)  # every simulation's init_pos / pos / matid (SavePositionOfAllVoxels), one D2H
             bt.close()
         barrier()
         e2e_t = time.perf_counter() - t0

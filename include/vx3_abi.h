@@ -320,7 +320,8 @@ int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *view);
 int vx3_batch_results(vx3_batch *b, vx3_result *out);
 
 /* Optional per-voxel outputs of collectResults (SavePositionOfAllVoxels):
- * init_pos / pos are [n_voxels][3], mats is matid per voxel.  NULL = skip. */
+ * init_pos / pos are [n_voxels][3], mats is matid per voxel.  NULL = skip.
+ * sim = -1: all simulations of the batch, concatenated in model order (buffers sized for the batch's total voxel count). */
 int vx3_batch_positions(vx3_batch *b, int sim, double *init_pos, double *pos, int32_t *mats);
 
 /* recommendedTimeStep() of simulation `sim` (src/VX3/VX3_VoxelyzeKernel.cu:184-217). */

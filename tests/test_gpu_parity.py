@@ -197,6 +197,45 @@ def test_batch_of_different_bodies():
             assert re.steps == ro.steps == 500
             assert re.dt == ro.dt
             np.testing.assert_allclose(list(re.current_com), list(ro.current_com), rtol=1e-12, atol=1e-15)
+        # per-voxel outputs of collectResults: one simulation at a time, and the whole batch in one call (sim = -1)
+        parts = [eng.positions(i) for i in range(len(built))]
+        ip_all, p_all, m_all = eng.positions(None)
+        np.testing.assert_array_equal(ip_all, np.concatenate([p[0] for p in parts]))
+        np.testing.assert_array_equal(p_all, np.concatenate([p[1] for p in parts]))
+        np.testing.assert_array_equal(m_all, np.concatenate([p[2] for p in parts]))
+        np.testing.assert_array_equal(parts[1][1], eng.state(1)["pos"])
+        assert set(m_all) <= {1, 2, 3}
+    finally:
+        for b, _ in built:
+            lib.vx3_builder_destroy(b)
+
+
+def test_batch_recreated_on_the_cached_arena_is_identical():
+    """Destroying a batch returns its arena / staging buffer to the cache; a batch created on the recycled (dirty) arena
+    must behave exactly like one created on fresh memory."""
+    specs = [cube_spec((4, 3, 3), seed=31, name="r0"), cube_spec((3, 3, 4), seed=32, holes=0.2, name="r1")]
+    lib = util.load_engine()
+    built = [s.build(lib) for s in specs]
+    try:
+        ref = None
+        for rounds in range(3):
+            eng = EngineBatch([d for _, d in built])
+            eng.step(300)
+            st = [eng.state(i) for i in range(2)]
+            eng.close()
+            if ref is None:
+                ref = st
+                big = EngineBatch([built[0][1]] * 1 + [built[1][1]])  # another user of the cache in between
+                big.step(50)
+                big.close()
+            else:
+                for i in range(2):
+                    util.assert_bit_equal(st[i], ref[i], KIN + LINKF + LINKS + ["link_flags", "vox_flags"], "recreated batch, sim %d" % i)
+        lib.vx3_engine_trim()
+        eng = EngineBatch([d for _, d in built])
+        eng.step(300)
+        util.assert_bit_equal(eng.state(0), ref[0], KIN, "after trim")
+        eng.close()
     finally:
         for b, _ in built:
             lib.vx3_builder_destroy(b)

@@ -4,11 +4,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -373,13 +376,34 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         return fail(VX3_ERR_NO_DEVICE, "no CUDA device available (this engine has no CPU fallback)");
     }
     if (device < 0 || device >= ndev) return fail(VX3_ERR_NO_DEVICE, "device index out of range");
+    // cudaGetDeviceProperties is slow (it queries every attribute): once per device and process
+    static std::mutex prop_mu;
+    static std::map<int, cudaDeviceProp> prop_cache;
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    {
+        std::lock_guard<std::mutex> lk(prop_mu);
+        auto it = prop_cache.find(device);
+        if (it == prop_cache.end()) {
+            cudaDeviceProp p;
+            CK(cudaGetDeviceProperties(&p, device));
+            it = prop_cache.emplace(device, p).first;
+        }
+        prop = it->second;
+    }
+    const bool timing = getenv("VX3_CREATE_TIMING") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[create timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tp0).count());
+        tp0 = now;
+    };
     if (prop.major < 10) return fail(VX3_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
     for (int i = 0; i < n; i++) {
         int rc = validate_model(models[i], i);
         if (rc) return rc;
     }
+    lap("validate");
     CK(cudaSetDevice(device));
     vx3_batch *b = new vx3_batch();
     b->device = device;
@@ -469,6 +493,14 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     std::vector<float4> lstrain(nslots, make_float4(0, 0, 0, 0));
     std::vector<float2> larea(nslots, make_float2(0, 0));
 
+    // Pass A (serial, small): materials, programs, externals, targets, CoM chunks — everything that appends to a table
+    // shared by the batch.  Pass B (below, one thread per range of simulations): the per-voxel and per-link arrays.
+    struct SimBuild {
+        std::vector<int> vm_global;
+        int ext_base = 0;
+        double maxSize = 0, maxCte = 0;
+    };
+    std::vector<SimBuild> sb(n);
     for (int s = 0; s < n; s++) {
         const vx3_model_desc &m = models[s];
         SimC &S = b->simc[s];
@@ -495,9 +527,10 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             while (sd.size() < 2) { sd.push_back(0.0f); ss.push_back(0.0f); }
             lg[i] = add_linkmat(lm, sd, ss);
         }
-        std::vector<int> vm_global(m.n_voxel_mats);
+        std::vector<int> &vm_global = sb[s].vm_global;
+        vm_global.resize(m.n_voxel_mats);
         b->matid[s].resize(m.n_voxel_mats);
-        double maxSize = 0, maxCte = 0;
+        double &maxSize = sb[s].maxSize, &maxCte = sb[s].maxCte;
         for (int i = 0; i < m.n_voxel_mats; i++) {
             const vx3_voxel_material &in = m.voxel_mats[i];
             VoxMatC vm;
@@ -589,11 +622,8 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                        (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0);
         dy.temp_amp = S.temp_amp;
         dy.temp_period = S.temp_period;
-        // voxels
-        const int vo = S.voff;
         b->vmat_local[s].assign(m.vox_mat, m.vox_mat + m.n_voxels);
-        double maxT = fabs(m.opt.temp_amplitude);
-        const int ext_base = (int)exts.size();
+        sb[s].ext_base = (int)exts.size();
         for (int i = 0; i < m.n_externals; i++) {
             const vx3_external &e = m.externals[i];
             ExtC x;
@@ -604,6 +634,34 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             exts.push_back(x);
         }
         S.tgt_off = (int)targets.size();
+        {
+            bool any_target = false;
+            for (int i = 0; i < m.n_voxel_mats; i++) any_target |= m.voxel_mats[i].is_target != 0;
+            if (any_target)
+                for (int i = 0; i < m.n_voxels; i++) {
+                    if (m.vox_mat[i] < 0 || m.vox_mat[i] >= m.n_voxel_mats) continue; // validate_model has already vetted the indices
+                    if (m.voxel_mats[m.vox_mat[i]].is_target) targets.push_back(S.voff + i); // registerTargets
+                }
+        }
+        S.ntgt = (int)targets.size() - S.tgt_off;
+        // CoM chunks
+        S.chunk_off = (int)chunks.size();
+        const int CH = 4096;
+        for (int c0 = 0; c0 < m.n_voxels; c0 += CH) chunks.push_back(Chunk{s, S.voff + c0, std::min(CH, m.n_voxels - c0), 0});
+        S.nchunks = (int)chunks.size() - S.chunk_off;
+        dy.status = VX3_SIM_RUNNING;
+        dy.link_cnt = m.n_links;
+    }
+
+    std::atomic<int> fill_err{0}, ghost_seen{0};
+    auto fill_sim = [&](int s) {
+        const vx3_model_desc &m = models[s];
+        SimC &S = b->simc[s];
+        const std::vector<int> &vm_global = sb[s].vm_global;
+        const std::vector<int> &lg = b->lmat_global[s];
+        const int vo = S.voff, ext_base = sb[s].ext_base;
+        double maxT = fabs(m.opt.temp_amplitude);
+        bool ghost = false;
         for (int i = 0; i < m.n_voxels; i++) {
             const size_t g = (size_t)vo + i;
             pose[8 * g + 0] = m.pos[3 * i]; pose[8 * g + 1] = m.pos[3 * i + 1]; pose[8 * g + 2] = m.pos[3 * i + 2];
@@ -621,7 +679,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 mom2[idx_mo(2, g)] = make_double2(m.ang_mom[3 * i + 1], m.ang_mom[3 * i + 2]);
             }
             vflags[g] = (m.vox_flags[i] & VXF_BOOLSTATE_MASK) | VXF_ENABLE_ATTACH;
-            b->any_ghost |= (m.vox_flags[i] & VX3_VOX_GHOST) != 0;
+            ghost |= (m.vox_flags[i] & VX3_VOX_GHOST) != 0;
             vmat[g] = vm_global[m.vox_mat[i]];
             vsim[g] = s;
             if (m.phase_offset) phase[g] = m.phase_offset[i];
@@ -634,7 +692,10 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 vlinks[6 * g + k] = li >= 0 ? S.loff + li : -1;
             }
             if (m.vox_ext && m.vox_ext[i] >= 0) {
-                if (m.vox_ext[i] >= m.n_externals) return cleanup(fail(VX3_ERR_INVALID, "external index out of range"));
+                if (m.vox_ext[i] >= m.n_externals) {
+                    fill_err = 1;
+                    return;
+                }
                 vext[g] = ext_base + m.vox_ext[i];
             }
             ixyz[3 * g] = m.ix[i]; ixyz[3 * g + 1] = m.iy[i]; ixyz[3 * g + 2] = m.iz[i];
@@ -642,11 +703,10 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 if (m.base_cilia) base_cilia[3 * g + k] = m.base_cilia[3 * i + k];
                 if (m.shift_cilia) shift_cilia[3 * g + k] = m.shift_cilia[3 * i + k];
             }
-            if (m.voxel_mats[m.vox_mat[i]].is_target) targets.push_back((int)g); // registerTargets
         }
-        S.ntgt = (int)targets.size() - S.tgt_off;
+        if (ghost) ghost_seen = 1;
         // collision grid cell: at least the largest possible collision envelope (2 * 0.625 * baseSizeAverage)
-        const double cell = 2 * VX3_COLLISION_ENVELOPE_RADIUS * maxSize * (1 + maxT * maxCte) * (1 + 1e-6);
+        const double cell = 2 * VX3_COLLISION_ENVELOPE_RADIUS * sb[s].maxSize * (1 + maxT * sb[s].maxCte) * (1 + 1e-6);
         S.cell_inv = cell > 0 ? 1.0 / cell : 1.0;
         // links
         for (int i = 0; i < m.n_links; i++) {
@@ -687,15 +747,26 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             larea[g] = make_float2(m.link_transverse_area ? m.link_transverse_area[i] : 0.5f * (a0 * a0 + a1 * a1),
                                    m.link_transverse_strain_sum ? m.link_transverse_strain_sum[i] : 0.0f);
         }
-        // CoM chunks
-        S.chunk_off = (int)chunks.size();
-        const int CH = 4096;
-        for (int c0 = 0; c0 < m.n_voxels; c0 += CH) chunks.push_back(Chunk{s, vo + c0, std::min(CH, m.n_voxels - c0), 0});
-        S.nchunks = (int)chunks.size() - S.chunk_off;
-        dy.status = VX3_SIM_RUNNING;
-        dy.link_cnt = m.n_links;
+    };
+    {
+        // one thread per contiguous range of simulations (disjoint output ranges); small batches stay on this thread
+        int nthreads = 1;
+        if (n >= 8 && nvox + nslots > 200000) nthreads = (int)std::min<size_t>({(size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)16, (size_t)n / 4});
+        if (nthreads <= 1) {
+            for (int s = 0; s < n; s++) fill_sim(s);
+        } else {
+            std::vector<std::thread> th;
+            for (int k = 0; k < nthreads; k++)
+                th.emplace_back([&, k]() {
+                    for (int s = (int)((long long)n * k / nthreads); s < (int)((long long)n * (k + 1) / nthreads); s++) fill_sim(s);
+                });
+            for (auto &x : th) x.join();
+        }
+        if (fill_err) return cleanup(fail(VX3_ERR_INVALID, "external index out of range"));
+        b->any_ghost |= ghost_seen != 0;
     }
 
+    lap("host model -> SoA vectors");
     Dev &D = b->D;
     memset(&D, 0, sizeof(D));
     D.nsims = n;
@@ -791,16 +862,30 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         plan.upload(&b->pplan.ndeps, ptab.ndeps);
     }
     plan.layout();
+    lap("persistent plan + arena layout");
     int rc;
     if ((rc = resources_acquire(device, plan.total, plan.up_bytes, b->res))) return cleanup(rc);
+    lap("acquire arena/staging");
     b->stream = b->res.stream;
     b->ev0 = b->res.ev0;
     b->ev1 = b->res.ev1;
-    for (const ArenaPlan::Item &it : plan.up) {
-        memcpy(b->res.h + it.off, it.src, it.bytes);
-        *it.field = b->res.d + it.off;
+    for (const ArenaPlan::Item &it : plan.up) *it.field = b->res.d + it.off;
+    if (plan.up_bytes < ((size_t)8 << 20)) {
+        for (const ArenaPlan::Item &it : plan.up) memcpy(b->res.h + it.off, it.src, it.bytes);
+    } else { // large batches: stage with several threads (one memcpy stream runs at a fraction of the host's memory bandwidth)
+        const int nt = (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; k++)
+            th.emplace_back([&, k]() {
+                for (const ArenaPlan::Item &it : plan.up) {
+                    const size_t a = it.bytes * k / nt, e = it.bytes * (k + 1) / nt;
+                    if (e > a) memcpy(b->res.h + it.off + a, (const char *)it.src + a, e - a);
+                }
+            });
+        for (auto &x : th) x.join();
     }
     for (const ArenaPlan::Item &it : plan.zero) *it.field = b->res.d + it.off;
+    lap("stage into pinned memory");
     cudaError_t ce = cudaSuccess;
     if (plan.up_bytes) ce = cudaMemcpyAsync(b->res.d, b->res.h, plan.up_bytes, cudaMemcpyHostToDevice, b->stream);
     if (ce == cudaSuccess && plan.total > plan.up_bytes) ce = cudaMemsetAsync(b->res.d + plan.up_bytes, 0, plan.total - plan.up_bytes, b->stream);
@@ -818,6 +903,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     ce = cudaStreamSynchronize(b->stream);
     if (ce == cudaSuccess) ce = cudaGetLastError();
     if (ce != cudaSuccess) return cleanup(fail(VX3_ERR_CUDA, std::string("batch init: ") + cudaGetErrorString(ce)));
+    lap("upload + device init");
     *out = b;
     return VX3_OK;
 }
@@ -1300,20 +1386,26 @@ extern "C" int vx3_batch_results(vx3_batch *b, vx3_result *out) {
 }
 
 extern "C" int vx3_batch_positions(vx3_batch *b, int sim, double *init_pos, double *pos, int32_t *mats) {
-    if (!b || sim < 0 || sim >= b->nsims) return fail(VX3_ERR_INVALID, "bad arguments");
+    if (!b || sim < -1 || sim >= b->nsims) return fail(VX3_ERR_INVALID, "bad arguments");
     CK(cudaSetDevice(b->device));
-    const SimC &S = b->simc[sim];
+    // sim = -1: every simulation of the batch, concatenated in model order (one device->host copy for the whole batch)
+    const int s0 = sim < 0 ? 0 : sim, s1 = sim < 0 ? b->nsims : sim + 1;
+    const size_t voff = b->simc[s0].voff;
+    size_t nv = 0;
+    for (int s = s0; s < s1; s++) nv += b->simc[s].nvox;
     std::vector<double> pose, ip;
     int rc;
-    if ((rc = d2h(b, pose, b->D.pose, 8 * (size_t)S.voff, 8 * (size_t)S.nvox))) return rc;
-    if ((rc = d2h(b, ip, (const double *)b->D.initpos, 3 * (size_t)S.voff, 3 * (size_t)S.nvox))) return rc;
+    if (pos && (rc = d2h(b, pose, b->D.pose, 8 * voff, 8 * nv))) return rc;
+    if (init_pos && (rc = d2h(b, ip, (const double *)b->D.initpos, 3 * voff, 3 * nv))) return rc;
     CK(cudaStreamSynchronize(b->stream));
-    for (int i = 0; i < S.nvox; i++) {
-        for (int k = 0; k < 3; k++) {
-            if (pos) pos[3 * i + k] = pose[8 * (size_t)i + k];
-            if (init_pos) init_pos[3 * i + k] = ip[3 * (size_t)i + k];
-        }
-        if (mats) mats[i] = b->matid[sim][b->vmat_local[sim][i]];
+    if (pos)
+        for (size_t i = 0; i < nv; i++)
+            for (int k = 0; k < 3; k++) pos[3 * i + k] = pose[8 * i + k];
+    if (init_pos) memcpy(init_pos, ip.data(), 3 * nv * sizeof(double));
+    if (mats) {
+        size_t o = 0;
+        for (int s = s0; s < s1; s++)
+            for (int i = 0; i < b->simc[s].nvox; i++) mats[o++] = b->matid[s][b->vmat_local[s][i]];
     }
     return VX3_OK;
 }

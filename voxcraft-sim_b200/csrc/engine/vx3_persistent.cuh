@@ -98,7 +98,35 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
     double *const P0 = D.pose, *const P1 = A.pose_alt;
 
     // ---- my link ----
-    int g = A.lk_slot[(size_t)blockIdx.x * T + tid];
+    // Lane assignment: a warp executes the union of its lanes' branches, and the large-angle branch of orientLink
+    // (VX3_Link.cu:111-125) costs ~50 % on top of the common path.  Typically a few links per CTA are in that regime, and
+    // with the host's order nearly every warp holds one or two of them (profiles/: 85 % of the warps ran the branch
+    // with 2 lanes active).  So each launch starts by sorting the CTA's links by regime: small-angle links fill the
+    // lanes from 0 up, large-angle links from the last lane down — the regime is sticky (hysteresis), so most warps stay
+    // uniform for the whole launch.  sMap translates the host's lane numbers (vx_lane) to the sorted ones.
+    __shared__ int sSlot[VX3_PERSIST_MAX_BLOCK];
+    __shared__ unsigned char sMap[VX3_PERSIST_MAX_BLOCK], sCls[VX3_PERSIST_MAX_BLOCK];
+    {
+        const int g0 = A.lk_slot[(size_t)blockIdx.x * T + tid];
+        int cls = 2; // 0 small-angle, 1 large-angle, 2 no link
+        if (g0 >= 0) cls = (D.lstate[g0 & ~VX3_PERSIST_DUP] & LKS_SMALL) ? 0 : 1;
+        sCls[tid] = (unsigned char)cls;
+        sSlot[tid] = -1;
+        __syncthreads();
+        if (tid == 0) {
+            int lo = 0, hi = T - 1;
+            for (int k = 0; k < T; k++) {
+                if (sCls[k] == 0) sMap[k] = (unsigned char)lo++;
+                else if (sCls[k] == 1) sMap[k] = (unsigned char)hi--;
+            }
+            for (int k = 0; k < T; k++)
+                if (sCls[k] == 2) sMap[k] = (unsigned char)lo++; // empty lanes in between
+        }
+        __syncthreads();
+        sSlot[sMap[tid]] = g0;
+        __syncthreads();
+    }
+    int g = sSlot[tid];
     const bool dup = g >= 0 && (g & VX3_PERSIST_DUP);
     if (g >= 0) g &= ~VX3_PERSIST_DUP;
     LinkRegs L;
@@ -173,6 +201,7 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             vl[i] = A.vx_lane[((size_t)blockIdx.x * T + tid) * 6 + i];
+            if (vl[i] >= 0) vl[i] = sMap[vl[i]];
             if (D.vlinks[6 * (size_t)v + i] < 0) vl[i] = -1;
         }
         const int ext = D.vext[v];
@@ -391,12 +420,13 @@ inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, c
     int ax = 0;
     for (int a = 1; a < 3; a++)
         if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
-    std::sort(idx.begin() + lo, idx.begin() + hi, [&](int p, int q) {
+    // (coordinate, index) is a strict total order, so the partition below is unique whatever nth_element does inside
+    const int ncl = nc / 2;
+    const int mid = lo + (int)((long long)(hi - lo) * ncl / nc);
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int p, int q) {
         const int cp = ixyz[3 * ((size_t)voff + p) + ax], cq = ixyz[3 * ((size_t)voff + q) + ax];
         return cp != cq ? cp < cq : p < q;
     });
-    const int ncl = nc / 2;
-    const int mid = lo + (int)((long long)(hi - lo) * ncl / nc);
     persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of);
     persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of);
 }
@@ -418,7 +448,7 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     for (int i = 0; i < V; i++) idx[i] = i;
     persist_rcb(idx, 0, V, 0, G, ixyz.data(), voff, cta_of);
     std::vector<std::vector<int>> vox(G), lnk(G);
-    for (int i = 0; i < V; i++) vox[cta_of[i]].push_back(i);
+    for (int i = 0; i < V; i++) vox[cta_of[i]].push_back(i); // ascending voxel index within a CTA
     for (int l = 0; l < L; l++) {
         const int2 e = lends[(size_t)loff + l];
         if (e.x < 0) continue;

@@ -63,9 +63,13 @@ class Batch:
         return list(arr)
 
     def positions(self, sim=0):
+        """(init_pos, pos, matid) of one simulation, or of the whole batch concatenated when sim is None / -1."""
         import numpy as np
-        nv = self.sizes[sim][0]
-        ip, p, m = np.zeros((nv, 3)), np.zeros((nv, 3)), np.zeros(nv, np.int32)
+        if sim is None or sim < 0:
+            sim, nv = -1, sum(s[0] for s in self.sizes)
+        else:
+            nv = self.sizes[sim][0]
+        ip, p, m = np.empty((nv, 3)), np.empty((nv, 3)), np.empty(nv, np.int32)
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         self._check(self.lib.vx3_batch_positions(self.h, sim, dp(ip), dp(p), m.ctypes.data_as(C.POINTER(C.c_int32))), "vx3_batch_positions")
         return ip, p, m
