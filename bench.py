@@ -333,8 +333,16 @@ def main():
         alg_bytes_launch = b_alg * nvox
     avg_launch_s = 1e-3 * top[1][0] / top[1][1]
     achieved = alg_bytes_launch / avg_launch_s / 1e9
+    traffic, traffic_src = None, None
+    try:  # ncu-measured DRAM bytes per launch of this kernel on this workload (profiles/traffic.json), when a capture exists
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ent = json.load(f).get(args.workload, {}).get(top[0])
+        if ent and (args.workload != "c3" or args.sims_per_gpu == 512):
+            traffic, traffic_src = ent["bytes_per_launch"], ent["capture"] + (" (" + ent["note"] + ")" if ent.get("note") else "")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_share_of_step": top[1][0] / total_prof,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_share_of_step": top[1][0] / total_prof,
                 "alg_bytes_per_launch": alg_bytes_launch, "avg_launch_us": 1e6 * avg_launch_s,
                 "kernel_ms": {k: round(v[0], 4) for k, v in stats.items()}, "kernel_launches": {k: v[1] for k, v in stats.items()}}
 

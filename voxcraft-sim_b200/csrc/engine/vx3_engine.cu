@@ -255,6 +255,10 @@ struct vx3_batch {
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
     bool any_ghost = false;
+    int link_queue = -1; // k_links variant: -1 = still being timed (launch_links), 0 = in place, 1 = large-angle queue
+    int lq_trials = 0;
+    double lq_ms[2] = {0, 0};
+    cudaEvent_t lq_ev[2] = {nullptr, nullptr};
     PersistentPlan pplan; // on-chip path for a single small collision-free body
     bool use_persistent = true;
 
@@ -915,6 +919,8 @@ extern "C" void vx3_batch_destroy(vx3_batch *b) {
     for (int sd = 0; sd < 2; sd++)
         if (b->halo.side[sd].peer_open) cudaIpcCloseMemHandle(b->halo.side[sd].peer_flag);
     for (auto &e : b->prof.ev) cudaEventDestroy(e);
+    for (auto &e : b->lq_ev)
+        if (e) cudaEventDestroy(e);
     for (void *p : b->allocs) cudaFree(p);
     resources_release(b->res); // arena, staging, stream and events go back to the cache
     delete b;
@@ -977,7 +983,7 @@ static long long next_com_step(const vx3_batch *b) {
 static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
     b->link_smtab = b->D.n_vmats <= VX3_SM_VMATS && b->D.n_lmats <= VX3_SM_LMATS;
     b->vox_smtab = b->D.n_vmats <= VX3_SM_VMATS;
-    const void *kl = b->link_smtab ? (const void *)k_links<true> : (const void *)k_links<false>;
+    const void *kl = b->link_smtab ? (const void *)k_links<true, true> : (const void *)k_links<false, true>; // the larger of the two variants
     const void *kv = b->vox_smtab ? (const void *)k_voxels<true> : (const void *)k_voxels<false>;
     int nl = 0, nv = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, kl, VX3_LINK_T, 0));
@@ -990,13 +996,51 @@ static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
     return VX3_OK;
 }
 
+// The link pass has two bit-identical variants (k_links<.., QUEUE>: the large-angle branch in place, or densely through a
+// shared-memory queue); which is faster depends on the batch, so the first streaming steps of a batch time both with CUDA
+// events (2 warm-up trials, then 3 each) and the batch keeps the faster.  VX3_LINK_QUEUE=0/1 pins the choice.
+static void launch_links(vx3_batch *b) {
+    const Dev &D = b->D;
+    cudaStream_t st = b->stream;
+    int variant = b->link_queue;
+    bool trial = false;
+    if (variant < 0) {
+        if (!b->lq_ev[0]) {
+            const char *e = getenv("VX3_LINK_QUEUE");
+            if (e && (e[0] == '0' || e[0] == '1')) b->link_queue = variant = e[0] - '0';
+            else if (b->halo.on) b->link_queue = variant = 1; // slabs of one large body (measured faster there); and a host-side event wait
+                                                              // inside a step could deadlock slabs that one thread queues in rounds
+            else {
+                cudaEventCreate(&b->lq_ev[0]);
+                cudaEventCreate(&b->lq_ev[1]);
+            }
+        }
+        if (variant < 0) {
+            trial = true;
+            variant = b->lq_trials & 1;
+            cudaEventRecord(b->lq_ev[0], st);
+        }
+    }
+    if (b->link_smtab) {
+        if (variant) LAUNCH_SM(KC_LINKS, (k_links<true, true>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        else LAUNCH_SM(KC_LINKS, (k_links<true, false>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+    } else {
+        if (variant) LAUNCH_SM(KC_LINKS, (k_links<false, true>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        else LAUNCH_SM(KC_LINKS, (k_links<false, false>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+    }
+    if (trial) {
+        cudaEventRecord(b->lq_ev[1], st);
+        float ms = 0;
+        if (cudaEventSynchronize(b->lq_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, b->lq_ev[0], b->lq_ev[1]) == cudaSuccess && b->lq_trials >= 2)
+            b->lq_ms[variant] += ms;
+        if (++b->lq_trials >= 8) b->link_queue = b->lq_ms[1] < b->lq_ms[0] ? 1 : 0;
+    }
+}
+
 static void launch_step(vx3_batch *b, bool check_stop) {
     const Dev &D = b->D;
     cudaStream_t st = b->stream;
-    if (D.nlinkslots > 0) {
-        if (b->link_smtab) LAUNCH_SM(KC_LINKS, k_links<true>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-        else LAUNCH_SM(KC_LINKS, k_links<false>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-    }
+    if (D.nlinkslots > 0) launch_links(b);
     if (b->any_collide) {
         LAUNCH(KC_GRID_COUNT, k_grid_count, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
         LAUNCH(KC_GRID_SCAN, k_grid_scan, 1, 1024, D);

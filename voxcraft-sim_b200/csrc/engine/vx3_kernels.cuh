@@ -123,70 +123,130 @@ __device__ __forceinline__ double2 ldv_if(const double2 *p, bool on) {
 
 __device__ __forceinline__ int4 link_c4(const Dev &D, long long g) { return g < D.nlinkslots ? __ldg(D.lc4 + g) : make_int4(-1, -1, 0, 0); }
 
+// Large-angle queue (VX3_LINK_QUEUE): the large-angle branch of orientLink costs ~540 instructions on top of ~780, and in an
+// actuated body a few percent of the links are in that regime — spread so that most warps hold one or two of them and
+// execute the whole branch for 2 active lanes (profiles/r01_sass_regions_k_links_c3.txt: 35 % of the kernel's warp
+// instructions ran with <= 3 lanes).  So the branch is not taken in place: a thread whose link needs it puts the branch's
+// inputs (pos2, angle2, rest: 8 doubles) into a shared-memory queue, and after a CTA barrier the first n threads of the
+// CTA run the branch for the n queued links, densely, and hand angle1 / angle2 / pos2.x / angle1v back through the same
+// slots.  Same arithmetic on the same values, executed by another lane: bit-identical.
+// Whether it pays depends on the batch: while warp 0 runs the branch the CTA's other warps wait at the barrier, which costs
+// latency hiding (measured: config 5 -11 %, config 3 +14 % on k_links), so both variants are compiled and the engine times
+// them on the batch's first streaming steps and keeps the faster one (vx3_engine.cu, launch_links).
+
 // SMTAB: the batch's material tables fit the shared-memory copies (the normal case); otherwise they are read from global
-template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles) {
+template <bool SMTAB, bool QUEUE> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles) {
     __shared__ LinkSmem sm;
+    __shared__ double sQ[QUEUE ? VX3_LINK_T : 1][12];
+    __shared__ int sQn[2];
     const int tid = threadIdx.x;
     const long long G = gridDim.x;
     if (SMTAB) {
         for (int i = tid; i < D.n_vmats * (int)(sizeof(VoxMatL) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.vm)[i] = reinterpret_cast<const int *>(D.vmatl_tab)[i];
         for (int i = tid; i < D.n_lmats * (int)(sizeof(LinkMatC) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.lm)[i] = reinterpret_cast<const int *>(D.lmat_tab)[i];
-        __syncthreads();
     }
+    if (tid < 2) sQn[tid] = 0;
+    __syncthreads();
     long long tile = blockIdx.x;
     int4 c4 = link_c4(D, tile * VX3_LINK_T + tid);
-    for (; tile < ntiles; tile += G) {
+    for (int it = 0; tile < ntiles; tile += G, it++) {
         // ---- the next item's constant indices (consumed by the next iteration) ----
         const int4 c4n = link_c4(D, (tile + G) * VX3_LINK_T + tid);
         const int gc = (int)(tile * VX3_LINK_T + tid);
         const int4 c = c4;
         c4 = c4n;
-        if (c.x < 0) continue; // empty pool slot / past the end
-        // ---- every load of this link, all independent ----
-        const double2 h0 = ldv(D.lh(0, gc)), h1 = ldv(D.lh(1, gc)), h2 = ldv(D.lh(2, gc)), h3 = ldv(D.lh(3, gc)), h4 = ldv(D.lh(4, gc));
-        const float4 sn = ldv(D.lstrain + gc);
-        const float2 ar = ldv(D.larea + gc);
+        bool live = c.x >= 0; // empty pool slot / past the end
         LinkRegs L;
-        L.state = ldv(D.lstate + gc);
-        const double2 *pa = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.x), *pb = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.y);
-        const double2 a0 = ldv(pa), a1 = ldv(pa + 1), a2 = ldv(pa + 2), a3 = ldv(pa + 3);
-        const double2 b0 = ldv(pb), b1 = ldv(pb + 1), b2 = ldv(pb + 2), b3 = ldv(pb + 3);
-        const int vmN = ldv(D.vmat + c.x), vmP = ldv(D.vmat + c.y);
-        const int4 *hp = reinterpret_cast<const int4 *>(D.simd + c.w);
-        const int4 hot0 = ldv(hp), hot1 = ldv(hp + 1);
-        L.pos2 = V3(h0.x, h0.y, h1.x);
-        L.angle1v = V3(h1.y, h2.x, h2.y);
-        L.angle2v = V3(h3.x, h3.y, h4.x);
-        L.rest = h4.y;
-        const V3 pN(a0.x, a0.y, a1.x), pP(b0.x, b0.y, b1.x);
-        const Q4 qN(a1.y, a2.x, a2.y, a3.x), qP(b1.y, b2.x, b2.y, b3.x);
-        const float tN = unpack_t(a3.y), pdN = unpack_pd(a3.y), tP = unpack_t(b3.y), pdP = unpack_pd(b3.y);
-        const double t = __hiloint2double(hot0.y, hot0.x);
-        const int status = hot0.z;
-        const float dt = __int_as_float(hot1.x);
-        const int hot_flags = hot1.y;
-        const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+        LinkMid mid;
+        float dmN = 0, dmP = 0;
+        mid.small = true;
+        if (!QUEUE && !live) continue;
+        if (live) {
+            // ---- every load of this link, all independent ----
+            const double2 h0 = ldv(D.lh(0, gc)), h1 = ldv(D.lh(1, gc)), h2 = ldv(D.lh(2, gc)), h3 = ldv(D.lh(3, gc)), h4 = ldv(D.lh(4, gc));
+            const float4 sn = ldv(D.lstrain + gc);
+            const float2 ar = ldv(D.larea + gc);
+            L.state = ldv(D.lstate + gc);
+            const double2 *pa = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.x), *pb = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.y);
+            const double2 a0 = ldv(pa), a1 = ldv(pa + 1), a2 = ldv(pa + 2), a3 = ldv(pa + 3);
+            const double2 b0 = ldv(pb), b1 = ldv(pb + 1), b2 = ldv(pb + 2), b3 = ldv(pb + 3);
+            const int vmN = ldv(D.vmat + c.x), vmP = ldv(D.vmat + c.y);
+            const int4 *hp = reinterpret_cast<const int4 *>(D.simd + c.w);
+            const int4 hot0 = ldv(hp), hot1 = ldv(hp + 1);
+            L.pos2 = V3(h0.x, h0.y, h1.x);
+            L.angle1v = V3(h1.y, h2.x, h2.y);
+            L.angle2v = V3(h3.x, h3.y, h4.x);
+            L.rest = h4.y;
+            const V3 pN(a0.x, a0.y, a1.x), pP(b0.x, b0.y, b1.x);
+            const Q4 qN(a1.y, a2.x, a2.y, a3.x), qP(b1.y, b2.x, b2.y, b3.x);
+            const float tN = unpack_t(a3.y), pdN = unpack_pd(a3.y), tP = unpack_t(b3.y), pdP = unpack_pd(b3.y);
+            const double t = __hiloint2double(hot0.y, hot0.x);
+            const int status = hot0.z;
+            const float dt = __int_as_float(hot1.x);
+            const int hot_flags = hot1.y;
+            const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+            // the few end-material values, read up front so that their latencies overlap
+            struct { double size, on_after; float cte, dmn; int fixed; } mN, mP;
+            {
+                const VoxMatL &a = SMTAB ? sm.vm[vmN] : D.vmatl_tab[vmN], &b = SMTAB ? sm.vm[vmP] : D.vmatl_tab[vmP];
+                mN.size = a.size[axis]; mN.on_after = a.thermal_on_after; mN.cte = a.alphaCTE; mN.dmn = a.dampMultNum; mN.fixed = a.fixed;
+                mP.size = b.size[axis]; mP.on_after = b.thermal_on_after; mP.cte = b.alphaCTE; mP.dmn = b.dampMultNum; mP.fixed = b.fixed;
+            }
+            if (L.state & (LKS_DETACHED | LKS_REMOVED)) live = false;
+            if (status != VX3_SIM_RUNNING || dt == 0 || (mN.fixed && mP.fixed)) live = false;
+            if (!QUEUE && !live) continue;
+            if (live) {
+                L.state &= ~LKS_JUST_CREATED;
+                L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
+                L.area = ar.x; L.tsum = ar.y;
+                if (hot_flags & SHF_THERMAL) { // updateRestLength() from either end's setTemperature (VX3_Voxel.cu:107-113)
+                    const bool actN = !mN.fixed && !(mN.on_after > t), actP = !mP.fixed && !(mP.on_after > t);
+                    if (actN || actP) L.rest = 0.5 * (mN.size * (1 + tN * mN.cte) + mP.size * (1 + tP * mP.cte)); // VX3_Voxel.h:95-98
+                }
+                // dampingMultiplier() = 2*_sqrtMass*zetaInternal/previousDt (float)
+                dmN = mN.dmn / pdN;
+                dmP = mP.dmn / pdP;
+                link_stage_a(L, pN, qN, pP, qP, mid);
+            }
+        }
+        if (QUEUE) {
+            // ---- the large-angle branch, densely (see above).  Two counters alternate so that one barrier pair per tile suffices ----
+            int *qn = &sQn[it & 1];
+            int slot = -1;
+            if (live && !mid.small) {
+                slot = atomicAdd(qn, 1);
+                double *q = sQ[slot];
+                q[0] = mid.pos2.x; q[1] = mid.pos2.y; q[2] = mid.pos2.z;
+                q[3] = mid.angle2.w; q[4] = mid.angle2.x; q[5] = mid.angle2.y; q[6] = mid.angle2.z;
+                q[7] = L.rest;
+            }
+            __syncthreads();
+            const int nq = *qn;
+            if (tid < nq) {
+                double *q = sQ[tid];
+                V3 p2(q[0], q[1], q[2]), a1v;
+                Q4 a1, a2(q[3], q[4], q[5], q[6]);
+                link_stage_large(p2, a1, a2, a1v, q[7]);
+                q[0] = p2.x;
+                q[1] = a1.w; q[2] = a1.x; q[3] = a1.y; q[4] = a1.z;
+                q[5] = a2.w; q[6] = a2.x; q[7] = a2.y; q[8] = a2.z;
+                q[9] = a1v.x; q[10] = a1v.y; q[11] = a1v.z;
+            }
+            if (tid == 0) sQn[(it + 1) & 1] = 0; // the other counter: nobody touches it until after the next barrier
+            __syncthreads();
+            if (slot >= 0) {
+                const double *q = sQ[slot];
+                mid.pos2 = V3(q[0], 0, 0);
+                mid.angle1 = Q4(q[1], q[2], q[3], q[4]);
+                mid.angle2 = Q4(q[5], q[6], q[7], q[8]);
+                mid.angle1v = V3(q[9], q[10], q[11]);
+            }
+            if (!live) continue;
+        } else if (!mid.small)
+            link_stage_large(mid.pos2, mid.angle1, mid.angle2, mid.angle1v, L.rest);
         const LinkMatC &lm = SMTAB ? sm.lm[c.z] : D.lmat_tab[c.z];
-        // the few end-material values, read up front so that their latencies overlap
-        struct { double size, on_after; float cte, dmn; int fixed; } mN, mP;
-        {
-            const VoxMatL &a = SMTAB ? sm.vm[vmN] : D.vmatl_tab[vmN], &b = SMTAB ? sm.vm[vmP] : D.vmatl_tab[vmP];
-            mN.size = a.size[axis]; mN.on_after = a.thermal_on_after; mN.cte = a.alphaCTE; mN.dmn = a.dampMultNum; mN.fixed = a.fixed;
-            mP.size = b.size[axis]; mP.on_after = b.thermal_on_after; mP.cte = b.alphaCTE; mP.dmn = b.dampMultNum; mP.fixed = b.fixed;
-        }
-        if (L.state & (LKS_DETACHED | LKS_REMOVED)) continue;
-        if (status != VX3_SIM_RUNNING || dt == 0 || (mN.fixed && mP.fixed)) continue;
-        L.state &= ~LKS_JUST_CREATED;
-        L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
-        L.area = ar.x; L.tsum = ar.y;
-        if (hot_flags & SHF_THERMAL) { // updateRestLength() from either end's setTemperature (VX3_Voxel.cu:107-113)
-            const bool actN = !mN.fixed && !(mN.on_after > t), actP = !mP.fixed && !(mP.on_after > t);
-            if (actN || actP) L.rest = 0.5 * (mN.size * (1 + tN * mN.cte) + mP.size * (1 + tP * mP.cte)); // VX3_Voxel.h:95-98
-        }
-        // dampingMultiplier() = 2*_sqrtMass*zetaInternal/previousDt (float)
-        const float dmN = mN.dmn / pdN, dmP = mP.dmn / pdP;
         LinkOut o;
-        link_update_forces(L, lm, D.strain_pool, D.stress_pool, pN, qN, pP, qP, dmN, dmP, o);
+        link_stage_c(L, mid, lm, D.strain_pool, D.stress_pool, dmN, dmP, o);
         *D.lh(0, gc) = make_double2(L.pos2.x, L.pos2.y);
         *D.lh(1, gc) = make_double2(L.pos2.z, L.angle1v.x);
         *D.lh(2, gc) = make_double2(L.angle1v.y, L.angle1v.z);

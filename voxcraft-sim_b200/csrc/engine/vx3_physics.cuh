@@ -165,13 +165,20 @@ __device__ __forceinline__ float link_update_strain(LinkRegs &L, const LinkMatC 
     }
 }
 
-// VX3_Link::updateForces (VX3_Link.cu:135-218) incl. orientLink (:90-133).  dmN/dmP = dampingMultiplier() of
-// the two end voxels (VX3_Voxel.h:206-208).
-__device__ __forceinline__ void link_update_forces(LinkRegs &L, const LinkMatC &m, const float *sd, const float *ss, const V3 &posN,
-                                                   const Q4 &qN, const V3 &posP, const Q4 &qP, float dmN, float dmP, LinkOut &o) {
+// VX3_Link::updateForces (VX3_Link.cu:135-218) incl. orientLink (:90-133), in three stages so that a kernel can run the
+// (rare, expensive) large-angle branch of orientLink for a whole tile in a few dense warps instead of in every warp:
+//   link_stage_a      orientLink up to the small/large decision (:91-110) and the small-angle case (:111-114)
+//   link_stage_large  the large-angle case (:115-125) + angle1's rotation vector — pure function of (pos2, angle2, rest)
+//   link_stage_c      rotation vector of angle2, strain/stress, beam forces, damping, rotation back (:127-218)
+// link_update_forces runs the three in sequence.  dmN/dmP = dampingMultiplier() of the two end voxels (VX3_Voxel.h:206-208).
+struct LinkMid {
+    V3 pos2, angle1v;
+    Q4 angle1, angle2;
+    bool small;
+};
+
+__device__ __forceinline__ void link_stage_a(LinkRegs &L, const V3 &posN, const Q4 &qN, const V3 &posP, const Q4 &qP, LinkMid &m) {
     const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
-    const V3 oldPos2 = L.pos2, oldAngle1v = L.angle1v, oldAngle2v = L.angle2v;
-    // ---- orientLink ----
     V3 pos2 = toAxisX(axis, posP - posN);
     Q4 angle1 = toAxisX(axis, qN);
     Q4 angle2 = toAxisX(axis, qP);
@@ -192,13 +199,31 @@ __device__ __forceinline__ void link_update_forces(LinkRegs &L, const LinkMatC &
     if (smallAngle) {
         pos2.x -= L.rest;
         L.state |= LKS_SMALL;
-    } else {
-        angle1.FromAngleToPosX(pos2);
-        angle2 = angle1 * angle2;
-        pos2 = V3(pos2.Length() - L.rest, 0, 0);
+    } else
         L.state &= ~LKS_SMALL;
-    }
-    const V3 angle1v = angle1.ToRotationVector();
+    m.pos2 = pos2;
+    m.angle1 = angle1;
+    m.angle2 = angle2;
+    m.angle1v = V3(0, 0, 0); // ToRotationVector of the identity
+    m.small = smallAngle;
+}
+
+__device__ __forceinline__ void link_stage_large(V3 &pos2, Q4 &angle1, Q4 &angle2, V3 &angle1v, double rest) {
+    angle1 = Q4();
+    angle1.FromAngleToPosX(pos2);
+    angle2 = angle1 * angle2;
+    pos2 = V3(pos2.Length() - rest, 0, 0);
+    angle1v = angle1.ToRotationVector();
+}
+
+__device__ __forceinline__ void link_stage_c(LinkRegs &L, const LinkMid &mid, const LinkMatC &m, const float *sd, const float *ss, float dmN, float dmP,
+                                             LinkOut &o) {
+    const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+    const V3 oldPos2 = L.pos2, oldAngle1v = L.angle1v, oldAngle2v = L.angle2v;
+    const V3 pos2 = mid.pos2;
+    const Q4 angle1 = mid.angle1, angle2 = mid.angle2;
+    const bool smallAngle = mid.small;
+    const V3 angle1v = mid.angle1v;
     const V3 angle2v = angle2.ToRotationVector();
     L.pos2 = pos2;
     L.angle1v = angle1v;
@@ -254,6 +279,14 @@ __device__ __forceinline__ void link_update_forces(LinkRegs &L, const LinkMatC &
     o.momentPos = momentPos;
 }
 
+__device__ __forceinline__ void link_update_forces(LinkRegs &L, const LinkMatC &m, const float *sd, const float *ss, const V3 &posN,
+                                                   const Q4 &qN, const V3 &posP, const Q4 &qP, float dmN, float dmP, LinkOut &o) {
+    LinkMid mid;
+    link_stage_a(L, posN, qN, posP, qP, mid);
+    if (!mid.small) link_stage_large(mid.pos2, mid.angle1, mid.angle2, mid.angle1v, L.rest);
+    link_stage_c(L, mid, m, sd, ss, dmN, dmP, o);
+}
+
 // ------------------------------------------------------------------ voxel
 struct VoxRegs {
     V3 pos, linMom, angMom;
@@ -280,23 +313,30 @@ __device__ __forceinline__ void voxel_floor_force(VoxRegs &v, const VoxMatC &m, 
         v.flags &= ~VX3_VOX_FLOOR_STATIC_FRICTION;
 }
 
-// VX3_Voxel::timeStep (VX3_Voxel.cu:162-277) for dt != 0.  linkF/linkM = sums of the incident links' forces and
-// moments in the voxel's local frame (force()/moment() :350-397); contact/ciliaF = pending contactForce and
-// CiliaForce*mat->Cilia; ff = force-field value at the pre-step position.
-__device__ __forceinline__ void voxel_time_step(VoxRegs &v, const VoxMatC &m, const ExtC *ext, int ix, int iy, int iz, float tempe,
-                                                const V3 &linkF, const V3 &linkM, const V3 &contact, const V3 &ciliaF, const V3 &ff,
-                                                double dt) {
+// VX3_Voxel::timeStep (VX3_Voxel.cu:162-277) for dt != 0, in the three parts its data flow falls into, so that a kernel
+// can run them in different warps (the on-chip persistent kernel does; the streaming kernel calls voxel_time_step):
+//   voxel_step_translate  force() + force field + floor + linear integration + translational DOF fixes (:175-218, :231-244 x/y/z)
+//                         reads the OLD orientation; owns pos, linMom, flags
+//   voxel_step_rotate     moment() + angular integration + rotational DOF fixes (:220-256); owns orient, angMom
+//   voxel_step_join       on the floor in static friction -> angMom = 0 (:259-264): needs the translate part's new pos.z / flags
+// linkF/linkM = sums of the incident links' forces and moments in the voxel's local frame (force()/moment() :350-397);
+// contact/ciliaF = pending contactForce and CiliaForce*mat->Cilia; ff = force-field value at the pre-step position.
+__device__ __forceinline__ bool voxel_fixed_all(const ExtC *ext) { return ext && (ext->dof & 0x3F) == 0x3F; }
+
+__device__ __forceinline__ void voxel_step_translate(V3 &pos, V3 &linMom, int &flags, const Q4 &orient, const VoxMatC &m, const ExtC *ext, int ix,
+                                                     int iy, int iz, float tempe, const V3 &linkF, const V3 &contact, const V3 &ciliaF,
+                                                     const V3 &ff, double dt) {
+    VoxRegs v; // the floor helpers work on a VoxRegs view
+    v.pos = pos; v.linMom = linMom; v.flags = flags; v.orient = orient;
     const bool floorEnabled = (v.flags & VX3_VOX_FLOOR_ENABLED) != 0;
-    if (ext && (ext->dof & 0x3F) == 0x3F) {
+    if (voxel_fixed_all(ext)) {
         const double s = m.nomSize;
-        v.pos = V3(ix * s, iy * s, iz * s) + V3(ext->translation[0], ext->translation[1], ext->translation[2]);
-        v.orient = Q4(ext->rotq[0], ext->rotq[1], ext->rotq[2], ext->rotq[3]);
-        v.linMom = V3();
-        v.angMom = V3();
+        pos = V3(ix * s, iy * s, iz * s) + V3(ext->translation[0], ext->translation[1], ext->translation[2]);
+        linMom = V3();
         return;
     }
     // force()
-    V3 curForce = v.orient.RotateVec3D(linkF);
+    V3 curForce = orient.RotateVec3D(linkF);
     if (ext) curForce += V3(ext->force[0], ext->force[1], ext->force[2]);
     curForce -= (v.linMom * m.massInverse) * m.globalDampT;
     curForce.z += m.gravityForce;
@@ -321,35 +361,62 @@ __device__ __forceinline__ void voxel_time_step(VoxRegs &v, const VoxMatC &m, co
     } else
         v.flags &= ~VX3_VOX_FLOOR_STATIC_FRICTION;
     v.pos += translate;
-    // moment()
-    V3 curMoment = v.orient.RotateVec3D(linkM);
-    if (ext) curMoment += V3(ext->moment[0], ext->moment[1], ext->moment[2]);
-    curMoment -= (v.angMom * m.momentInertiaInverse) * m.globalDampR;
-    v.angMom += curMoment * dt;
-    v.orient = Q4(v.angMom * (dt * m.momentInertiaInverse)) * v.orient;
     if (ext) {
         const int dof = ext->dof;
         const double size = m.nomSize;
         if (dof & VX3_DOF_X_TRANSLATE) { v.pos.x = ix * size + ext->translation[0]; v.linMom.x = 0; }
         if (dof & VX3_DOF_Y_TRANSLATE) { v.pos.y = iy * size + ext->translation[1]; v.linMom.y = 0; }
         if (dof & VX3_DOF_Z_TRANSLATE) { v.pos.z = iz * size + ext->translation[2]; v.linMom.z = 0; }
+    }
+    pos = v.pos;
+    linMom = v.linMom;
+    flags = v.flags;
+}
+
+__device__ __forceinline__ void voxel_step_rotate(Q4 &orient, V3 &angMom, const VoxMatC &m, const ExtC *ext, const V3 &linkM, double dt) {
+    if (voxel_fixed_all(ext)) {
+        orient = Q4(ext->rotq[0], ext->rotq[1], ext->rotq[2], ext->rotq[3]);
+        angMom = V3();
+        return;
+    }
+    // moment()
+    V3 curMoment = orient.RotateVec3D(linkM);
+    if (ext) curMoment += V3(ext->moment[0], ext->moment[1], ext->moment[2]);
+    curMoment -= (angMom * m.momentInertiaInverse) * m.globalDampR;
+    angMom += curMoment * dt;
+    orient = Q4(angMom * (dt * m.momentInertiaInverse)) * orient;
+    if (ext) {
+        const int dof = ext->dof;
         const int rot = dof & (VX3_DOF_X_ROTATE | VX3_DOF_Y_ROTATE | VX3_DOF_Z_ROTATE);
         if (rot) {
             if (rot == (VX3_DOF_X_ROTATE | VX3_DOF_Y_ROTATE | VX3_DOF_Z_ROTATE)) {
-                v.orient = Q4(ext->rotq[0], ext->rotq[1], ext->rotq[2], ext->rotq[3]);
-                v.angMom = V3();
+                orient = Q4(ext->rotq[0], ext->rotq[1], ext->rotq[2], ext->rotq[3]);
+                angMom = V3();
             } else {
-                V3 tmpRotVec = v.orient.ToRotationVector();
-                if (dof & VX3_DOF_X_ROTATE) { tmpRotVec.x = 0; v.angMom.x = 0; }
-                if (dof & VX3_DOF_Y_ROTATE) { tmpRotVec.y = 0; v.angMom.y = 0; }
-                if (dof & VX3_DOF_Z_ROTATE) { tmpRotVec.z = 0; v.angMom.z = 0; }
-                v.orient.FromRotationVector(tmpRotVec);
+                V3 tmpRotVec = orient.ToRotationVector();
+                if (dof & VX3_DOF_X_ROTATE) { tmpRotVec.x = 0; angMom.x = 0; }
+                if (dof & VX3_DOF_Y_ROTATE) { tmpRotVec.y = 0; angMom.y = 0; }
+                if (dof & VX3_DOF_Z_ROTATE) { tmpRotVec.z = 0; angMom.z = 0; }
+                orient.FromRotationVector(tmpRotVec);
             }
         }
     }
-    if (floorEnabled && floor_penetration(m, tempe, v.pos.z) >= 0) { // VX3_Voxel.cu:259-264
-        if (v.flags & VX3_VOX_FLOOR_STATIC_FRICTION) v.angMom = V3(0, 0, 0);
-    }
+}
+
+// true = the voxel rests on the floor in static friction after this step: its angular momentum is cleared (VX3_Voxel.cu:259-264)
+__device__ __forceinline__ bool voxel_step_join(const V3 &pos, int flags, const VoxMatC &m, const ExtC *ext, float tempe) {
+    if (voxel_fixed_all(ext)) return false; // timeStep returned before (:166-173)
+    const bool floorEnabled = (flags & VX3_VOX_FLOOR_ENABLED) != 0;
+    return floorEnabled && floor_penetration(m, tempe, pos.z) >= 0 && (flags & VX3_VOX_FLOOR_STATIC_FRICTION);
+}
+
+__device__ __forceinline__ void voxel_time_step(VoxRegs &v, const VoxMatC &m, const ExtC *ext, int ix, int iy, int iz, float tempe,
+                                                const V3 &linkF, const V3 &linkM, const V3 &contact, const V3 &ciliaF, const V3 &ff,
+                                                double dt) {
+    const Q4 orient0 = v.orient;
+    voxel_step_translate(v.pos, v.linMom, v.flags, orient0, m, ext, ix, iy, iz, tempe, linkF, contact, ciliaF, ff, dt);
+    voxel_step_rotate(v.orient, v.angMom, m, ext, linkM, dt);
+    if (voxel_step_join(v.pos, v.flags, m, ext, tempe)) v.angMom = V3(0, 0, 0);
 }
 
 } // namespace vx3
