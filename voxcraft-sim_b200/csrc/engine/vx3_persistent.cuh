@@ -14,7 +14,12 @@
 // (point-to-point flags, release/acquire).  The reference orders the same two phases with two device-wide child-grid
 // syncs per step (src/VX3/VX3_VoxelyzeKernel.cu:259-269 gpu_update_links, :306-312 gpu_update_voxels).
 //
-// Temperature: each voxel's temperature for the next step is computed by its owner and travels in its pose record.
+// Voxel phase in three roles: a voxel's step is three nearly independent latency chains — translation (force, floor,
+// friction, position), rotation (moment, quaternion update: sqrt/sin/cos) and the next step's temperature (sin) — so three
+// threads in three different warps run them concurrently (lanes [0,RO) translate, [RO,2RO) rotate, [2RO,3RO) temperature;
+// RO = the CTA's voxel count rounded up to a warp).  They meet through shared memory (old orientation, this step's
+// temperature, the "resting on the floor" decision that clears the angular momentum) and each stores its own part of
+// the 64-byte pose record.  Temperature: each voxel's temperature for the next step travels in its pose record.
 // The physics is the same code as the streaming kernels (vx3_physics.cuh), so the two paths alternate freely (the
 // streaming path takes the CoM-sampling steps) and are bit-identical.
 #pragma once
@@ -46,6 +51,7 @@ struct PersistentPlan {
     int *deps = nullptr;           // [grid][VX3_PERSIST_MAX_DEPS]: CTAs whose poses this CTA's links read
     int *ndeps = nullptr;          // [grid]
     double *pose_alt = nullptr;    // [nvox][8]: odd-parity pose buffer
+    int ro = 0;                    // voxel lanes per role
 };
 #define VX3_PERSIST_DUP (1 << 30)
 
@@ -53,7 +59,9 @@ struct PersistArgs {
     unsigned int *ctl, *flags;
     const int *lk_slot, *vx_id, *vx_lane, *deps, *ndeps;
     double *pose_alt;
+    int ro; // role offset: voxel lanes per role (multiple of 32, 3 * ro <= block)
 };
+#define VX3_PERSIST_MAX_RO 96
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     unsigned int v;
@@ -173,9 +181,15 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
 #pragma unroll
     for (int k = 0; k < 12; k++) sF[tid][k] = 0.0;
 
-    // ---- my voxel ----
-    const int v = A.vx_id[(size_t)blockIdx.x * T + tid];
-    VoxRegs r;
+    // ---- my voxel and my role in its step: 0 translate, 1 rotate, 2 temperature ----
+    __shared__ double sOrient[2][VX3_PERSIST_MAX_RO][4]; // orientation by step parity: the rotate role writes the new one while the translate role reads the old
+    __shared__ float sTemp[VX3_PERSIST_MAX_RO];          // this step's temperature (temperature role -> translate role)
+    __shared__ int sZero[2][VX3_PERSIST_MAX_RO];         // translate role -> rotate role, by step parity: on the floor in static friction, clear angMom (VX3_Voxel.cu:259-264)
+    const int role = tid / A.ro, vk = tid - role * A.ro;
+    const int v = role < 3 ? A.vx_id[(size_t)blockIdx.x * T + vk] : -1;
+    V3 pos, linMom, angMom;
+    Q4 orient;
+    int vflags = 0;
     VoxMatC vm;
     float tempe = 0, tempe_next = 0; // this step's temperature / the next step's (published in the pose record)
     float pd_cur = 0;
@@ -186,29 +200,34 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
     bool vthermal = false, vint = false;
     if (v >= 0) {
         vm = D.vmat_tab[D.vmat[v]];
-        r.flags = D.vflags[v];
+        vflags = D.vflags[v];
         phase = D.phase[v];
-        vthermal = vary && !(r.flags & VXF_REMOVED) && !vm.fixed;
-        vint = !(r.flags & VXF_REMOVED) && !vm.fixed;
-        load_pose(P0, v, r.pos, r.orient);
+        vthermal = vary && !(vflags & VXF_REMOVED) && !vm.fixed;
+        vint = !(vflags & VXF_REMOVED) && !vm.fixed;
+        load_pose(P0, v, pos, orient);
         const double tp = P0[8 * (size_t)v + 7];
         tempe_next = unpack_t(tp);
         pd_cur = unpack_pd(tp);
         tempe = D.tempe[v];
         const double2 m0 = *D.mo(0, v), m1 = *D.mo(1, v), m2 = *D.mo(2, v);
-        r.linMom = V3(m0.x, m0.y, m1.x);
-        r.angMom = V3(m1.y, m2.x, m2.y);
+        linMom = V3(m0.x, m0.y, m1.x);
+        angMom = V3(m1.y, m2.x, m2.y);
 #pragma unroll
         for (int i = 0; i < 6; i++) {
-            vl[i] = A.vx_lane[((size_t)blockIdx.x * T + tid) * 6 + i];
+            vl[i] = A.vx_lane[((size_t)blockIdx.x * T + vk) * 6 + i];
             if (vl[i] >= 0) vl[i] = sMap[vl[i]];
             if (D.vlinks[6 * (size_t)v + i] < 0) vl[i] = -1;
         }
         const int ext = D.vext[v];
         px = ext >= 0 ? &D.exts[ext] : nullptr;
         ic[0] = D.ixyz[3 * (size_t)v]; ic[1] = D.ixyz[3 * (size_t)v + 1]; ic[2] = D.ixyz[3 * (size_t)v + 2];
-        // the odd-parity buffer starts as a copy: voxels that are never integrated keep their record in both
-        store_pose(P1, v, r.pos, r.orient, tempe_next, pd_cur);
+        if (role == 0) {
+            // the odd-parity buffer starts as a copy: voxels that are never integrated keep their record in both
+            store_pose(P1, v, pos, orient, tempe_next, pd_cur);
+            sZero[0][vk] = 0;
+        } else if (role == 1) {
+            sOrient[0][vk][0] = orient.w; sOrient[0][vk][1] = orient.x; sOrient[0][vk][2] = orient.y; sOrient[0][vk][3] = orient.z;
+        }
     }
     const bool fixedAll = px && (px->dof & 0x3F) == 0x3F;
 
@@ -274,10 +293,10 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
             if (intP) pdP = dtF;
         }
         TICK(1);
-        // --- the temperature the NEXT step starts with (gpu_update_temperature at t+dt) ---
-        if (v >= 0) {
+        // --- this step's temperature for the translate role (floor penetration) ---
+        if (v >= 0 && role == 2) {
             tempe = tempe_next;
-            if (vthermal && !(vm.thermal_on_after > t + dtF)) tempe_next = voxel_temperature(S, t + dtF, phase);
+            sTemp[vk] = tempe;
         }
         if (__syncthreads_or(mydiv)) { // a link of this CTA diverged in this step: doTimeStep returns false before the voxel pass
             if (tid == 0) atomicMax(divword, (unsigned int)(nsteps - s));
@@ -285,40 +304,60 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
             break;
         }
         TICK(2);
-        // ================= voxel phase (gpu_update_voxels) =================
+        // ================= voxel phase (gpu_update_voxels), three roles in three warps =================
         if (v >= 0 && vint) {
-            V3 F(0, 0, 0), M(0, 0, 0);
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                if (vl[i] >= 0) {
-                    const double *f = sF[vl[i]] + ((i & 1) ? 6 : 0);
-                    F += V3(f[0], f[1], f[2]);
-                    M += V3(f[3], f[4], f[5]);
-                }
-            }
-            V3 ff(0, 0, 0);
-            if (S.has_ff && !fixedAll) {
-                double vars[9];
-                prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
-                ff.x = eval_slot(D, S, VX3_PROG_FORCE_X, vars, 0.0);
-                ff.y = eval_slot(D, S, VX3_PROG_FORCE_Y, vars, 0.0);
-                ff.z = eval_slot(D, S, VX3_PROG_FORCE_Z, vars, 0.0);
-            }
-            voxel_time_step(r, vm, px, ic[0], ic[1], ic[2], tempe, F, M, V3(), V3(), ff, dt);
-            if (S.has_attach_cond) {
-                double vars[9];
-                prog_vars(S, dy, t, r.pos.x, r.pos.y, r.pos.z, vars);
-                bool all = true;
-                for (int c = 0; c < 5 && all; c++) all = eval_slot(D, S, VX3_PROG_ATTACH_0 + c, vars, 1.0) > 0;
-                if (all) r.flags |= VXF_ENABLE_ATTACH;
-                else r.flags &= ~VXF_ENABLE_ATTACH;
-            }
-            pd_cur = dtF;
             double *w = Pw + 8 * (size_t)v;
-            stcg2(w, r.pos.x, r.pos.y);
-            stcg2(w + 2, r.pos.z, r.orient.w);
-            stcg2(w + 4, r.orient.x, r.orient.y);
-            stcg2(w + 6, r.orient.z, pack_tp(tempe_next, dtF));
+            if (role == 0) { // ---- translate ----
+                V3 F(0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    if (vl[i] >= 0) {
+                        const double *f = sF[vl[i]] + ((i & 1) ? 6 : 0);
+                        F += V3(f[0], f[1], f[2]);
+                    }
+                V3 ff(0, 0, 0);
+                if (S.has_ff && !fixedAll) {
+                    double vars[9];
+                    prog_vars(S, dy, t, pos.x, pos.y, pos.z, vars);
+                    ff.x = eval_slot(D, S, VX3_PROG_FORCE_X, vars, 0.0);
+                    ff.y = eval_slot(D, S, VX3_PROG_FORCE_Y, vars, 0.0);
+                    ff.z = eval_slot(D, S, VX3_PROG_FORCE_Z, vars, 0.0);
+                }
+                const double *oq = sOrient[s & 1][vk];
+                const Q4 orient0(oq[0], oq[1], oq[2], oq[3]);
+                tempe = sTemp[vk];
+                voxel_step_translate(pos, linMom, vflags, orient0, vm, px, ic[0], ic[1], ic[2], tempe, F, V3(), V3(), ff, dt);
+                sZero[(s + 1) & 1][vk] = voxel_step_join(pos, vflags, vm, px, tempe) ? 1 : 0;
+                if (S.has_attach_cond) {
+                    double vars[9];
+                    prog_vars(S, dy, t, pos.x, pos.y, pos.z, vars);
+                    bool all = true;
+                    for (int c = 0; c < 5 && all; c++) all = eval_slot(D, S, VX3_PROG_ATTACH_0 + c, vars, 1.0) > 0;
+                    if (all) vflags |= VXF_ENABLE_ATTACH;
+                    else vflags &= ~VXF_ENABLE_ATTACH;
+                }
+                stcg2(w, pos.x, pos.y);
+                __stcg(w + 2, pos.z);
+            } else if (role == 1) { // ---- rotate ----
+                if (sZero[s & 1][vk]) angMom = V3(0, 0, 0); // the previous step's join
+                V3 M(0, 0, 0);
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    if (vl[i] >= 0) {
+                        const double *f = sF[vl[i]] + ((i & 1) ? 9 : 3);
+                        M += V3(f[0], f[1], f[2]);
+                    }
+                voxel_step_rotate(orient, angMom, vm, px, M, dt);
+                double *nq = sOrient[(s + 1) & 1][vk];
+                nq[0] = orient.w; nq[1] = orient.x; nq[2] = orient.y; nq[3] = orient.z;
+                __stcg(w + 3, orient.w);
+                stcg2(w + 4, orient.x, orient.y);
+                __stcg(w + 6, orient.z);
+            } else { // ---- the temperature the NEXT step starts with (gpu_update_temperature at t+dt) ----
+                if (vthermal && !(vm.thermal_on_after > t + dtF)) tempe_next = voxel_temperature(S, t + dtF, phase);
+                pd_cur = dtF;
+                __stcg(w + 7, pack_tp(tempe_next, dtF));
+            }
         }
         t += dtF; // currentTime += dt (:352)
         done = s + 1;
@@ -357,12 +396,17 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
         D.lstrain[g] = make_float4(L.strain, L.maxStrain, L.strainOffset, L.stress);
         D.lstate[g] = L.state;
     }
+    // (the translate role's last join decision is visible to the rotate role: every exit path passes a CTA barrier after it)
     if (v >= 0) {
-        *D.mo(0, v) = make_double2(r.linMom.x, r.linMom.y);
-        *D.mo(1, v) = make_double2(r.linMom.z, r.angMom.x);
-        *D.mo(2, v) = make_double2(r.angMom.y, r.angMom.z);
-        D.vflags[v] = r.flags;
-        D.tempe[v] = tempe;
+        double *mo0 = reinterpret_cast<double *>(D.mo(0, v)), *mo1 = reinterpret_cast<double *>(D.mo(1, v)), *mo2 = reinterpret_cast<double *>(D.mo(2, v));
+        if (role == 0) {
+            mo0[0] = linMom.x; mo0[1] = linMom.y; mo1[0] = linMom.z;
+            D.vflags[v] = vflags;
+        } else if (role == 1) {
+            if (vint && sZero[done & 1][vk]) angMom = V3(0, 0, 0);
+            mo1[1] = angMom.x; mo2[0] = angMom.y; mo2[1] = angMom.z;
+        } else
+            D.tempe[v] = tempe;
     }
     if (timing && tid == 0) {
         unsigned long long *o = reinterpret_cast<unsigned long long *>(A.ctl + 4) + 8 * blockIdx.x;
@@ -396,7 +440,12 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
         while (ld_acquire_u32(A.ctl + 1) < G) {}
     }
     __syncthreads();
-    if (v >= 0) store_pose(P0, v, r.pos, r.orient, tempe_next, pd_cur);
+    if (v >= 0) { // each role restores its part of the record in the batch's pose array (the even buffer)
+        double *w = P0 + 8 * (size_t)v;
+        if (role == 0) { w[0] = pos.x; w[1] = pos.y; w[2] = pos.z; }
+        else if (role == 1) { w[3] = orient.w; w[4] = orient.x; w[5] = orient.y; w[6] = orient.z; }
+        else w[7] = pack_tp(tempe_next, pd_cur);
+    }
 }
 
 // host side ---------------------------------------------------------------------------------------------------
@@ -458,8 +507,11 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     }
     int most = 1;
     for (int c = 0; c < G; c++) most = std::max(most, (int)std::max(vox[c].size(), lnk[c].size()));
-    int T = (most + 31) / 32 * 32;
-    if (T > VX3_PERSIST_MAX_BLOCK) return; // blocks too large for one item per thread: streaming path
+    int mostv = 1;
+    for (int c = 0; c < G; c++) mostv = std::max(mostv, (int)vox[c].size());
+    const int ro = (mostv + 31) / 32 * 32; // voxel lanes per role (translate / rotate / temperature)
+    int T = (std::max(most, 3 * ro) + 31) / 32 * 32;
+    if (T > VX3_PERSIST_MAX_BLOCK || ro > VX3_PERSIST_MAX_RO) return; // blocks too large for one item per thread: streaming path
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_persistent, T, 0) != cudaSuccess || nb < 1) {
         cudaGetLastError();
@@ -504,6 +556,7 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     p.timing = getenv("VX3_PERSIST_TIMING") != nullptr;
     p.grid = G;
     p.block = T;
+    p.ro = ro;
     p.ok = true;
 }
 
@@ -515,7 +568,7 @@ inline int persistent_run(PersistentPlan &p, const Dev &D, cudaStream_t st, long
         int cs = check_stop ? 1 : 0;
         Dev d = D;
         int tm = p.timing ? 1 : 0;
-        PersistArgs a{p.ctl, p.flags, p.lk_slot, p.vx_id, p.vx_lane, p.deps, p.ndeps, p.pose_alt};
+        PersistArgs a{p.ctl, p.flags, p.lk_slot, p.vx_id, p.vx_lane, p.deps, p.ndeps, p.pose_alt, p.ro};
         if (cudaMemsetAsync(p.ctl, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) return -1;
         if (cudaMemsetAsync(p.flags, 0, (size_t)p.grid * 32 * sizeof(unsigned int), st) != cudaSuccess) return -1;
         void *args[] = {(void *)&d, (void *)&n, (void *)&cs, (void *)&tm, (void *)&a};
