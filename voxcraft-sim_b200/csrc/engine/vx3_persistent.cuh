@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "vx3_kernels.cuh"
@@ -122,13 +123,37 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
         sSlot[tid] = -1;
         __syncthreads();
         if (tid == 0) {
-            int lo = 0, hi = T - 1;
+            // Large-angle links go to the warp that has a scheduler to itself: warps are dealt to the SM's four schedulers
+            // round-robin, so with nw warps the scheduler (nw % 4) hosts one warp fewer than schedulers 0..(nw % 4)-1 — its
+            // first warp, index nw % 4, is the least contended place for the longest instruction stream.  Overflow goes
+            // to the lanes from the top down; small-angle links fill the remaining lanes from 0 up.
+            const int nw = T / 32, lw = nw % 4;
+            int nl = 0;
+            for (int k = 0; k < T; k++) nl += sCls[k] == 1;
+            const int in_lw = lw < nw - 1 ? (nl < 32 ? nl : 32) : 0; // lanes [32*lw, 32*lw + in_lw), then (T - 1 - j) for the rest
+            int li = 0, lo = 0;
+            auto next_free = [&](int x) { // next lane not reserved for a large-angle link
+                for (;; x++) {
+                    if (x >= T) return x;
+                    const bool res = (x >= 32 * lw && x < 32 * lw + in_lw) || (x > T - 1 - (nl - in_lw));
+                    if (!res) return x;
+                }
+            };
+            lo = next_free(0);
             for (int k = 0; k < T; k++) {
-                if (sCls[k] == 0) sMap[k] = (unsigned char)lo++;
-                else if (sCls[k] == 1) sMap[k] = (unsigned char)hi--;
+                if (sCls[k] == 1) {
+                    sMap[k] = (unsigned char)(li < in_lw ? 32 * lw + li : T - 1 - (li - in_lw));
+                    li++;
+                } else if (sCls[k] == 0) {
+                    sMap[k] = (unsigned char)lo;
+                    lo = next_free(lo + 1);
+                }
             }
             for (int k = 0; k < T; k++)
-                if (sCls[k] == 2) sMap[k] = (unsigned char)lo++; // empty lanes in between
+                if (sCls[k] == 2) { // empty lanes take what is left
+                    sMap[k] = (unsigned char)lo;
+                    lo = next_free(lo + 1);
+                }
         }
         __syncthreads();
         sSlot[sMap[tid]] = g0;
@@ -454,7 +479,7 @@ struct PersistentTables {
 };
 
 // recursive coordinate bisection: voxels idx[lo, hi) go to CTAs [c0, c0 + nc)
-inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, const int16_t *ixyz, int voff, std::vector<int> &cta_of) {
+inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, const int16_t *ixyz, int voff, std::vector<int> &cta_of, int depth = 0) {
     if (nc == 1) {
         for (int i = lo; i < hi; i++) cta_of[idx[i]] = c0;
         return;
@@ -476,8 +501,14 @@ inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, c
         const int cp = ixyz[3 * ((size_t)voff + p) + ax], cq = ixyz[3 * ((size_t)voff + q) + ax];
         return cp != cq ? cp < cq : p < q;
     });
-    persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of);
-    persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of);
+    if (depth < 2 && hi - lo > 2048) { // the two halves touch disjoint ranges of idx and cta_of: run the top levels on 4 threads
+        std::thread left([&]() { persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of, depth + 1); });
+        persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of, depth + 1);
+        left.join();
+    } else {
+        persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of, depth + 1);
+        persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of, depth + 1);
+    }
 }
 
 // Decides whether the batch qualifies, cuts the body into blocks and builds the per-CTA lane tables.  The device arrays
