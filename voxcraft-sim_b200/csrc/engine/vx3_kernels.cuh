@@ -265,6 +265,125 @@ template <bool SMTAB, bool QUEUE> __global__ void __launch_bounds__(VX3_LINK_T, 
     }
 }
 
+// Third variant of the link pass, without any CTA barrier: a lane whose link turns out to need the large-angle branch
+// does NOT process it — it pushes the link's slot number onto its warp's private queue (shared memory, warp-aggregated
+// push) and idles for the rest of the iteration, so the warp runs the small-angle path only (~780 instructions instead
+// of ~1200).  Whenever a warp's queue holds 32 entries (and once more at the end) the warp spends one iteration on a
+// DENSE pass: every lane takes one deferred link, reloads its inputs (nothing has been stored for it yet, so they are
+// unchanged) and runs the complete update, large-angle branch included, with all lanes busy.  The gathers of a dense pass
+// are uncoalesced, but only the few percent of deferred links pay for that.  Same arithmetic on the same inputs: bit-identical
+// to the other two variants.
+template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links_deferred(Dev D, int ntiles) {
+    __shared__ LinkSmem sm;
+    __shared__ int sDef[VX3_LINK_T / 32][64];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long G = gridDim.x;
+    if (SMTAB) {
+        for (int i = tid; i < D.n_vmats * (int)(sizeof(VoxMatL) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.vm)[i] = reinterpret_cast<const int *>(D.vmatl_tab)[i];
+        for (int i = tid; i < D.n_lmats * (int)(sizeof(LinkMatC) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.lm)[i] = reinterpret_cast<const int *>(D.lmat_tab)[i];
+    }
+    __syncthreads();
+    long long tile = blockIdx.x;
+    int4 c4 = link_c4(D, tile * VX3_LINK_T + tid);
+    int nd = 0; // entries in this warp's queue (warp-uniform)
+    for (;;) {
+        const bool tiles_left = tile < ntiles; // uniform over the CTA
+        bool dense;
+        int gc;
+        int4 c;
+        if (nd >= 32 || (!tiles_left && nd > 0)) { // ---- dense pass over deferred links ----
+            dense = true;
+            const int take = nd < 32 ? nd : 32;
+            gc = lane < take ? sDef[wid][nd - take + lane] : -1;
+            nd -= take;
+            c = gc >= 0 ? __ldg(D.lc4 + gc) : make_int4(-1, -1, 0, 0);
+        } else if (tiles_left) { // ---- the next tile; the item after it is prefetched into registers ----
+            dense = false;
+            const int4 c4n = link_c4(D, (tile + G) * VX3_LINK_T + tid);
+            gc = (int)(tile * VX3_LINK_T + tid);
+            c = c4;
+            c4 = c4n;
+            tile += G;
+        } else
+            break;
+        bool live = c.x >= 0; // empty pool slot / past the end
+        LinkRegs L;
+        LinkMid mid;
+        float dmN = 0, dmP = 0;
+        mid.small = true;
+        if (live) {
+            // ---- every load of this link, all independent ----
+            const double2 h0 = ldv(D.lh(0, gc)), h1 = ldv(D.lh(1, gc)), h2 = ldv(D.lh(2, gc)), h3 = ldv(D.lh(3, gc)), h4 = ldv(D.lh(4, gc));
+            const float4 sn = ldv(D.lstrain + gc);
+            const float2 ar = ldv(D.larea + gc);
+            L.state = ldv(D.lstate + gc);
+            const double2 *pa = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.x), *pb = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.y);
+            const double2 a0 = ldv(pa), a1 = ldv(pa + 1), a2 = ldv(pa + 2), a3 = ldv(pa + 3);
+            const double2 b0 = ldv(pb), b1 = ldv(pb + 1), b2 = ldv(pb + 2), b3 = ldv(pb + 3);
+            const int vmN = ldv(D.vmat + c.x), vmP = ldv(D.vmat + c.y);
+            const int4 *hp = reinterpret_cast<const int4 *>(D.simd + c.w);
+            const int4 hot0 = ldv(hp), hot1 = ldv(hp + 1);
+            L.pos2 = V3(h0.x, h0.y, h1.x);
+            L.angle1v = V3(h1.y, h2.x, h2.y);
+            L.angle2v = V3(h3.x, h3.y, h4.x);
+            L.rest = h4.y;
+            const V3 pN(a0.x, a0.y, a1.x), pP(b0.x, b0.y, b1.x);
+            const Q4 qN(a1.y, a2.x, a2.y, a3.x), qP(b1.y, b2.x, b2.y, b3.x);
+            const float tN = unpack_t(a3.y), pdN = unpack_pd(a3.y), tP = unpack_t(b3.y), pdP = unpack_pd(b3.y);
+            const double t = __hiloint2double(hot0.y, hot0.x);
+            const int status = hot0.z;
+            const float dt = __int_as_float(hot1.x);
+            const int hot_flags = hot1.y;
+            const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+            struct { double size, on_after; float cte, dmn; int fixed; } mN, mP;
+            {
+                const VoxMatL &a = SMTAB ? sm.vm[vmN] : D.vmatl_tab[vmN], &b = SMTAB ? sm.vm[vmP] : D.vmatl_tab[vmP];
+                mN.size = a.size[axis]; mN.on_after = a.thermal_on_after; mN.cte = a.alphaCTE; mN.dmn = a.dampMultNum; mN.fixed = a.fixed;
+                mP.size = b.size[axis]; mP.on_after = b.thermal_on_after; mP.cte = b.alphaCTE; mP.dmn = b.dampMultNum; mP.fixed = b.fixed;
+            }
+            if (L.state & (LKS_DETACHED | LKS_REMOVED)) live = false;
+            if (status != VX3_SIM_RUNNING || dt == 0 || (mN.fixed && mP.fixed)) live = false;
+            if (live) {
+                L.state &= ~LKS_JUST_CREATED;
+                L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
+                L.area = ar.x; L.tsum = ar.y;
+                if (hot_flags & SHF_THERMAL) { // updateRestLength() from either end's setTemperature (VX3_Voxel.cu:107-113)
+                    const bool actN = !mN.fixed && !(mN.on_after > t), actP = !mP.fixed && !(mP.on_after > t);
+                    if (actN || actP) L.rest = 0.5 * (mN.size * (1 + tN * mN.cte) + mP.size * (1 + tP * mP.cte)); // VX3_Voxel.h:95-98
+                }
+                dmN = mN.dmn / pdN; // dampingMultiplier() = 2*_sqrtMass*zetaInternal/previousDt (float)
+                dmP = mP.dmn / pdP;
+                link_stage_a(L, pN, qN, pP, qP, mid);
+            }
+        }
+        // ---- defer the links that need the large-angle branch (not in a dense pass: there they run it) ----
+        const bool defer = live && !dense && !mid.small;
+        const unsigned dm = __ballot_sync(0xFFFFFFFFu, defer);
+        if (defer) sDef[wid][nd + __popc(dm & ((1u << lane) - 1u))] = gc;
+        nd += __popc(dm);
+        __syncwarp();
+        if (!live || defer) continue;
+        if (!mid.small) link_stage_large(mid.pos2, mid.angle1, mid.angle2, mid.angle1v, L.rest);
+        const LinkMatC &lm = SMTAB ? sm.lm[c.z] : D.lmat_tab[c.z];
+        LinkOut o;
+        link_stage_c(L, mid, lm, D.strain_pool, D.stress_pool, dmN, dmP, o);
+        *D.lh(0, gc) = make_double2(L.pos2.x, L.pos2.y);
+        *D.lh(1, gc) = make_double2(L.pos2.z, L.angle1v.x);
+        *D.lh(2, gc) = make_double2(L.angle1v.y, L.angle1v.z);
+        *D.lh(3, gc) = make_double2(L.angle2v.x, L.angle2v.y);
+        *D.lh(4, gc) = make_double2(L.angle2v.z, L.rest);
+        D.lstrain[gc] = make_float4(L.strain, L.maxStrain, L.strainOffset, L.stress);
+        D.lstate[gc] = L.state;
+        *D.lf(0, gc) = make_double2(o.forceNeg.x, o.forceNeg.y);
+        *D.lf(1, gc) = make_double2(o.forceNeg.z, o.momentNeg.x);
+        *D.lf(2, gc) = make_double2(o.momentNeg.y, o.momentNeg.z);
+        *D.lf(3, gc) = make_double2(o.forcePos.x, o.forcePos.y);
+        *D.lf(4, gc) = make_double2(o.forcePos.z, o.momentPos.x);
+        *D.lf(5, gc) = make_double2(o.momentPos.y, o.momentPos.z);
+        if (L.strain > 100) D.simd[c.w].diverged = 1;
+    }
+}
+
 // ------------------------------------------------------------------ voxels
 __device__ __forceinline__ void prog_vars(const SimC &S, const SimD &dy, double t, double x, double y, double z, double *vars) {
     vars[0] = x; vars[1] = y; vars[2] = z;
