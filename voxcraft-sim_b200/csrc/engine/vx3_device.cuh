@@ -195,9 +195,10 @@ struct Dev {
     // receiving voxel and direction instead makes the voxel pass stream, but a direction without a link leaves a 16-byte hole
     // in its sector, and every partially written sector costs an ECC read-modify-write at eviction: measured 2.5x slower.)
     double2 *lf2;
-    // collision grid (hashed uniform grid)
+    // collision grid (hashed uniform grid, per-bucket lists)
     int32_t hmask;
-    int32_t *cell_cnt, *cell_start, *cell_cursor, *cell_items;
+    int32_t *cell_head; // [hmask+1] first voxel of the bucket's list, -1 = empty (reset every step)
+    int32_t *cell_next; // [nvox] next voxel in the same bucket
     int4 *vcell;      // cx, cy, cz, bucket (bucket<0: not in grid)
     Cand *cands;
     int32_t *cand_count;

@@ -47,8 +47,8 @@ extern "C" size_t vx3_abi_sizeof(const char *name) {
 }
 
 // ------------------------------------------------------------------ per-kernel timing (bench hook)
-enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_COUNT, KC_GRID_SCAN, KC_GRID_FILL, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_SIGNALS, KC_COM, KC_TAIL, KC_PERSISTENT, KC_HALO, KC_COUNT };
-static const char *const kKernelNames[KC_COUNT] = {"k_links", "k_voxels", "k_grid_count", "k_grid_scan", "k_grid_fill", "k_contact", "k_resolve",
+enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_BUILD, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_SIGNALS, KC_COM, KC_TAIL, KC_PERSISTENT, KC_HALO, KC_COUNT };
+static const char *const kKernelNames[KC_COUNT] = {"k_links", "k_voxels", "k_grid_build", "k_contact", "k_resolve",
                                                    "k_detach", "k_surface", "k_secondary", "k_signals", "k_com_partial", "k_tail", "k_persistent", "k_halo"};
 struct Profiler {
     bool on = false;
@@ -842,10 +842,8 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         while (H < 2 * (int)nvox && H < (1 << 24)) H <<= 1;
         D.hmask = H - 1;
         plan.zeroed(&D.contact, nvox * 3);
-        plan.zeroed(&D.cell_cnt, (size_t)H);
-        plan.zeroed(&D.cell_start, (size_t)H + 1);
-        plan.zeroed(&D.cell_cursor, (size_t)H);
-        plan.zeroed(&D.cell_items, nvox);
+        plan.zeroed(&D.cell_head, (size_t)H);
+        plan.zeroed(&D.cell_next, nvox);
         plan.zeroed(&D.vcell, nvox);
         D.cand_cap = 2048;
         plan.zeroed(&D.cands, (size_t)D.cand_cap);
@@ -1050,10 +1048,9 @@ static void launch_step(vx3_batch *b, bool check_stop) {
     cudaStream_t st = b->stream;
     if (D.nlinkslots > 0) launch_links(b);
     if (b->any_collide) {
-        LAUNCH(KC_GRID_COUNT, k_grid_count, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
-        LAUNCH(KC_GRID_SCAN, k_grid_scan, 1, 1024, D);
-        LAUNCH(KC_GRID_FILL, k_grid_fill, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
-        LAUNCH(KC_CONTACT, k_contact, cdiv(D.nvox, 128), 128, D);
+        cudaMemsetAsync(D.cell_head, 0xFF, sizeof(int32_t) * ((size_t)D.hmask + 1), st); // every bucket's list empty (-1)
+        LAUNCH(KC_GRID_BUILD, k_grid_build, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
+        LAUNCH(KC_CONTACT, k_contact, cdiv(D.nvox, VX3_CONTACT_WARPS), 32 * VX3_CONTACT_WARPS, D);
         if (b->any_sticky) LAUNCH(KC_RESOLVE, k_resolve, 1, 1024, D);
     } else if (b->any_detach || b->any_secondary) { // keep the surface flags current (regenerateSurfaceVoxels after a detach / removal)
         LAUNCH(KC_SURFACE, k_surface, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);

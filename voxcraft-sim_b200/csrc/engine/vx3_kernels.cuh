@@ -1,6 +1,6 @@
 // Streaming step kernels: one launch per phase over the concatenated SoA arrays of the whole batch.
 // Phase order per step = VX3_VoxelyzeKernel::doTimeStep (src/VX3/VX3_VoxelyzeKernel.cu:237-359):
-//   k_links -> [k_grid_count, k_grid_scan, k_grid_fill, k_contact, k_resolve] -> [k_detach] -> k_voxels
+//   k_links -> [k_grid_build, k_contact, k_resolve] -> [k_detach] -> k_voxels -> [k_signals] -> [k_secondary]
 //   -> [k_com_partial] -> k_tail
 #pragma once
 #include "vx3_physics.cuh"
@@ -549,9 +549,14 @@ __device__ __forceinline__ unsigned cell_hash(int sim, int cx, int cy, int cz) {
 __device__ __forceinline__ bool sim_collides(const SimC &S) { return S.enable_collision || S.enable_attach; }
 
 // regenerateSurfaceVoxels (:495-513) + uniform-grid insert (replaces the O(S^2) sweep of gpu_update_attach :833-843).
+// The grid is a hash table of per-bucket lists: a surface voxel pushes itself onto its bucket's list with one atomicExch
+// (cell_head[bucket] -> cell_next[v]); no counting, no scan, no second pass.  The order inside a list is whatever the
+// atomics produce — the contact phase sorts each voxel's partners by index before it accumulates, so the
+// result does not depend on it.  cell_head is reset to -1 by a memset node before this kernel.
 // Also publishes this step's temperature (what updateTemperature :219-235 set) for the contact phase.
-__global__ void __launch_bounds__(VX3_BLOCK) k_grid_count(Dev D) {
+__global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0) *D.cand_count = 0;
     if (v >= D.nvox) return;
     const int sim = D.vsim[v];
     const SimC &S = D.simc[sim];
@@ -574,7 +579,7 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_count(Dev D) {
             vc.y = (int)floor(p.y * S.cell_inv);
             vc.z = (int)floor(p.z * S.cell_inv);
             vc.w = (int)(cell_hash(sim, vc.x, vc.y, vc.z) & (unsigned)D.hmask);
-            atomicAdd(&D.cell_cnt[vc.w], 1);
+            D.cell_next[v] = atomicExch(&D.cell_head[vc.w], v);
         }
     }
     D.vcell[v] = vc;
@@ -595,63 +600,6 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_surface(Dev D) {
     }
     const int nf = interior ? (flags | VX3_VOX_SURFACE) : (flags & ~VX3_VOX_SURFACE);
     if (nf != flags) D.vflags[v] = nf;
-}
-
-// exclusive scan of the bucket counts (single CTA, int4-vectorised), resets the counters for the next step
-__global__ void __launch_bounds__(1024) k_grid_scan(Dev D) {
-    __shared__ int part[1024];
-    const int H = D.hmask + 1;            // power of two >= 1024
-    const int per = H / 1024;             // buckets per thread (multiple of 4 when H >= 4096)
-    const int b0 = threadIdx.x * per;
-    int s = 0;
-    if (per >= 4) {
-        const int4 *c4 = reinterpret_cast<const int4 *>(D.cell_cnt + b0);
-        for (int i = 0; i < per / 4; i++) {
-            const int4 c = c4[i];
-            s += c.x + c.y + c.z + c.w;
-        }
-    } else
-        for (int i = 0; i < per; i++) s += D.cell_cnt[b0 + i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) { // Hillis-Steele inclusive scan
-        int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    int run = part[threadIdx.x] - s;
-    if (per >= 4) {
-        int4 *c4 = reinterpret_cast<int4 *>(D.cell_cnt + b0);
-        int4 *s4 = reinterpret_cast<int4 *>(D.cell_start + b0);
-        int4 *u4 = reinterpret_cast<int4 *>(D.cell_cursor + b0);
-        for (int i = 0; i < per / 4; i++) {
-            const int4 c = c4[i];
-            int4 o;
-            o.x = run; o.y = o.x + c.x; o.z = o.y + c.y; o.w = o.z + c.z;
-            run = o.w + c.w;
-            s4[i] = o;
-            u4[i] = o;
-            c4[i] = make_int4(0, 0, 0, 0);
-        }
-    } else
-        for (int i = 0; i < per; i++) {
-            const int c = D.cell_cnt[b0 + i];
-            D.cell_start[b0 + i] = run;
-            D.cell_cursor[b0 + i] = run;
-            D.cell_cnt[b0 + i] = 0;
-            run += c;
-        }
-    if (threadIdx.x == 1023) D.cell_start[H] = part[1023];
-    if (threadIdx.x == 0) *D.cand_count = 0;
-}
-
-__global__ void __launch_bounds__(VX3_BLOCK) k_grid_fill(Dev D) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= D.nvox) return;
-    const int b = D.vcell[v].w;
-    if (b < 0) return;
-    D.cell_items[atomicAdd(&D.cell_cursor[b], 1)] = v;
 }
 
 // is_neighbor (VX3_VoxelyzeKernel.cu:651-680), iterative
@@ -693,61 +641,147 @@ __device__ __forceinline__ V3 pair_contact_force(const Dev &D, int hi, int lo, c
     return V3(0, 0, 0);
 }
 
-// Contact phase of one surface voxel: all partners inside the collision envelope
-// (handle_collision_attachment, VX3_VoxelyzeKernel.cu:682-727), accumulated in ascending partner index = the
-// canonical sequential pair order.  emit = also count target hits and emit attach candidates
-// for the pairs this voxel leads (it is the higher index).
-__device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
-    const int sim = D.vsim[v];
-    const SimC &S = D.simc[sim];
-    SimD &dy = D.simd[sim];
-    const int4 vc = D.vcell[v];
-    const int matv = D.vmat[v];
-    const VoxMatC &mv = D.vmat_tab[matv];
-    const V3 pv = load_pos(D.pose, v);
-    const double bsv = base_size_average(mv, D.tempe[v]);
+// Is voxel u (found in one of the 27 cells around v's) a contact partner of v?  The envelope test of
+// handle_collision_attachment (VX3_VoxelyzeKernel.cu:682-705); direct lattice neighbours are skipped (is_neighbor depth 1)
+// unless the link was made this step (`fresh`: its contact force is added and taken back, :827-830).
+struct ContactSelf {
+    int v, sim, matv;
+    int4 vc;
+    V3 pv;
+    double bsv;
+    bool fixedv;
     int vl[6], vo[6]; // own links and their other ends
+};
+__device__ __forceinline__ void contact_self(const Dev &D, int v, ContactSelf &c) {
+    c.v = v;
+    c.sim = D.vsim[v];
+    c.vc = D.vcell[v];
+    c.matv = D.vmat[v];
+    const VoxMatC &mv = D.vmat_tab[c.matv];
+    c.fixedv = mv.fixed;
+    c.pv = load_pos(D.pose, v);
+    c.bsv = base_size_average(mv, D.tempe[v]);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        vl[i] = D.vlinks[6 * (size_t)v + i];
-        vo[i] = -1;
-        if (vl[i] >= 0) {
-            const int2 e = D.lends[vl[i]];
-            vo[i] = (e.x == v) ? e.y : e.x;
+        c.vl[i] = D.vlinks[6 * (size_t)v + i];
+        c.vo[i] = -1;
+        if (c.vl[i] >= 0) {
+            const int2 e = D.lends[c.vl[i]];
+            c.vo[i] = (e.x == v) ? e.y : e.x;
         }
     }
+}
+__device__ __forceinline__ bool contact_candidate(const Dev &D, const ContactSelf &c, int u, int cx, int cy, int cz, bool &fresh) {
+    const int v = c.v;
+    if (u == v) return false;
+    const int4 uc = D.vcell[u];
+    if (uc.x != cx || uc.y != cy || uc.z != cz || D.vsim[u] != c.sim) return false; // other cell hashed to this bucket
+    const VoxMatC &mu = D.vmat_tab[D.vmat[u]];
+    if (c.fixedv && mu.fixed) return false;
+    const V3 pu = load_pos(D.pose, u);
+    const V3 diff = (v > u) ? (c.pv - pu) : (pu - c.pv); // voxel1 - voxel2, voxel1 = higher index
+    const double bsu = base_size_average(mu, D.tempe[u]);
+    const double watch = ((v > u) ? (c.bsv + bsu) : (bsu + c.bsv)) * VX3_COLLISION_ENVELOPE_RADIUS;
+    if (diff.x > watch || diff.x < -watch) return false;
+    if (diff.y > watch || diff.y < -watch) return false;
+    if (diff.z > watch || diff.z < -watch) return false;
+    if (diff.Length() > watch) return false;
+    bool linked = false;
+    fresh = false;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (c.vo[i] == u) {
+            linked = true;
+            if (D.lstate[c.vl[i]] & LKS_JUST_CREATED) fresh = true;
+        }
+    return !(linked && !fresh);
+}
+
+// One partner of v (sorted position irrelevant here): contact force on v from this pair, target hit, signal trigger and,
+// for the pairs v leads (v is the higher index) when emit is set, the attach-candidate test (:729-812) on the step-start
+// link graph with an atomic append of the candidate.
+__device__ __forceinline__ V3 contact_partner(const Dev &D, const SimC &S, int v, int entry, bool emit, int &hits, bool &fire) {
+    const int u = entry & 0x3FFFFFFF;
+    const bool fresh = (entry >> 30) & 1;
+    const int hi = v > u ? v : u, lo = v > u ? u : v;
+    const VoxMatC &m1 = D.vmat_tab[D.vmat[hi]], &m2 = D.vmat_tab[D.vmat[lo]];
+    V3 f(0, 0, 0);
+    if (S.enable_collision) {
+        f = pair_contact_force(D, hi, lo, m1, m2);
+        if (v != hi) f = -f;
+        if ((m1.is_target && !m2.is_target) || (m2.is_target && !m1.is_target)) {
+            if (v == hi) hits++;
+            if (!D.vmat_tab[D.vmat[v]].is_target) fire = true;
+        }
+    }
+    if (!emit || v != hi || fresh) return f;
+    const int fl = D.vflags[lo], fh = D.vflags[hi];
+    if (!(fh & VXF_ENABLE_ATTACH) || !(fl & VXF_ENABLE_ATTACH)) return f;
+    if (m1.fixed || m2.fixed) return f;
+    if (D.vmat[hi] != D.vmat[lo]) return f;
+    if (!m1.sticky) return f;
+    V3 p1, p2;
+    Q4 q1;
+    load_pose(D.pose, hi, p1, q1);
+    p2 = load_pos(D.pose, lo);
+    const V3 e = p1 - p2;
+    const V3 ea = q1.RotateVec3DInv(-e);
+    const V3 fa = ea.Abs();
+    int dir1, dir2, axis, rev = 0;
+    if (fa.x >= fa.y && fa.x >= fa.z) {
+        axis = 0;
+        if (ea.x < 0) { dir1 = 1; dir2 = 0; rev = 1; } else { dir1 = 0; dir2 = 1; }
+    } else if (fa.y >= fa.x && fa.y >= fa.z) {
+        axis = 1;
+        if (ea.y < 0) { dir1 = 3; dir2 = 2; rev = 1; } else { dir1 = 2; dir2 = 3; }
+    } else {
+        axis = 2;
+        if (ea.z < 0) { dir1 = 5; dir2 = 4; rev = 1; } else { dir1 = 4; dir2 = 5; }
+    }
+    // slots only fill up during the attach phase, so an occupied slot now stays a rejection at this pair's turn
+    if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) return f;
+    if (is_neighbor(D, hi, lo, 5)) return f; // links are only added during the phase: true now stays true
+    const int slot = atomicAdd(D.cand_count, 1);
+    if (slot < D.cand_cap) {
+        Cand cd;
+        cd.key = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+        cd.info = dir1 | (dir2 << 3) | (axis << 6) | (rev << 8);
+        cd._pad = 0;
+        D.cands[slot] = cd;
+    }
+    return f;
+}
+
+__device__ __forceinline__ void contact_fire_signal(const Dev &D, const SimD &dy, int v, int matv) { // receiveSignal(100, currentTime, force = true) (VX3_Voxel.cu:315-335)
+    const SigMatC &sm = D.smat_tab[matv];
+    double *sg = D.sig + 6 * (size_t)v;
+    const double t = dy.t;
+    sg[2] = t + sm.inactive_period;
+    sg[0] = 100.0;
+    double val = 100.0 * sm.value_decay;
+    if (val < 0.1) val = 0;
+    sg[4] = val;
+    sg[5] = t;
+}
+
+// Contact phase of one surface voxel, one thread (used by k_resolve to re-evaluate the two voxels of an accepted attach in
+// sequence position): all partners inside the collision envelope, accumulated in ascending partner index = the canonical
+// sequential pair order.
+__device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
+    ContactSelf cs;
+    contact_self(D, v, cs);
+    const SimC &S = D.simc[cs.sim];
+    SimD &dy = D.simd[cs.sim];
     int partner[VX3_MAX_PARTNERS];
     int np = 0;
     for (int dz = -1; dz <= 1; dz++)
         for (int dy_ = -1; dy_ <= 1; dy_++)
             for (int dx = -1; dx <= 1; dx++) {
-                const int cx = vc.x + dx, cy = vc.y + dy_, cz = vc.z + dz;
-                const int b = (int)(cell_hash(sim, cx, cy, cz) & (unsigned)D.hmask);
-                const int s0 = D.cell_start[b], s1 = D.cell_start[b + 1];
-                for (int k = s0; k < s1; k++) {
-                    const int u = D.cell_items[k];
-                    if (u == v) continue;
-                    const int4 uc = D.vcell[u];
-                    if (uc.x != cx || uc.y != cy || uc.z != cz || D.vsim[u] != sim) continue; // other cell hashed to this bucket
-                    const VoxMatC &mu = D.vmat_tab[D.vmat[u]];
-                    if (mv.fixed && mu.fixed) continue;
-                    const V3 pu = load_pos(D.pose, u);
-                    const V3 diff = (v > u) ? (pv - pu) : (pu - pv); // voxel1 - voxel2, voxel1 = higher index
-                    const double bsu = base_size_average(mu, D.tempe[u]);
-                    const double watch = ((v > u) ? (bsv + bsu) : (bsu + bsv)) * VX3_COLLISION_ENVELOPE_RADIUS;
-                    if (diff.x > watch || diff.x < -watch) continue;
-                    if (diff.y > watch || diff.y < -watch) continue;
-                    if (diff.z > watch || diff.z < -watch) continue;
-                    if (diff.Length() > watch) continue;
-                    // direct lattice neighbours are skipped (is_neighbor depth 1) unless the link was made this step
-                    bool linked = false, fresh = false;
-#pragma unroll
-                    for (int i = 0; i < 6; i++)
-                        if (vo[i] == u) {
-                            linked = true;
-                            if (D.lstate[vl[i]] & LKS_JUST_CREATED) fresh = true;
-                        }
-                    if (linked && !fresh) continue;
+                const int cx = cs.vc.x + dx, cy = cs.vc.y + dy_, cz = cs.vc.z + dz;
+                const int b = (int)(cell_hash(cs.sim, cx, cy, cz) & (unsigned)D.hmask);
+                for (int u = D.cell_head[b]; u >= 0; u = D.cell_next[u]) {
+                    bool fresh;
+                    if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) continue;
                     if (np < VX3_MAX_PARTNERS) partner[np++] = fresh ? (u | (1 << 30)) : u;
                     else dy.err = VX3_ERR_CAPACITY;
                 }
@@ -766,79 +800,83 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
     int hits = 0;
     bool fire = false; // EnableSignals: a non-target voxel touching a target voxel fires (:719-725)
     for (int i = 0; i < np; i++) {
-        const int u = partner[i] & 0x3FFFFFFF;
-        const bool fresh = (partner[i] >> 30) & 1;
-        const int hi = v > u ? v : u, lo = v > u ? u : v;
-        const VoxMatC &m1 = D.vmat_tab[D.vmat[hi]], &m2 = D.vmat_tab[D.vmat[lo]];
+        const V3 f = contact_partner(D, S, v, partner[i], emit, hits, fire);
         if (S.enable_collision) {
-            V3 f = pair_contact_force(D, hi, lo, m1, m2);
-            if (v != hi) f = -f;
             c += f;
-            if (fresh) c -= f; // a link was created for this pair: its contact force is taken back (:827-830)
-            if ((m1.is_target && !m2.is_target) || (m2.is_target && !m1.is_target)) {
-                if (v == hi) hits++;
-                if (!mv.is_target) fire = true;
-            }
-        }
-        if (!emit || v != hi || fresh) continue;
-        // ---- attach candidate test (:729-812) on the step-start link graph ----
-        const int fl = D.vflags[lo], fh = D.vflags[hi];
-        if (!(fh & VXF_ENABLE_ATTACH) || !(fl & VXF_ENABLE_ATTACH)) continue;
-        if (m1.fixed || m2.fixed) continue;
-        if (D.vmat[hi] != D.vmat[lo]) continue;
-        if (!m1.sticky) continue;
-        V3 p1, p2;
-        Q4 q1, q2;
-        load_pose(D.pose, hi, p1, q1);
-        p2 = load_pos(D.pose, lo);
-        const V3 e = p1 - p2;
-        const V3 ea = q1.RotateVec3DInv(-e);
-        const V3 f = ea.Abs();
-        int dir1, dir2, axis, rev = 0;
-        if (f.x >= f.y && f.x >= f.z) {
-            axis = 0;
-            if (ea.x < 0) { dir1 = 1; dir2 = 0; rev = 1; } else { dir1 = 0; dir2 = 1; }
-        } else if (f.y >= f.x && f.y >= f.z) {
-            axis = 1;
-            if (ea.y < 0) { dir1 = 3; dir2 = 2; rev = 1; } else { dir1 = 2; dir2 = 3; }
-        } else {
-            axis = 2;
-            if (ea.z < 0) { dir1 = 5; dir2 = 4; rev = 1; } else { dir1 = 4; dir2 = 5; }
-        }
-        // slots only fill up during the attach phase, so an occupied slot now stays a rejection at this pair's turn
-        if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) continue;
-        if (is_neighbor(D, hi, lo, 5)) continue; // links are only added during the phase: true now stays true
-        const int slot = atomicAdd(D.cand_count, 1);
-        if (slot < D.cand_cap) {
-            Cand cd;
-            cd.key = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
-            cd.info = dir1 | (dir2 << 3) | (axis << 6) | (rev << 8);
-            cd._pad = 0;
-            D.cands[slot] = cd;
+            if ((partner[i] >> 30) & 1) c -= f; // a link was created for this pair: its contact force is taken back (:827-830)
         }
     }
     if (S.enable_collision) {
         store3(D.contact, v, c);
         if (emit && hits) atomicAdd(&dy.collision_count, hits);
-        if (emit && fire && S.enable_signals) { // receiveSignal(100, currentTime, force = true) (VX3_Voxel.cu:315-335)
-            const SigMatC &sm = D.smat_tab[matv];
-            double *sg = D.sig + 6 * (size_t)v;
-            const double t = dy.t;
-            sg[2] = t + sm.inactive_period;
-            sg[0] = 100.0;
-            double val = 100.0 * sm.value_decay;
-            if (val < 0.1) val = 0;
-            sg[4] = val;
-            sg[5] = t;
-        }
+        if (emit && fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.matv);
     }
 }
 
-__global__ void __launch_bounds__(128) k_contact(Dev D) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= D.nvox) return;
+// The contact phase of the step, one WARP per surface voxel: 27 lanes walk the 27 cells around the voxel's cell at once,
+// the partners found are ranked by index, every lane evaluates one partner (contact force, target hit, attach-candidate
+// test incl. the depth-5 neighbour search), and lane 0 adds the forces up in ascending partner index — the same sums in the
+// same order as the one-thread version above.
+#define VX3_CONTACT_WARPS 4
+__global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS) k_contact(Dev D) {
+    __shared__ int sList[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS], sSorted[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS];
+    __shared__ double sForce[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS][3];
+    __shared__ int sCnt[VX3_CONTACT_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int v = blockIdx.x * VX3_CONTACT_WARPS + w;
+    if (v >= D.nvox) return; // (whole warps leave together)
     if (D.vcell[v].w < 0) return;
-    contact_phase(D, v, true);
+    ContactSelf cs;
+    contact_self(D, v, cs);
+    const SimC &S = D.simc[cs.sim];
+    SimD &dy = D.simd[cs.sim];
+    if (lane == 0) sCnt[w] = 0;
+    __syncwarp();
+    if (lane < 27) {
+        const int dx = lane % 3 - 1, dy_ = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+        const int cx = cs.vc.x + dx, cy = cs.vc.y + dy_, cz = cs.vc.z + dz;
+        const int b = (int)(cell_hash(cs.sim, cx, cy, cz) & (unsigned)D.hmask);
+        for (int u = D.cell_head[b]; u >= 0; u = D.cell_next[u]) {
+            bool fresh;
+            if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) continue;
+            const int k = atomicAdd(&sCnt[w], 1);
+            if (k < VX3_MAX_PARTNERS) sList[w][k] = fresh ? (u | (1 << 30)) : u;
+        }
+    }
+    __syncwarp();
+    int n = sCnt[w];
+    if (n > VX3_MAX_PARTNERS) {
+        if (lane == 0) dy.err = VX3_ERR_CAPACITY;
+        n = VX3_MAX_PARTNERS;
+    }
+    // rank by partner index (indices are unique)
+    for (int i = lane; i < n; i += 32) {
+        const int key = sList[w][i] & 0x3FFFFFFF;
+        int r = 0;
+        for (int j = 0; j < n; j++) r += (sList[w][j] & 0x3FFFFFFF) < key;
+        sSorted[w][r] = sList[w][i];
+    }
+    __syncwarp();
+    int hits = 0;
+    bool fire = false;
+    for (int i = lane; i < n; i += 32) {
+        const V3 f = contact_partner(D, S, v, sSorted[w][i], true, hits, fire);
+        sForce[w][i][0] = f.x; sForce[w][i][1] = f.y; sForce[w][i][2] = f.z;
+    }
+    __syncwarp();
+    hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+    fire = __any_sync(0xFFFFFFFFu, fire);
+    if (lane == 0 && S.enable_collision) {
+        V3 c(0, 0, 0);
+        for (int i = 0; i < n; i++) {
+            const V3 f(sForce[w][i][0], sForce[w][i][1], sForce[w][i][2]);
+            c += f;
+            if ((sSorted[w][i] >> 30) & 1) c -= f;
+        }
+        store3(D.contact, v, c);
+        if (hits) atomicAdd(&dy.collision_count, hits);
+        if (fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.matv);
+    }
 }
 
 // Sequential resolution of the attach candidates in canonical (first, second) order: a candidate is accepted
