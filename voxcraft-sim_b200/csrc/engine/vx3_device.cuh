@@ -30,6 +30,7 @@ namespace vx3 {
 
 #define VX3_DEV_MAX_TOKENS 128 // per-voxel programs (force field, attach conditions) on the device evaluator
 #define VX3_MAX_PARTNERS 96    // contact partners of one voxel inside the collision envelope
+#define VX3_CELL_SLOTS 8       // voxels a grid bucket holds inline (one 32-byte sector)
 
 // Voxel material constants the step reads (all derived values precomputed in the reference's arithmetic).
 struct VoxMatC {
@@ -132,6 +133,16 @@ struct alignas(16) SimD {
 
 struct Chunk { int32_t sim, vstart, vcount, _pad; };
 
+// Everything the contact phase reads of a voxel — as itself or as somebody's candidate partner — in one aligned 64-byte
+// record, so that a candidate costs one memory round trip instead of a chain (cell -> material index -> material -> pose).
+struct alignas(64) ContactRec {
+    int32_t cx, cy, cz, bucket; // grid cell and hash bucket; bucket < 0: not in the grid (interior / removed / not colliding)
+    double px, py, pz;          // position
+    double bs;                  // baseSizeAverage() at this step's temperature (VX3_Voxel.h:101-104)
+    int32_t sim, mat;           // simulation, global voxel-material index
+    int32_t fixed, _pad;
+};
+
 struct Cand { // attach candidate (VX3_VoxelyzeKernel.cu:729-812), sorted by (hi, lo) before resolution
     unsigned long long key; // hi<<32 | lo (global voxel indices)
     int32_t info;           // dir1 | dir2<<3 | axis<<6 | reverse<<8
@@ -197,9 +208,11 @@ struct Dev {
     double2 *lf2;
     // collision grid (hashed uniform grid, per-bucket lists)
     int32_t hmask;
-    int32_t *cell_head; // [hmask+1] first voxel of the bucket's list, -1 = empty (reset every step)
-    int32_t *cell_next; // [nvox] next voxel in the same bucket
-    int4 *vcell;      // cx, cy, cz, bucket (bucket<0: not in grid)
+    // bucket b: cell_cnt[b] voxels; the first VX3_CELL_SLOTS of them inline in cell_items[b][], the rest (rare) chained
+    // through cell_ovf[b] (voxel + 1, 0 = none) / cell_next[].  cell_cnt and cell_ovf are one allocation, zeroed every step
+    int32_t *cell_cnt, *cell_ovf, *cell_items, *cell_next;
+    struct ContactRec *crec; // [nvox] what the contact phase needs of a voxel, in one 64-byte record (written by k_grid_build)
+    int32_t *uf;      // [nvox] union-find parents over the voxels (NULL unless a simulation can attach), see uf_find
     Cand *cands;
     int32_t *cand_count;
     int32_t cand_cap;

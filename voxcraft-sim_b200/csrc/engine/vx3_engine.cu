@@ -781,6 +781,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     D.lstride = (int)LS;
     // ---- plan the arena: every array is a slice; uploaded slices first, zero-initialised ones after ----
     ArenaPlan plan;
+    std::vector<int32_t> uf_host;
 #define UP(field, vec) plan.upload(const_cast<std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type **>(&D.field), vec)
     UP(simc, b->simc);
     UP(simd, simd);
@@ -838,13 +839,32 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     plan.zeroed(&D.lf2, 6 * LS);
     plan.zeroed(&D.com_part, chunks.size() * 6);
     if (b->any_collide) {
-        int H = 1024;
-        while (H < 2 * (int)nvox && H < (1 << 24)) H <<= 1;
+        int H = 1024; // buckets >= 2 x voxels: two occupied cells in one bucket are rare, a walk meets few foreign voxels
+        while ((size_t)H < 2 * nvox && H < (1 << 24)) H <<= 1;
         D.hmask = H - 1;
         plan.zeroed(&D.contact, nvox * 3);
-        plan.zeroed(&D.cell_head, (size_t)H);
+        plan.zeroed(&D.cell_cnt, 2 * (size_t)H); // counts, then overflow heads
+        plan.zeroed(&D.cell_items, (size_t)H * VX3_CELL_SLOTS);
         plan.zeroed(&D.cell_next, nvox);
-        plan.zeroed(&D.vcell, nvox);
+        plan.zeroed(&D.crec, nvox);
+        if (b->any_sticky) { // connected components of the models' link graphs (roots = smallest voxel index), for uf_find
+            uf_host.resize(nvox);
+            for (size_t v = 0; v < nvox; v++) uf_host[v] = (int32_t)v;
+            auto find = [&](int x) {
+                while (uf_host[x] != x) {
+                    uf_host[x] = uf_host[uf_host[x]];
+                    x = uf_host[x];
+                }
+                return x;
+            };
+            for (size_t g = 0; g < nslots; g++) {
+                if (lends[g].x < 0) continue;
+                const int ra = find(lends[g].x), rb = find(lends[g].y);
+                if (ra != rb) uf_host[std::max(ra, rb)] = std::min(ra, rb);
+            }
+            for (size_t v = 0; v < nvox; v++) uf_host[v] = find((int)v);
+            plan.upload(&D.uf, uf_host);
+        }
         D.cand_cap = 2048;
         plan.zeroed(&D.cands, (size_t)D.cand_cap);
         plan.zeroed(&D.cand_count, 1);
@@ -887,6 +907,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         for (auto &x : th) x.join();
     }
     for (const ArenaPlan::Item &it : plan.zero) *it.field = b->res.d + it.off;
+    if (D.cell_cnt) D.cell_ovf = D.cell_cnt + ((size_t)D.hmask + 1);
     lap("stage into pinned memory");
     cudaError_t ce = cudaSuccess;
     if (plan.up_bytes) ce = cudaMemcpyAsync(b->res.d, b->res.h, plan.up_bytes, cudaMemcpyHostToDevice, b->stream);
@@ -1048,7 +1069,7 @@ static void launch_step(vx3_batch *b, bool check_stop) {
     cudaStream_t st = b->stream;
     if (D.nlinkslots > 0) launch_links(b);
     if (b->any_collide) {
-        cudaMemsetAsync(D.cell_head, 0xFF, sizeof(int32_t) * ((size_t)D.hmask + 1), st); // every bucket's list empty (-1)
+        cudaMemsetAsync(D.cell_cnt, 0, 2 * sizeof(int32_t) * ((size_t)D.hmask + 1), st); // every bucket empty (counts and overflow heads)
         LAUNCH(KC_GRID_BUILD, k_grid_build, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
         LAUNCH(KC_CONTACT, k_contact, cdiv(D.nvox, VX3_CONTACT_WARPS), 32 * VX3_CONTACT_WARPS, D);
         if (b->any_sticky) LAUNCH(KC_RESOLVE, k_resolve, 1, 1024, D);

@@ -549,11 +549,12 @@ __device__ __forceinline__ unsigned cell_hash(int sim, int cx, int cy, int cz) {
 __device__ __forceinline__ bool sim_collides(const SimC &S) { return S.enable_collision || S.enable_attach; }
 
 // regenerateSurfaceVoxels (:495-513) + uniform-grid insert (replaces the O(S^2) sweep of gpu_update_attach :833-843).
-// The grid is a hash table of per-bucket lists: a surface voxel pushes itself onto its bucket's list with one atomicExch
-// (cell_head[bucket] -> cell_next[v]); no counting, no scan, no second pass.  The order inside a list is whatever the
-// atomics produce — the contact phase sorts each voxel's partners by index before it accumulates, so the
-// result does not depend on it.  cell_head is reset to -1 by a memset node before this kernel.
-// Also publishes this step's temperature (what updateTemperature :219-235 set) for the contact phase.
+// The grid is a hash table of buckets with VX3_CELL_SLOTS inline slots each (one 32-byte sector): a surface voxel takes
+// slot atomicAdd(cell_cnt[bucket]) — no counting pass, no scan, no second pass; a voxel that finds the inline slots taken
+// (many voxels squeezed into one cell, or two cells in one bucket) chains itself onto the bucket's overflow list.  The
+// order inside a bucket is whatever the atomics produce — the contact phase sorts each voxel's partners by index before
+// it accumulates, so the result does not depend on it.  cell_cnt / cell_ovf are zeroed by a memset node
+// before this kernel.  Also writes each voxel's ContactRec and publishes this step's temperature (updateTemperature :219-235).
 __global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v == 0) *D.cand_count = 0;
@@ -561,10 +562,18 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
     const int sim = D.vsim[v];
     const SimC &S = D.simc[sim];
     const SimD &dy = D.simd[sim];
-    int4 vc = make_int4(0, 0, 0, -1);
+    ContactRec rec;
+    rec.cx = rec.cy = rec.cz = 0;
+    rec.bucket = -1;
+    rec.px = rec.py = rec.pz = rec.bs = 0;
+    rec.sim = sim;
+    rec.mat = 0;
+    rec.fixed = 0;
+    rec._pad = 0;
     if (dy.status == VX3_SIM_RUNNING && !dy.diverged && dy.dt != 0 && sim_collides(S)) {
         int flags = D.vflags[v];
-        D.tempe[v] = unpack_t(D.pose[8 * (size_t)v + 7]); // this step's temperature, for the contact phase
+        const float tempe = unpack_t(D.pose[8 * (size_t)v + 7]);
+        D.tempe[v] = tempe; // this step's temperature, for the contact phase
         bool interior = true; // VX3_Voxel::updateSurface (VX3_Voxel.cu:515-524): the bit named SURFACE means interior
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -575,14 +584,22 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
         if (nf != flags) D.vflags[v] = nf;
         if (!interior && !(flags & VXF_REMOVED)) {
             const V3 p = load_pos(D.pose, v);
-            vc.x = (int)floor(p.x * S.cell_inv);
-            vc.y = (int)floor(p.y * S.cell_inv);
-            vc.z = (int)floor(p.z * S.cell_inv);
-            vc.w = (int)(cell_hash(sim, vc.x, vc.y, vc.z) & (unsigned)D.hmask);
-            D.cell_next[v] = atomicExch(&D.cell_head[vc.w], v);
+            const int mat = D.vmat[v];
+            const VoxMatC &m = D.vmat_tab[mat];
+            rec.cx = (int)floor(p.x * S.cell_inv);
+            rec.cy = (int)floor(p.y * S.cell_inv);
+            rec.cz = (int)floor(p.z * S.cell_inv);
+            rec.bucket = (int)(cell_hash(sim, rec.cx, rec.cy, rec.cz) & (unsigned)D.hmask);
+            rec.px = p.x; rec.py = p.y; rec.pz = p.z;
+            rec.bs = base_size_average(m, tempe);
+            rec.mat = mat;
+            rec.fixed = m.fixed;
+            const int slot = atomicAdd(&D.cell_cnt[rec.bucket], 1);
+            if (slot < VX3_CELL_SLOTS) D.cell_items[VX3_CELL_SLOTS * (size_t)rec.bucket + slot] = v;
+            else D.cell_next[v] = atomicExch(&D.cell_ovf[rec.bucket], v + 1) - 1;
         }
     }
-    D.vcell[v] = vc;
+    D.crec[v] = rec;
 }
 
 // surface flags only (simulations without collisions but with detach): regenerateSurfaceVoxels (:495-513)
@@ -601,6 +618,21 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_surface(Dev D) {
     const int nf = interior ? (flags | VX3_VOX_SURFACE) : (flags & ~VX3_VOX_SURFACE);
     if (nf != flags) D.vflags[v] = nf;
 }
+
+// Connectivity filter in front of the depth-5 neighbour search.  uf[] is a union-find forest over the voxels: the host
+// initialises it with the connected components of the model's link graph, k_resolve unions the two trees whenever it
+// accepts an attach, and nothing ever splits a tree (detach / removal only remove links).  So the forest's components are
+// a superset of the real ones: different roots => no path at all => not within 5 links, exactly; same root => ask the
+// search.  Bodies of a pile that have not stuck together skip the search (up to ~1000 dependent path steps) entirely.
+__device__ __forceinline__ int uf_find(const Dev &D, int x) {
+    int p = D.uf[x];
+    while (p != x) {
+        x = p;
+        p = D.uf[x];
+    }
+    return x;
+}
+__device__ __forceinline__ bool uf_disconnected(const Dev &D, int a, int b) { return D.uf && uf_find(D, a) != uf_find(D, b); }
 
 // is_neighbor (VX3_VoxelyzeKernel.cu:651-680), iterative
 __device__ bool is_neighbor(const Dev &D, int v1, int v2, int depth) {
@@ -645,49 +677,55 @@ __device__ __forceinline__ V3 pair_contact_force(const Dev &D, int hi, int lo, c
 // handle_collision_attachment (VX3_VoxelyzeKernel.cu:682-705); direct lattice neighbours are skipped (is_neighbor depth 1)
 // unless the link was made this step (`fresh`: its contact force is added and taken back, :827-830).
 struct ContactSelf {
-    int v, sim, matv;
-    int4 vc;
-    V3 pv;
-    double bsv;
-    bool fixedv;
-    int vl[6], vo[6]; // own links and their other ends
+    int v;
+    ContactRec r;
+    bool have_links;
+    int vl[6], vo[6]; // own links and their other ends (loaded when the first candidate passes the envelope test)
 };
+__device__ __forceinline__ ContactRec load_crec(const Dev &D, int v) {
+    ContactRec r;
+    const int4 *s = reinterpret_cast<const int4 *>(D.crec + v);
+    const int4 a = s[0], b = s[1], c = s[2], d = s[3];
+    r.cx = a.x; r.cy = a.y; r.cz = a.z; r.bucket = a.w;
+    r.px = __hiloint2double(b.y, b.x); r.py = __hiloint2double(b.w, b.z);
+    r.pz = __hiloint2double(c.y, c.x); r.bs = __hiloint2double(c.w, c.z);
+    r.sim = d.x; r.mat = d.y; r.fixed = d.z; r._pad = 0;
+    return r;
+}
 __device__ __forceinline__ void contact_self(const Dev &D, int v, ContactSelf &c) {
     c.v = v;
-    c.sim = D.vsim[v];
-    c.vc = D.vcell[v];
-    c.matv = D.vmat[v];
-    const VoxMatC &mv = D.vmat_tab[c.matv];
-    c.fixedv = mv.fixed;
-    c.pv = load_pos(D.pose, v);
-    c.bsv = base_size_average(mv, D.tempe[v]);
+    c.r = load_crec(D, v);
+    c.have_links = false;
+}
+__device__ __forceinline__ void contact_self_links(const Dev &D, ContactSelf &c) {
+    if (c.have_links) return;
+    c.have_links = true;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        c.vl[i] = D.vlinks[6 * (size_t)v + i];
+        c.vl[i] = D.vlinks[6 * (size_t)c.v + i];
         c.vo[i] = -1;
         if (c.vl[i] >= 0) {
             const int2 e = D.lends[c.vl[i]];
-            c.vo[i] = (e.x == v) ? e.y : e.x;
+            c.vo[i] = (e.x == c.v) ? e.y : e.x;
         }
     }
 }
-__device__ __forceinline__ bool contact_candidate(const Dev &D, const ContactSelf &c, int u, int cx, int cy, int cz, bool &fresh) {
+__device__ __forceinline__ bool contact_candidate(const Dev &D, ContactSelf &c, int u, int cx, int cy, int cz, bool &fresh) {
     const int v = c.v;
+    fresh = false;
     if (u == v) return false;
-    const int4 uc = D.vcell[u];
-    if (uc.x != cx || uc.y != cy || uc.z != cz || D.vsim[u] != c.sim) return false; // other cell hashed to this bucket
-    const VoxMatC &mu = D.vmat_tab[D.vmat[u]];
-    if (c.fixedv && mu.fixed) return false;
-    const V3 pu = load_pos(D.pose, u);
-    const V3 diff = (v > u) ? (c.pv - pu) : (pu - c.pv); // voxel1 - voxel2, voxel1 = higher index
-    const double bsu = base_size_average(mu, D.tempe[u]);
-    const double watch = ((v > u) ? (c.bsv + bsu) : (bsu + c.bsv)) * VX3_COLLISION_ENVELOPE_RADIUS;
+    const ContactRec ur = load_crec(D, u);
+    if (ur.cx != cx || ur.cy != cy || ur.cz != cz || ur.sim != c.r.sim) return false; // other cell hashed to this bucket
+    if (c.r.fixed && ur.fixed) return false;
+    const V3 pv(c.r.px, c.r.py, c.r.pz), pu(ur.px, ur.py, ur.pz);
+    const V3 diff = (v > u) ? (pv - pu) : (pu - pv); // voxel1 - voxel2, voxel1 = higher index
+    const double watch = ((v > u) ? (c.r.bs + ur.bs) : (ur.bs + c.r.bs)) * VX3_COLLISION_ENVELOPE_RADIUS;
     if (diff.x > watch || diff.x < -watch) return false;
     if (diff.y > watch || diff.y < -watch) return false;
     if (diff.z > watch || diff.z < -watch) return false;
     if (diff.Length() > watch) return false;
+    contact_self_links(D, c);
     bool linked = false;
-    fresh = false;
 #pragma unroll
     for (int i = 0; i < 6; i++)
         if (c.vo[i] == u) {
@@ -695,6 +733,25 @@ __device__ __forceinline__ bool contact_candidate(const Dev &D, const ContactSel
             if (D.lstate[c.vl[i]] & LKS_JUST_CREATED) fresh = true;
         }
     return !(linked && !fresh);
+}
+// All voxels of bucket b, through fn(u): the inline slots (their records are prefetched first: the candidates' loads are
+// independent of each other), then the overflow chain.
+__device__ __forceinline__ void prefetch_crec(const Dev &D, int u) { asm volatile("prefetch.global.L2 [%0];" ::"l"(D.crec + u)); }
+template <class F> __device__ __forceinline__ void bucket_for_each(const Dev &D, int b, F fn) {
+    const int n = D.cell_cnt[b];
+    if (n == 0) return;
+    const int4 *it = reinterpret_cast<const int4 *>(D.cell_items + VX3_CELL_SLOTS * (size_t)b);
+    const int4 i0 = it[0], i1 = it[1];
+    const int ids[VX3_CELL_SLOTS] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    const int m = n < VX3_CELL_SLOTS ? n : VX3_CELL_SLOTS;
+#pragma unroll
+    for (int k = 0; k < VX3_CELL_SLOTS; k++)
+        if (k < m) prefetch_crec(D, ids[k]);
+#pragma unroll
+    for (int k = 0; k < VX3_CELL_SLOTS; k++)
+        if (k < m) fn(ids[k]);
+    if (n > VX3_CELL_SLOTS)
+        for (int u = D.cell_ovf[b] - 1; u >= 0; u = D.cell_next[u]) fn(u);
 }
 
 // One partner of v (sorted position irrelevant here): contact force on v from this pair, target hit, signal trigger and,
@@ -740,7 +797,7 @@ __device__ __forceinline__ V3 contact_partner(const Dev &D, const SimC &S, int v
     }
     // slots only fill up during the attach phase, so an occupied slot now stays a rejection at this pair's turn
     if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) return f;
-    if (is_neighbor(D, hi, lo, 5)) return f; // links are only added during the phase: true now stays true
+    if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) return f; // links are only added during the phase: true now stays true
     const int slot = atomicAdd(D.cand_count, 1);
     if (slot < D.cand_cap) {
         Cand cd;
@@ -770,21 +827,21 @@ __device__ __forceinline__ void contact_fire_signal(const Dev &D, const SimD &dy
 __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
     ContactSelf cs;
     contact_self(D, v, cs);
-    const SimC &S = D.simc[cs.sim];
-    SimD &dy = D.simd[cs.sim];
+    const SimC &S = D.simc[cs.r.sim];
+    SimD &dy = D.simd[cs.r.sim];
     int partner[VX3_MAX_PARTNERS];
     int np = 0;
     for (int dz = -1; dz <= 1; dz++)
         for (int dy_ = -1; dy_ <= 1; dy_++)
             for (int dx = -1; dx <= 1; dx++) {
-                const int cx = cs.vc.x + dx, cy = cs.vc.y + dy_, cz = cs.vc.z + dz;
-                const int b = (int)(cell_hash(cs.sim, cx, cy, cz) & (unsigned)D.hmask);
-                for (int u = D.cell_head[b]; u >= 0; u = D.cell_next[u]) {
+                const int cx = cs.r.cx + dx, cy = cs.r.cy + dy_, cz = cs.r.cz + dz;
+                const int b = (int)(cell_hash(cs.r.sim, cx, cy, cz) & (unsigned)D.hmask);
+                bucket_for_each(D, b, [&](int u) {
                     bool fresh;
-                    if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) continue;
+                    if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) return;
                     if (np < VX3_MAX_PARTNERS) partner[np++] = fresh ? (u | (1 << 30)) : u;
                     else dy.err = VX3_ERR_CAPACITY;
-                }
+                });
             }
     // ascending partner index (insertion sort; np is small)
     for (int i = 1; i < np; i++) {
@@ -809,7 +866,7 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
     if (S.enable_collision) {
         store3(D.contact, v, c);
         if (emit && hits) atomicAdd(&dy.collision_count, hits);
-        if (emit && fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.matv);
+        if (emit && fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.r.mat);
     }
 }
 
@@ -825,23 +882,23 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS) k_contact(Dev D) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int v = blockIdx.x * VX3_CONTACT_WARPS + w;
     if (v >= D.nvox) return; // (whole warps leave together)
-    if (D.vcell[v].w < 0) return;
     ContactSelf cs;
     contact_self(D, v, cs);
-    const SimC &S = D.simc[cs.sim];
-    SimD &dy = D.simd[cs.sim];
+    if (cs.r.bucket < 0) return;
+    const SimC &S = D.simc[cs.r.sim];
+    SimD &dy = D.simd[cs.r.sim];
     if (lane == 0) sCnt[w] = 0;
     __syncwarp();
     if (lane < 27) {
         const int dx = lane % 3 - 1, dy_ = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-        const int cx = cs.vc.x + dx, cy = cs.vc.y + dy_, cz = cs.vc.z + dz;
-        const int b = (int)(cell_hash(cs.sim, cx, cy, cz) & (unsigned)D.hmask);
-        for (int u = D.cell_head[b]; u >= 0; u = D.cell_next[u]) {
+        const int cx = cs.r.cx + dx, cy = cs.r.cy + dy_, cz = cs.r.cz + dz;
+        const int b = (int)(cell_hash(cs.r.sim, cx, cy, cz) & (unsigned)D.hmask);
+        bucket_for_each(D, b, [&](int u) {
             bool fresh;
-            if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) continue;
+            if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) return;
             const int k = atomicAdd(&sCnt[w], 1);
             if (k < VX3_MAX_PARTNERS) sList[w][k] = fresh ? (u | (1 << 30)) : u;
-        }
+        });
     }
     __syncwarp();
     int n = sCnt[w];
@@ -875,7 +932,7 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS) k_contact(Dev D) {
         }
         store3(D.contact, v, c);
         if (hits) atomicAdd(&dy.collision_count, hits);
-        if (fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.matv);
+        if (fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.r.mat);
     }
 }
 
@@ -919,7 +976,7 @@ __global__ void __launch_bounds__(1024) k_resolve(Dev D) {
         const int info = sinfo[c];
         const int dir1 = info & 7, dir2 = (info >> 3) & 7, axis = (info >> 6) & 3, rev = (info >> 8) & 1;
         if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) continue;
-        if (is_neighbor(D, hi, lo, 5)) continue;
+        if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) continue;
         const int sim = D.vsim[hi];
         const SimC &S = D.simc[sim];
         SimD &dy = D.simd[sim];
@@ -942,6 +999,10 @@ __global__ void __launch_bounds__(1024) k_resolve(Dev D) {
         const float sn = (float)mn.nomSize, sp = (float)mp.nomSize; // transverseArea() with zero strain
         D.larea[g] = make_float2(0.5f * (sn * sn + sp * sp), 0.0f);
         dy.attach_events++;
+        if (D.uf) { // the two voxels' trees become one
+            const int ra = uf_find(D, hi), rb = uf_find(D, lo);
+            if (ra != rb) D.uf[ra > rb ? ra : rb] = ra > rb ? rb : ra;
+        }
         __threadfence_block();
         if (S.enable_collision) { // take this pair's contact force back in sequence position (:827-830)
             contact_phase(D, hi, false);
