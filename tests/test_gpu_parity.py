@@ -325,6 +325,29 @@ def test_collisions_and_attach(sticky):
         lib.vx3_builder_destroy(b)
 
 
+def test_collision_grid_overflow_chains(monkeypatch):
+    """A 4-bucket hash table: every bucket holds many cells' voxels, far more than its 8 inline slots, so the walk goes
+    through the overflow chains and meets mostly foreign voxels.  Nothing may change: same contacts, same attach events."""
+    monkeypatch.setenv("VX3_GRID_BUCKETS", "4")
+    spec = collide_spec(True, name="overflow")
+    lib, b, d = build(spec)
+    try:
+        eng = EngineBatch([d])
+        orc = OracleSim(d)
+        dt = float(np.float32(0.9 * orc.recommended_dt()))
+        for i in range(8):
+            eng.step(500, dt)
+            orc.step(500, dt)
+            se, so = eng.state(0), orc.state()
+            for k in ("link_vneg", "link_vpos", "link_axis", "vox_links", "link_flags", "vox_flags"):
+                np.testing.assert_array_equal(se[k], so[k], err_msg="%s chunk %d" % (k, i))
+            check_state(se, so, "overflow chunk %d" % i)
+        assert orc.counts()["attach"] > 0
+        assert eng.results()[0].collision_count == orc.result().collision_count > 0
+    finally:
+        lib.vx3_builder_destroy(b)
+
+
 def test_config4_small_pile():
     """Config 4 at oracle-checkable size: 2x2x2 grid of 3^3 sticky actuated bodies dropped onto each other
     (collisions + attach + detach enabled), hashed-grid contacts vs the oracle's all-pairs sweep."""

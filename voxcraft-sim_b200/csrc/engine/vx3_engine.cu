@@ -841,6 +841,10 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     if (b->any_collide) {
         int H = 1024; // buckets >= 2 x voxels: two occupied cells in one bucket are rare, a walk meets few foreign voxels
         while ((size_t)H < 2 * nvox && H < (1 << 24)) H <<= 1;
+        if (const char *e = getenv("VX3_GRID_BUCKETS")) { // test hook: a tiny table forces shared buckets and overflow chains
+            int h = atoi(e);
+            if (h >= 1 && (h & (h - 1)) == 0) H = h;
+        }
         D.hmask = H - 1;
         plan.zeroed(&D.contact, nvox * 3);
         plan.zeroed(&D.cell_cnt, 2 * (size_t)H); // counts, then overflow heads
