@@ -16,5 +16,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 3
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_links -s 40 -c 2 -o gpurun_out/prof_links_c3 -f python bench.py --workload c3 --steps 1 --warmup 1 --sim-steps 50 --skip-cpu --skip-e2e > gpurun_out/ncu_links.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_voxels -s 40 -c 2 -o gpurun_out/prof_voxels_c3 -f python bench.py --workload c3 --steps 1 --warmup 1 --sim-steps 50 --skip-cpu --skip-e2e > gpurun_out/ncu_voxels.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persistent -s 1 -c 1 -o gpurun_out/prof_persistent_c2 -f python bench.py --steps 1 --warmup 1 --sim-steps 200 --skip-cpu --skip-e2e > gpurun_out/ncu_persist.log 2>&1
-VX3_LINK_QUEUE=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_links_deferred -s 4 -c 1 -o gpurun_out/prof_links_deferred_c5 -f python bench.py --workload c5 --steps 1 --warmup 0 --sim-steps 8 --skip-cpu --skip-e2e > gpurun_out/ncu_links_c5.log 2>&1
+VX3_LINK_QUEUE=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_links_deferred -s 4 -c 1 -o gpurun_out/prof_links_deferred_c5 -f python bench.py --workload c5 --steps 1 --warmup 0 --sim-steps 8 --skip-cpu --skip-e2e > gpurun_out/ncu_links_c5.log 2>&1
 ls -la gpurun_out

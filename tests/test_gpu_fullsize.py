@@ -1,7 +1,7 @@
 """GPU checks at BASELINE.json's sizes, through properties that do not need the (slow) oracle for the whole run:
   * config 2 at full size: the on-chip persistent kernel (148 blocks, face links evaluated on both sides, one exchange per
     step) and the streaming kernels agree bit for bit, and both match the oracle over a short horizon;
-  * config 3 (sample of the batch): a simulation steps identically inside a batch and alone, the three link-pass variants
+  * config 3 (sample of the batch): a simulation steps identically inside a batch and alone, the two link-pass variants
     are bit-identical, and sampled robots match the oracle;
   * config 5 (reduced length, full cross-section): link-pass variants bit-identical on a single large body."""
 import os
@@ -80,7 +80,7 @@ def test_config3_sample_batch_properties():
                 return out
             return _with_env("VX3_LINK_QUEUE", variant, go)
         base = run("0")
-        for variant in ("1", "2", None):  # CTA queue, warp-deferred dense passes, timing-based choice
+        for variant in ("1", None):  # deferred dense passes, timing-based choice
             other = run(variant)
             for a, b_ in zip(base, other):
                 util.assert_bit_equal(a, b_, BITS, "config 3 sample, link pass variant %s" % variant)
@@ -116,7 +116,7 @@ def test_config5_cross_section_link_variants_bit_identical():
                 return st, r
             return _with_env("VX3_LINK_QUEUE", variant, go)
         s0, r0 = run("0")
-        for variant in ("1", "2"):
+        for variant in ("1",):
             s1, r1 = run(variant)
             util.assert_bit_equal(s0, s1, BITS, "config 5 slice, link pass variant %s" % variant)
             assert list(r0.current_com) == list(r1.current_com)

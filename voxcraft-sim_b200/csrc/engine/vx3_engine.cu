@@ -255,9 +255,9 @@ struct vx3_batch {
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
     bool any_ghost = false;
-    int link_queue = -1; // link pass variant: -1 = still being timed (launch_links), 0 = in place, 1 = CTA queue, 2 = warp-deferred dense passes
+    int link_queue = -1; // link pass variant: -1 = still being timed (launch_links), 0 = in place, 1 = deferred dense passes
     int lq_trials = 0;
-    double lq_ms[3] = {0, 0, 0};
+    double lq_ms[2] = {0, 0};
     cudaEvent_t lq_ev[2] = {nullptr, nullptr};
     PersistentPlan pplan; // on-chip path for a single small collision-free body
     bool use_persistent = true;
@@ -1006,7 +1006,7 @@ static long long next_com_step(const vx3_batch *b) {
 static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
     b->link_smtab = b->D.n_vmats <= VX3_SM_VMATS && b->D.n_lmats <= VX3_SM_LMATS;
     b->vox_smtab = b->D.n_vmats <= VX3_SM_VMATS;
-    const void *kl = b->link_smtab ? (const void *)k_links<true, true> : (const void *)k_links<false, true>; // the larger of the two variants
+    const void *kl = b->link_smtab ? (const void *)k_links<true> : (const void *)k_links<false>;
     const void *kv = b->vox_smtab ? (const void *)k_voxels<true> : (const void *)k_voxels<false>;
     int nl = 0, nv = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, kl, VX3_LINK_T, 0));
@@ -1019,10 +1019,9 @@ static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
     return VX3_OK;
 }
 
-// The link pass has three bit-identical variants (the large-angle branch in place; densely through a CTA-wide shared-memory
-// queue; deferred to dense per-warp passes); which is fastest depends on the batch, so the first streaming steps of a batch
-// time them with CUDA events (one warm-up round, then 3 trials each) and the batch keeps the fastest.
-// VX3_LINK_QUEUE=0/1/2 pins the choice.
+// The link pass has two bit-identical variants (k_links: the large-angle branch in place; k_links_deferred: those links
+// deferred to dense per-warp passes); which is faster depends on the batch, so the first streaming steps of a batch time
+// both with CUDA events (one warm-up round, then 3 trials each) and the batch keeps the faster.  VX3_LINK_QUEUE=0/1 pins it.
 static void launch_links(vx3_batch *b) {
     const Dev &D = b->D;
     cudaStream_t st = b->stream;
@@ -1031,8 +1030,8 @@ static void launch_links(vx3_batch *b) {
     if (variant < 0) {
         if (!b->lq_ev[0]) {
             const char *e = getenv("VX3_LINK_QUEUE");
-            if (e && e[0] >= '0' && e[0] <= '2') b->link_queue = variant = e[0] - '0';
-            else if (b->halo.on) b->link_queue = variant = 2; // slabs of one large body (measured fastest there); and a host-side event wait
+            if (e && (e[0] == '0' || e[0] == '1')) b->link_queue = variant = e[0] - '0';
+            else if (b->halo.on) b->link_queue = variant = 1; // slabs of one large body (measured faster there); and a host-side event wait
                                                               // inside a step could deadlock slabs that one thread queues in rounds
             else {
                 cudaEventCreate(&b->lq_ev[0]);
@@ -1041,30 +1040,23 @@ static void launch_links(vx3_batch *b) {
         }
         if (variant < 0) {
             trial = true;
-            variant = b->lq_trials % 3;
+            variant = b->lq_trials & 1;
             cudaEventRecord(b->lq_ev[0], st);
         }
     }
     if (b->link_smtab) {
-        if (variant == 2) LAUNCH_SM(KC_LINKS, k_links_deferred<true>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-        else if (variant == 1) LAUNCH_SM(KC_LINKS, (k_links<true, true>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-        else LAUNCH_SM(KC_LINKS, (k_links<true, false>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<true>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        else LAUNCH_SM(KC_LINKS, k_links<true>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
     } else {
-        if (variant == 2) LAUNCH_SM(KC_LINKS, k_links_deferred<false>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-        else if (variant == 1) LAUNCH_SM(KC_LINKS, (k_links<false, true>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-        else LAUNCH_SM(KC_LINKS, (k_links<false, false>), b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<false>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        else LAUNCH_SM(KC_LINKS, k_links<false>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
     }
     if (trial) {
         cudaEventRecord(b->lq_ev[1], st);
         float ms = 0;
-        if (cudaEventSynchronize(b->lq_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, b->lq_ev[0], b->lq_ev[1]) == cudaSuccess && b->lq_trials >= 3)
+        if (cudaEventSynchronize(b->lq_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, b->lq_ev[0], b->lq_ev[1]) == cudaSuccess && b->lq_trials >= 2)
             b->lq_ms[variant] += ms;
-        if (++b->lq_trials >= 12) {
-            int best = 0;
-            for (int k = 1; k < 3; k++)
-                if (b->lq_ms[k] < b->lq_ms[best]) best = k;
-            b->link_queue = best;
-        }
+        if (++b->lq_trials >= 8) b->link_queue = b->lq_ms[1] < b->lq_ms[0] ? 1 : 0;
     }
 }
 

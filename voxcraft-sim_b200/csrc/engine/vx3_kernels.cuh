@@ -123,33 +123,27 @@ __device__ __forceinline__ double2 ldv_if(const double2 *p, bool on) {
 
 __device__ __forceinline__ int4 link_c4(const Dev &D, long long g) { return g < D.nlinkslots ? __ldg(D.lc4 + g) : make_int4(-1, -1, 0, 0); }
 
-// Large-angle queue (VX3_LINK_QUEUE): the large-angle branch of orientLink costs ~540 instructions on top of ~780, and in an
-// actuated body a few percent of the links are in that regime — spread so that most warps hold one or two of them and
-// execute the whole branch for 2 active lanes (profiles/r01_sass_regions_k_links_c3.txt: 35 % of the kernel's warp
-// instructions ran with <= 3 lanes).  So the branch is not taken in place: a thread whose link needs it puts the branch's
-// inputs (pos2, angle2, rest: 8 doubles) into a shared-memory queue, and after a CTA barrier the first n threads of the
-// CTA run the branch for the n queued links, densely, and hand angle1 / angle2 / pos2.x / angle1v back through the same
-// slots.  Same arithmetic on the same values, executed by another lane: bit-identical.
-// Whether it pays depends on the batch: while warp 0 runs the branch the CTA's other warps wait at the barrier, which costs
-// latency hiding (measured: config 5 -11 %, config 3 +14 % on k_links), so both variants are compiled and the engine times
-// them on the batch's first streaming steps and keeps the faster one (vx3_engine.cu, launch_links).
+// The large-angle branch of orientLink costs ~540 instructions on top of ~780, and in an actuated body a few percent of
+// the links are in that regime — spread so that most warps hold one or two of them and execute the whole branch for 2
+// active lanes (profiles/r01_sass_regions_k_links_c3.txt: 35 % of this kernel's warp instructions ran with <= 3 lanes).
+// k_links runs the branch in place; k_links_deferred (below) defers those links to dense passes.  Which is faster depends
+// on the batch, so the engine times both on a batch's first streaming steps and keeps the faster (vx3_engine.cu,
+// launch_links).  (A third variant, a CTA-wide shared-memory queue drained by one warp between two barriers, was never
+// the fastest on any workload and was removed.)
 
 // SMTAB: the batch's material tables fit the shared-memory copies (the normal case); otherwise they are read from global
-template <bool SMTAB, bool QUEUE> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles) {
+template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles) {
     __shared__ LinkSmem sm;
-    __shared__ double sQ[QUEUE ? VX3_LINK_T : 1][12];
-    __shared__ int sQn[2];
     const int tid = threadIdx.x;
     const long long G = gridDim.x;
     if (SMTAB) {
         for (int i = tid; i < D.n_vmats * (int)(sizeof(VoxMatL) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.vm)[i] = reinterpret_cast<const int *>(D.vmatl_tab)[i];
         for (int i = tid; i < D.n_lmats * (int)(sizeof(LinkMatC) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.lm)[i] = reinterpret_cast<const int *>(D.lmat_tab)[i];
     }
-    if (tid < 2) sQn[tid] = 0;
     __syncthreads();
     long long tile = blockIdx.x;
     int4 c4 = link_c4(D, tile * VX3_LINK_T + tid);
-    for (int it = 0; tile < ntiles; tile += G, it++) {
+    for (; tile < ntiles; tile += G) {
         // ---- the next item's constant indices (consumed by the next iteration) ----
         const int4 c4n = link_c4(D, (tile + G) * VX3_LINK_T + tid);
         const int gc = (int)(tile * VX3_LINK_T + tid);
@@ -160,8 +154,8 @@ template <bool SMTAB, bool QUEUE> __global__ void __launch_bounds__(VX3_LINK_T, 
         LinkMid mid;
         float dmN = 0, dmP = 0;
         mid.small = true;
-        if (!QUEUE && !live) continue;
-        if (live) {
+        if (!live) continue;
+        {
             // ---- every load of this link, all independent ----
             const double2 h0 = ldv(D.lh(0, gc)), h1 = ldv(D.lh(1, gc)), h2 = ldv(D.lh(2, gc)), h3 = ldv(D.lh(3, gc)), h4 = ldv(D.lh(4, gc));
             const float4 sn = ldv(D.lstrain + gc);
@@ -194,8 +188,8 @@ template <bool SMTAB, bool QUEUE> __global__ void __launch_bounds__(VX3_LINK_T, 
             }
             if (L.state & (LKS_DETACHED | LKS_REMOVED)) live = false;
             if (status != VX3_SIM_RUNNING || dt == 0 || (mN.fixed && mP.fixed)) live = false;
-            if (!QUEUE && !live) continue;
-            if (live) {
+            if (!live) continue;
+            {
                 L.state &= ~LKS_JUST_CREATED;
                 L.strain = sn.x; L.maxStrain = sn.y; L.strainOffset = sn.z; L.stress = sn.w;
                 L.area = ar.x; L.tsum = ar.y;
@@ -209,41 +203,7 @@ template <bool SMTAB, bool QUEUE> __global__ void __launch_bounds__(VX3_LINK_T, 
                 link_stage_a(L, pN, qN, pP, qP, mid);
             }
         }
-        if (QUEUE) {
-            // ---- the large-angle branch, densely (see above).  Two counters alternate so that one barrier pair per tile suffices ----
-            int *qn = &sQn[it & 1];
-            int slot = -1;
-            if (live && !mid.small) {
-                slot = atomicAdd(qn, 1);
-                double *q = sQ[slot];
-                q[0] = mid.pos2.x; q[1] = mid.pos2.y; q[2] = mid.pos2.z;
-                q[3] = mid.angle2.w; q[4] = mid.angle2.x; q[5] = mid.angle2.y; q[6] = mid.angle2.z;
-                q[7] = L.rest;
-            }
-            __syncthreads();
-            const int nq = *qn;
-            if (tid < nq) {
-                double *q = sQ[tid];
-                V3 p2(q[0], q[1], q[2]), a1v;
-                Q4 a1, a2(q[3], q[4], q[5], q[6]);
-                link_stage_large(p2, a1, a2, a1v, q[7]);
-                q[0] = p2.x;
-                q[1] = a1.w; q[2] = a1.x; q[3] = a1.y; q[4] = a1.z;
-                q[5] = a2.w; q[6] = a2.x; q[7] = a2.y; q[8] = a2.z;
-                q[9] = a1v.x; q[10] = a1v.y; q[11] = a1v.z;
-            }
-            if (tid == 0) sQn[(it + 1) & 1] = 0; // the other counter: nobody touches it until after the next barrier
-            __syncthreads();
-            if (slot >= 0) {
-                const double *q = sQ[slot];
-                mid.pos2 = V3(q[0], 0, 0);
-                mid.angle1 = Q4(q[1], q[2], q[3], q[4]);
-                mid.angle2 = Q4(q[5], q[6], q[7], q[8]);
-                mid.angle1v = V3(q[9], q[10], q[11]);
-            }
-            if (!live) continue;
-        } else if (!mid.small)
-            link_stage_large(mid.pos2, mid.angle1, mid.angle2, mid.angle1v, L.rest);
+        if (!mid.small) link_stage_large(mid.pos2, mid.angle1, mid.angle2, mid.angle1v, L.rest);
         const LinkMatC &lm = SMTAB ? sm.lm[c.z] : D.lmat_tab[c.z];
         LinkOut o;
         link_stage_c(L, mid, lm, D.strain_pool, D.stress_pool, dmN, dmP, o);
@@ -265,14 +225,14 @@ template <bool SMTAB, bool QUEUE> __global__ void __launch_bounds__(VX3_LINK_T, 
     }
 }
 
-// Third variant of the link pass, without any CTA barrier: a lane whose link turns out to need the large-angle branch
+// Second variant of the link pass: a lane whose link turns out to need the large-angle branch
 // does NOT process it — it pushes the link's slot number onto its warp's private queue (shared memory, warp-aggregated
 // push) and idles for the rest of the iteration, so the warp runs the small-angle path only (~780 instructions instead
 // of ~1200).  Whenever a warp's queue holds 32 entries (and once more at the end) the warp spends one iteration on a
 // DENSE pass: every lane takes one deferred link, reloads its inputs (nothing has been stored for it yet, so they are
 // unchanged) and runs the complete update, large-angle branch included, with all lanes busy.  The gathers of a dense pass
 // are uncoalesced, but only the few percent of deferred links pay for that.  Same arithmetic on the same inputs: bit-identical
-// to the other two variants.
+// to k_links.  No CTA barrier anywhere.
 template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links_deferred(Dev D, int ntiles) {
     __shared__ LinkSmem sm;
     __shared__ int sDef[VX3_LINK_T / 32][64];

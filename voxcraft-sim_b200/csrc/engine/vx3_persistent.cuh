@@ -522,6 +522,7 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     const int L = simc[0].lcap, V = simc[0].nvox, voff = simc[0].voff, loff = simc[0].loff;
     if (V < 1) return;
     int G = prop.multiProcessorCount;
+    if ((long long)V > (long long)G * VX3_PERSIST_MAX_RO || (long long)L > (long long)G * VX3_PERSIST_MAX_BLOCK) return; // cannot fit: skip the partitioning
     if ((V + 15) / 16 < G) G = (V + 15) / 16; // at least ~16 voxels per CTA
     if (G < 1) G = 1;
     std::vector<int> idx(V), cta_of(V, 0);
