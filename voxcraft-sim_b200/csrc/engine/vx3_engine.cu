@@ -201,6 +201,18 @@ extern "C" void vx3_engine_trim(void) {
     cudaSetDevice(cur);
 }
 
+// std::vector without the serial zero fill of resize(): the batch builder's threads write every element themselves
+template <class T> struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+    template <class U, class... A> void construct(U *p, A &&...a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void *)p) U; // default-init: no write for trivial types
+        else ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+template <class T> using RawVec = std::vector<T, NoInitAlloc<T>>;
+
 // slices of the arena, planned first (sizes), then staged + uploaded in one go
 struct ArenaPlan {
     struct Item {
@@ -209,7 +221,7 @@ struct ArenaPlan {
         size_t bytes, off;
     };
     std::vector<Item> up, zero;
-    template <class T, class U> void upload(T **field, const std::vector<U> &h) {
+    template <class T, class U, class Al> void upload(T **field, const std::vector<U, Al> &h) {
         static_assert(sizeof(T) == sizeof(U), "element size");
         if (h.empty()) zero.push_back(Item{(void **)field, nullptr, sizeof(T), 0});
         else up.push_back(Item{(void **)field, h.data(), h.size() * sizeof(U), 0});
@@ -478,24 +490,29 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     }
 
     const size_t VS = (nvox + 31) / 32 * 32, LS = (std::max<size_t>(nslots, 1) + 31) / 32 * 32;
-    std::vector<double> pose(nvox * 8, 0.0), phase(nvox, 0.0), initpos(nvox * 3);
-    std::vector<double2> mom2(3 * VS, make_double2(0.0, 0.0));
-    std::vector<int32_t> vflags(nvox), vmat(nvox), vsim(nvox), vlinks(nvox * 6), vext(nvox, -1);
-    std::vector<float> tempe(nvox, 0.0f);
-    std::vector<int16_t> ixyz(nvox * 3);
-    std::vector<double> base_cilia, shift_cilia;
+    // the per-voxel / per-link arrays: uninitialised, every element is written by the fill tasks below
+    RawVec<double> pose(nvox * 8), phase(nvox), initpos(nvox * 3);
+    RawVec<double2> mom2(3 * VS);
+    RawVec<int32_t> vflags(nvox), vmat(nvox), vsim(nvox), vlinks(nvox * 6), vext(nvox);
+    RawVec<float> tempe(nvox);
+    RawVec<int16_t> ixyz(nvox * 3);
+    RawVec<double> base_cilia, shift_cilia;
     bool any_cilia = false;
     for (int s = 0; s < n; s++) any_cilia |= models[s].opt.enable_cilia != 0;
     if (any_cilia) {
-        base_cilia.assign(nvox * 3, 0.0);
-        shift_cilia.assign(nvox * 3, 0.0);
+        base_cilia.resize(nvox * 3);
+        shift_cilia.resize(nvox * 3);
     }
-    std::vector<int2> lends(nslots, make_int2(-1, -1));
-    std::vector<int4> lc4(nslots, make_int4(-1, -1, 0, 0)), vc4(nvox);
-    std::vector<int32_t> lstate(nslots, 0), lmat(nslots, 0);
-    std::vector<double2> lh2(5 * LS, make_double2(0.0, 0.0));
-    std::vector<float4> lstrain(nslots, make_float4(0, 0, 0, 0));
-    std::vector<float2> larea(nslots, make_float2(0, 0));
+    RawVec<int2> lends(nslots);
+    RawVec<int4> lc4(nslots), vc4(nvox);
+    RawVec<int32_t> lstate(nslots), lmat(nslots);
+    RawVec<double2> lh2(5 * LS);
+    RawVec<float4> lstrain(nslots);
+    RawVec<float2> larea(nslots);
+    for (size_t v = nvox; v < VS; v++) // padding of the blocked records
+        for (int p = 0; p < 3; p++) mom2[idx_mo(p, v)] = make_double2(0.0, 0.0);
+    for (size_t g = nslots; g < LS; g++)
+        for (int p = 0; p < 5; p++) lh2[idx_lh(p, g)] = make_double2(0.0, 0.0);
 
     // Pass A (serial, small): materials, programs, externals, targets, CoM chunks — everything that appends to a table
     // shared by the batch.  Pass B (below, one thread per range of simulations): the per-voxel and per-link arrays.
@@ -655,46 +672,45 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.nchunks = (int)chunks.size() - S.chunk_off;
         dy.status = VX3_SIM_RUNNING;
         dy.link_cnt = m.n_links;
+        // collision grid cell: at least the largest possible collision envelope (2 * 0.625 * baseSizeAverage)
+        double maxT = fabs(m.opt.temp_amplitude);
+        if (m.temp && (m.opt.enable_collision || m.opt.enable_attach))
+            for (int i = 0; i < m.n_voxels; i++) maxT = std::max(maxT, (double)fabsf(m.temp[i]));
+        const double cell = 2 * VX3_COLLISION_ENVELOPE_RADIUS * sb[s].maxSize * (1 + maxT * sb[s].maxCte) * (1 + 1e-6);
+        S.cell_inv = cell > 0 ? 1.0 / cell : 1.0;
     }
 
     std::atomic<int> fill_err{0}, ghost_seen{0};
-    auto fill_sim = [&](int s) {
+    // Pass B tasks: voxels [i0, i1) resp. link slots [i0, i1) of simulation s.  Every element of every array is written.
+    auto fill_voxels = [&](int s, int i0, int i1) {
         const vx3_model_desc &m = models[s];
-        SimC &S = b->simc[s];
+        const SimC &S = b->simc[s];
         const std::vector<int> &vm_global = sb[s].vm_global;
-        const std::vector<int> &lg = b->lmat_global[s];
         const int vo = S.voff, ext_base = sb[s].ext_base;
-        double maxT = fabs(m.opt.temp_amplitude);
         bool ghost = false;
-        for (int i = 0; i < m.n_voxels; i++) {
+        for (int i = i0; i < i1; i++) {
             const size_t g = (size_t)vo + i;
             pose[8 * g + 0] = m.pos[3 * i]; pose[8 * g + 1] = m.pos[3 * i + 1]; pose[8 * g + 2] = m.pos[3 * i + 2];
             if (m.orient) for (int k = 0; k < 4; k++) pose[8 * g + 3 + k] = m.orient[4 * i + k];
-            else pose[8 * g + 3] = 1.0;
-            for (int k = 0; k < 3; k++) {
-                initpos[3 * g + k] = m.pos[3 * i + k];
-            }
-            if (m.lin_mom) {
-                mom2[idx_mo(0, g)] = make_double2(m.lin_mom[3 * i], m.lin_mom[3 * i + 1]);
-                mom2[idx_mo(1, g)].x = m.lin_mom[3 * i + 2];
-            }
-            if (m.ang_mom) {
-                mom2[idx_mo(1, g)].y = m.ang_mom[3 * i];
-                mom2[idx_mo(2, g)] = make_double2(m.ang_mom[3 * i + 1], m.ang_mom[3 * i + 2]);
-            }
+            else { pose[8 * g + 3] = 1.0; pose[8 * g + 4] = pose[8 * g + 5] = pose[8 * g + 6] = 0.0; }
+            pose[8 * g + 7] = 0.0; // {temperature, previousDt}: k_temp_init
+            for (int k = 0; k < 3; k++) initpos[3 * g + k] = m.pos[3 * i + k];
+            const double l0 = m.lin_mom ? m.lin_mom[3 * i] : 0.0, l1 = m.lin_mom ? m.lin_mom[3 * i + 1] : 0.0, l2 = m.lin_mom ? m.lin_mom[3 * i + 2] : 0.0;
+            const double a0 = m.ang_mom ? m.ang_mom[3 * i] : 0.0, a1 = m.ang_mom ? m.ang_mom[3 * i + 1] : 0.0, a2 = m.ang_mom ? m.ang_mom[3 * i + 2] : 0.0;
+            mom2[idx_mo(0, g)] = make_double2(l0, l1);
+            mom2[idx_mo(1, g)] = make_double2(l2, a0);
+            mom2[idx_mo(2, g)] = make_double2(a1, a2);
             vflags[g] = (m.vox_flags[i] & VXF_BOOLSTATE_MASK) | VXF_ENABLE_ATTACH;
             ghost |= (m.vox_flags[i] & VX3_VOX_GHOST) != 0;
             vmat[g] = vm_global[m.vox_mat[i]];
             vsim[g] = s;
-            if (m.phase_offset) phase[g] = m.phase_offset[i];
-            if (m.temp) {
-                tempe[g] = m.temp[i];
-                maxT = std::max(maxT, (double)fabsf(m.temp[i]));
-            }
+            phase[g] = m.phase_offset ? m.phase_offset[i] : 0.0;
+            tempe[g] = m.temp ? m.temp[i] : 0.0f;
             for (int k = 0; k < 6; k++) {
                 int li = m.vox_links[6 * i + k];
                 vlinks[6 * g + k] = li >= 0 ? S.loff + li : -1;
             }
+            vext[g] = -1;
             if (m.vox_ext && m.vox_ext[i] >= 0) {
                 if (m.vox_ext[i] >= m.n_externals) {
                     fill_err = 1;
@@ -702,19 +718,32 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 }
                 vext[g] = ext_base + m.vox_ext[i];
             }
+            vc4[g] = make_int4(vmat[g], s, vext[g], 0);
             ixyz[3 * g] = m.ix[i]; ixyz[3 * g + 1] = m.iy[i]; ixyz[3 * g + 2] = m.iz[i];
             if (any_cilia) for (int k = 0; k < 3; k++) {
-                if (m.base_cilia) base_cilia[3 * g + k] = m.base_cilia[3 * i + k];
-                if (m.shift_cilia) shift_cilia[3 * g + k] = m.shift_cilia[3 * i + k];
+                base_cilia[3 * g + k] = m.base_cilia ? m.base_cilia[3 * i + k] : 0.0;
+                shift_cilia[3 * g + k] = m.shift_cilia ? m.shift_cilia[3 * i + k] : 0.0;
             }
         }
         if (ghost) ghost_seen = 1;
-        // collision grid cell: at least the largest possible collision envelope (2 * 0.625 * baseSizeAverage)
-        const double cell = 2 * VX3_COLLISION_ENVELOPE_RADIUS * sb[s].maxSize * (1 + maxT * sb[s].maxCte) * (1 + 1e-6);
-        S.cell_inv = cell > 0 ? 1.0 / cell : 1.0;
-        // links
-        for (int i = 0; i < m.n_links; i++) {
+    };
+    auto fill_links = [&](int s, int i0, int i1) { // slots up to the simulation's capacity: the spare ones are marked empty
+        const vx3_model_desc &m = models[s];
+        const SimC &S = b->simc[s];
+        const std::vector<int> &lg = b->lmat_global[s];
+        const int vo = S.voff;
+        for (int i = i0; i < i1; i++) {
             const size_t g = (size_t)S.loff + i;
+            if (i >= m.n_links) { // spare pool slot (attach)
+                lends[g] = make_int2(-1, -1);
+                lc4[g] = make_int4(-1, -1, 0, 0);
+                lstate[g] = 0;
+                lmat[g] = 0;
+                for (int p = 0; p < 5; p++) lh2[idx_lh(p, g)] = make_double2(0.0, 0.0);
+                lstrain[g] = make_float4(0, 0, 0, 0);
+                larea[g] = make_float2(0, 0);
+                continue;
+            }
             const int vn = m.link_vneg[i], vp = m.link_vpos[i], ax = m.link_axis[i];
             lends[g] = make_int2(vo + vn, vo + vp);
             lmat[g] = lg[m.link_mat[i]];
@@ -723,24 +752,22 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             if (!m.link_small_angle || m.link_small_angle[i]) st |= LKS_SMALL;
             if (m.link_flags && (m.link_flags[i] & VX3_LINK_LOCAL_VELOCITY_VALID)) st |= LKS_VALID;
             lstate[g] = st;
-            {
-                double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                for (int k = 0; k < 3; k++) {
-                    if (m.link_pos2) h[k] = m.link_pos2[3 * i + k];
-                    if (m.link_angle1v) h[3 + k] = m.link_angle1v[3 * i + k];
-                    if (m.link_angle2v) h[6 + k] = m.link_angle2v[3 * i + k];
-                }
-                lh2[idx_lh(0, g)] = make_double2(h[0], h[1]);
-                lh2[idx_lh(1, g)] = make_double2(h[2], h[3]);
-                lh2[idx_lh(2, g)] = make_double2(h[4], h[5]);
-                lh2[idx_lh(3, g)] = make_double2(h[6], h[7]);
-                lh2[idx_lh(4, g)].x = h[8];
+            double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < 3; k++) {
+                if (m.link_pos2) h[k] = m.link_pos2[3 * i + k];
+                if (m.link_angle1v) h[3 + k] = m.link_angle1v[3 * i + k];
+                if (m.link_angle2v) h[6 + k] = m.link_angle2v[3 * i + k];
             }
             const vx3_voxel_material &mn = m.voxel_mats[m.vox_mat[vn]], &mp = m.voxel_mats[m.vox_mat[vp]];
             const float tn = m.temp ? m.temp[vn] : 0.0f, tp = m.temp ? m.temp[vp] : 0.0f;
             // VX3_Link::reset() defaults (VX3_Link.cu:58-70) unless the model carries link state
-            if (m.link_rest_length) lh2[idx_lh(4, g)].y = m.link_rest_length[i];
-            else lh2[idx_lh(4, g)].y = 0.5 * ((mn.nomSize * mn.extScale[ax]) * (1 + tn * mn.alphaCTE) + (mp.nomSize * mp.extScale[ax]) * (1 + tp * mp.alphaCTE));
+            const double rest = m.link_rest_length ? m.link_rest_length[i]
+                                                   : 0.5 * ((mn.nomSize * mn.extScale[ax]) * (1 + tn * mn.alphaCTE) + (mp.nomSize * mp.extScale[ax]) * (1 + tp * mp.alphaCTE));
+            lh2[idx_lh(0, g)] = make_double2(h[0], h[1]);
+            lh2[idx_lh(1, g)] = make_double2(h[2], h[3]);
+            lh2[idx_lh(2, g)] = make_double2(h[4], h[5]);
+            lh2[idx_lh(3, g)] = make_double2(h[6], h[7]);
+            lh2[idx_lh(4, g)] = make_double2(h[8], rest);
             float4 sn = make_float4(0, 0, 0, 0);
             if (m.link_strain) sn.x = m.link_strain[i];
             if (m.link_max_strain) sn.y = m.link_max_strain[i];
@@ -753,17 +780,28 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         }
     };
     {
-        // one thread per contiguous range of simulations (disjoint output ranges); small batches stay on this thread
+        // tasks of <= 64k items, pulled by a few threads (disjoint output ranges); small batches stay on this thread
+        struct Task { int s, kind, i0, i1; };
+        std::vector<Task> tasks;
+        const int CH = 65536;
+        for (int s = 0; s < n; s++) {
+            for (int i = 0; i < models[s].n_voxels; i += CH) tasks.push_back(Task{s, 0, i, std::min(i + CH, models[s].n_voxels)});
+            for (int i = 0; i < b->simc[s].lcap; i += CH) tasks.push_back(Task{s, 1, i, std::min(i + CH, b->simc[s].lcap)});
+        }
         int nthreads = 1;
-        if (n >= 8 && nvox + nslots > 200000) nthreads = (int)std::min<size_t>({(size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)16, (size_t)n / 4});
-        if (nthreads <= 1) {
-            for (int s = 0; s < n; s++) fill_sim(s);
-        } else {
+        if (nvox + nslots > 200000) nthreads = (int)std::min<size_t>({(size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)16, tasks.size()});
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (size_t k; (k = next.fetch_add(1)) < tasks.size();) {
+                const Task &t = tasks[k];
+                if (t.kind == 0) fill_voxels(t.s, t.i0, t.i1);
+                else fill_links(t.s, t.i0, t.i1);
+            }
+        };
+        if (nthreads <= 1) worker();
+        else {
             std::vector<std::thread> th;
-            for (int k = 0; k < nthreads; k++)
-                th.emplace_back([&, k]() {
-                    for (int s = (int)((long long)n * k / nthreads); s < (int)((long long)n * (k + 1) / nthreads); s++) fill_sim(s);
-                });
+            for (int k = 0; k < nthreads; k++) th.emplace_back(worker);
             for (auto &x : th) x.join();
         }
         if (fill_err) return cleanup(fail(VX3_ERR_INVALID, "external index out of range"));
@@ -829,7 +867,6 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     UP(lends, lends);
     UP(lstate, lstate);
     UP(lmat, lmat);
-    for (size_t g = 0; g < nvox; g++) vc4[g] = make_int4(vmat[g], vsim[g], vext[g], 0);
     UP(lc4, lc4);
     UP(vc4, vc4);
     UP(lh2, lh2);
@@ -876,7 +913,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     // on-chip path for a single small collision-free body: its control words, flags, lane tables and the odd-parity pose
     // buffer are arena slices too
     PersistentTables ptab;
-    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost || b->any_signals, any_cilia, prop, lends, vlinks, ixyz, ptab);
+    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost || b->any_signals, any_cilia, prop, lends.data(), vlinks.data(), ixyz.data(), ptab);
     if (b->pplan.ok) {
         plan.zeroed(&b->pplan.ctl, 4 + 2 * 8 * (size_t)b->pplan.grid);
         plan.zeroed(&b->pplan.flags, (size_t)b->pplan.grid * 32);
@@ -1459,15 +1496,31 @@ extern "C" int vx3_batch_positions(vx3_batch *b, int sim, double *init_pos, doub
     const size_t voff = b->simc[s0].voff;
     size_t nv = 0;
     for (int s = s0; s < s1; s++) nv += b->simc[s].nvox;
-    std::vector<double> pose, ip;
-    int rc;
-    if (pos && (rc = d2h(b, pose, b->D.pose, 8 * voff, 8 * nv))) return rc;
-    if (init_pos && (rc = d2h(b, ip, (const double *)b->D.initpos, 3 * voff, 3 * nv))) return rc;
+    // device -> host through the batch's pinned staging buffer when it is large enough (idle after creation), else pageable
+    const size_t pose_bytes = pos ? 8 * nv * sizeof(double) : 0, ip_bytes = init_pos ? 3 * nv * sizeof(double) : 0;
+    std::vector<double> pose_v, ip_v;
+    const double *pose_h = nullptr, *ip_h = nullptr;
+    if (pose_bytes + ip_bytes <= b->res.hcap) {
+        if (pos) {
+            CK(cudaMemcpyAsync(b->res.h, b->D.pose + 8 * voff, pose_bytes, cudaMemcpyDeviceToHost, b->stream));
+            pose_h = reinterpret_cast<const double *>(b->res.h);
+        }
+        if (init_pos) {
+            CK(cudaMemcpyAsync(b->res.h + pose_bytes, b->D.initpos + 3 * voff, ip_bytes, cudaMemcpyDeviceToHost, b->stream));
+            ip_h = reinterpret_cast<const double *>(b->res.h + pose_bytes);
+        }
+    } else {
+        int rc;
+        if (pos && (rc = d2h(b, pose_v, b->D.pose, 8 * voff, 8 * nv))) return rc;
+        if (init_pos && (rc = d2h(b, ip_v, (const double *)b->D.initpos, 3 * voff, 3 * nv))) return rc;
+        pose_h = pose_v.data();
+        ip_h = ip_v.data();
+    }
     CK(cudaStreamSynchronize(b->stream));
     if (pos)
         for (size_t i = 0; i < nv; i++)
-            for (int k = 0; k < 3; k++) pos[3 * i + k] = pose[8 * i + k];
-    if (init_pos) memcpy(init_pos, ip.data(), 3 * nv * sizeof(double));
+            for (int k = 0; k < 3; k++) pos[3 * i + k] = pose_h[8 * i + k];
+    if (init_pos) memcpy(init_pos, ip_h, ip_bytes);
     if (mats) {
         size_t o = 0;
         for (int s = s0; s < s1; s++)

@@ -514,8 +514,7 @@ inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, c
 // Decides whether the batch qualifies, cuts the body into blocks and builds the per-CTA lane tables.  The device arrays
 // are slices of the batch arena, placed by the caller (vx3_engine.cu).
 inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bool any_collide, bool any_dynamic_topology, bool any_cilia,
-                            const cudaDeviceProp &prop, const std::vector<int2> &lends, const std::vector<int32_t> &vlinks,
-                            const std::vector<int16_t> &ixyz, PersistentTables &tb) {
+                            const cudaDeviceProp &prop, const int2 *lends, const int32_t *vlinks, const int16_t *ixyz, PersistentTables &tb) {
     p.ok = false;
     if (simc.size() != 1 || any_collide || any_dynamic_topology || any_cilia) return;
     if (!prop.cooperativeLaunch) return;
@@ -527,7 +526,7 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     if (G < 1) G = 1;
     std::vector<int> idx(V), cta_of(V, 0);
     for (int i = 0; i < V; i++) idx[i] = i;
-    persist_rcb(idx, 0, V, 0, G, ixyz.data(), voff, cta_of);
+    persist_rcb(idx, 0, V, 0, G, ixyz, voff, cta_of);
     std::vector<std::vector<int>> vox(G), lnk(G);
     for (int i = 0; i < V; i++) vox[cta_of[i]].push_back(i); // ascending voxel index within a CTA
     for (int l = 0; l < L; l++) {
