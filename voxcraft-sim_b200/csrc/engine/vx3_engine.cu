@@ -161,6 +161,19 @@ static int resources_acquire(int device, size_t dbytes, size_t hbytes, Resources
     return VX3_OK;
 }
 
+// grows the device arena of an acquired set (nothing has been uploaded into it yet)
+static int resources_grow_device(Resources &r, size_t dbytes) {
+    if (r.dcap >= dbytes) return VX3_OK;
+    if (r.d) cudaFree(r.d);
+    r.d = nullptr;
+    r.dcap = 0;
+    const size_t want = (dbytes + (dbytes >> 3) + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+    cudaError_t e = cudaMalloc((void **)&r.d, want);
+    if (e != cudaSuccess) return fail(VX3_ERR_CUDA, std::string("cudaMalloc (batch arena): ") + cudaGetErrorString(e));
+    r.dcap = want;
+    return VX3_OK;
+}
+
 static void resources_release(Resources &r) {
     if (!r.stream && !r.d && !r.h) return;
     std::vector<Resources> drop;
@@ -227,9 +240,19 @@ struct ArenaPlan {
         else up.push_back(Item{(void **)field, h.data(), h.size() * sizeof(U), 0});
     }
     template <class T> void zeroed(T **field, size_t n) { zero.push_back(Item{(void **)field, nullptr, std::max<size_t>(n, 1) * sizeof(T), 0}); }
+    // arrays that were built in place in the staging buffer: same offset in the arena, nothing to copy
+    std::vector<Item> placed;
+    size_t placed_bytes = 0;
+    template <class T> T *take(char *staging, T **field, size_t n) {
+        const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        placed.push_back(Item{(void **)field, nullptr, bytes, placed_bytes});
+        T *p = reinterpret_cast<T *>(staging + placed_bytes);
+        placed_bytes += (bytes + 255) & ~(size_t)255;
+        return p;
+    }
     size_t up_bytes = 0, total = 0;
     void layout() {
-        size_t o = 0;
+        size_t o = placed_bytes;
         for (Item &i : up) { i.off = o; o += (i.bytes + 255) & ~(size_t)255; }
         up_bytes = o;
         for (Item &i : zero) { i.off = o; o += (i.bytes + 255) & ~(size_t)255; }
@@ -490,25 +513,59 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     }
 
     const size_t VS = (nvox + 31) / 32 * 32, LS = (std::max<size_t>(nslots, 1) + 31) / 32 * 32;
-    // the per-voxel / per-link arrays: uninitialised, every element is written by the fill tasks below
-    RawVec<double> pose(nvox * 8), phase(nvox), initpos(nvox * 3);
-    RawVec<double2> mom2(3 * VS);
-    RawVec<int32_t> vflags(nvox), vmat(nvox), vsim(nvox), vlinks(nvox * 6), vext(nvox);
-    RawVec<float> tempe(nvox);
-    RawVec<int16_t> ixyz(nvox * 3);
-    RawVec<double> base_cilia, shift_cilia;
     bool any_cilia = false;
     for (int s = 0; s < n; s++) any_cilia |= models[s].opt.enable_cilia != 0;
-    if (any_cilia) {
-        base_cilia.resize(nvox * 3);
-        shift_cilia.resize(nvox * 3);
+    // ---- the per-voxel / per-link arrays are built IN PLACE in the pinned staging buffer (no intermediate copies): acquire
+    // it now, sized by an upper bound of everything that will be uploaded; the device arena may still grow later ----
+    Dev &D = b->D;
+    memset(&D, 0, sizeof(D));
+    size_t big_bytes = nvox * (8 * 8 + 8 + 24 + 4 * 5 + 4 + 6 * 4 + 6 + 16 + (any_cilia ? 48 : 0)) + 3 * VS * 16 + nslots * (8 + 16 + 4 + 4 + 16 + 8) + 5 * LS * 16;
+    size_t small_bound = (size_t)n * (sizeof(SimC) + sizeof(SimD) + 64) + nvox * 8 + 64 * 256 + (size_t)256 * 256 * 40 + ((size_t)1 << 20);
+    for (int s = 0; s < n; s++) {
+        const vx3_model_desc &m = models[s];
+        small_bound += (size_t)(2 * m.n_voxel_mats + m.n_link_mats + 2) * (sizeof(VoxMatC) + sizeof(VoxMatL) + sizeof(SigMatC) + sizeof(LinkMatC) + 512);
+        for (int i = 0; i < m.n_voxel_mats; i++) small_bound += 16 * (size_t)(m.voxel_mats[i].n_data + 4);
+        for (int i = 0; i < m.n_link_mats; i++) small_bound += 16 * (size_t)(m.link_mats[i].m.n_data + 4);
+        for (int p = 0; p < VX3_PROG_COUNT; p++) small_bound += sizeof(vx3_token) * (size_t)(m.prog[p].n + 1);
+        small_bound += sizeof(ExtC) * (size_t)(m.n_externals + 1) + sizeof(Chunk) * (size_t)(m.n_voxels / 4096 + 2);
     }
-    RawVec<int2> lends(nslots);
-    RawVec<int4> lc4(nslots), vc4(nvox);
-    RawVec<int32_t> lstate(nslots), lmat(nslots);
-    RawVec<double2> lh2(5 * LS);
-    RawVec<float4> lstrain(nslots);
-    RawVec<float2> larea(nslots);
+    big_bytes += 40 * 256; // alignment of the slices
+    {
+        int rc0 = resources_acquire(device, big_bytes + (6 * LS * 16) + small_bound, big_bytes + small_bound, b->res);
+        if (rc0) return cleanup(rc0);
+    }
+    b->stream = b->res.stream;
+    b->ev0 = b->res.ev0;
+    b->ev1 = b->res.ev1;
+    ArenaPlan plan;
+    char *const stg = b->res.h;
+    double *pose = plan.take(stg, &D.pose, nvox * 8);
+    double2 *mom2 = plan.take(stg, &D.mom2, 3 * VS);
+    int32_t *vflags = plan.take(stg, &D.vflags, nvox);
+#define TAKE(field, count) plan.take(stg, const_cast<std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type **>(&D.field), count)
+    int32_t *vmat = TAKE(vmat, nvox);
+    int32_t *vsim = TAKE(vsim, nvox);
+    double *phase = TAKE(phase, nvox);
+    float *tempe = plan.take(stg, &D.tempe, nvox);
+    int32_t *vlinks = plan.take(stg, &D.vlinks, nvox * 6);
+    int32_t *vext = TAKE(vext, nvox);
+    int16_t *ixyz = TAKE(ixyz, nvox * 3);
+    double *initpos = plan.take(stg, &D.initpos, nvox * 3);
+    double *base_cilia = nullptr, *shift_cilia = nullptr;
+    if (any_cilia) {
+        base_cilia = TAKE(base_cilia, nvox * 3);
+        shift_cilia = TAKE(shift_cilia, nvox * 3);
+    }
+    int2 *lends = plan.take(stg, &D.lends, nslots);
+    int32_t *lstate = plan.take(stg, &D.lstate, nslots);
+    int32_t *lmat = plan.take(stg, &D.lmat, nslots);
+    int4 *lc4 = plan.take(stg, &D.lc4, nslots);
+    int4 *vc4 = TAKE(vc4, nvox);
+    double2 *lh2 = plan.take(stg, &D.lh2, 5 * LS);
+    float4 *lstrain = plan.take(stg, &D.lstrain, nslots);
+    float2 *larea = plan.take(stg, &D.larea, nslots);
+#undef TAKE
+    if (plan.placed_bytes > big_bytes) return cleanup(fail(VX3_ERR_INVALID, "internal: staging bound too small"));
     for (size_t v = nvox; v < VS; v++) // padding of the blocked records
         for (int p = 0; p < 3; p++) mom2[idx_mo(p, v)] = make_double2(0.0, 0.0);
     for (size_t g = nslots; g < LS; g++)
@@ -808,17 +865,14 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         b->any_ghost |= ghost_seen != 0;
     }
 
-    lap("host model -> SoA vectors");
-    Dev &D = b->D;
-    memset(&D, 0, sizeof(D));
+    lap("host model -> SoA arrays (in staging)");
     D.nsims = n;
     D.nvox = (int)nvox;
     D.nlinkslots = (int)nslots;
     D.nchunks = (int)chunks.size();
     D.vstride = (int)VS;
     D.lstride = (int)LS;
-    // ---- plan the arena: every array is a slice; uploaded slices first, zero-initialised ones after ----
-    ArenaPlan plan;
+    // ---- plan the rest of the arena: the small tables follow the in-place arrays, zero-initialised slices come last ----
     std::vector<int32_t> uf_host;
 #define UP(field, vec) plan.upload(const_cast<std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type **>(&D.field), vec)
     UP(simc, b->simc);
@@ -844,34 +898,11 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     UP(exts, exts);
     UP(chunks, chunks);
     UP(targets, targets);
-    UP(pose, pose);
-    UP(mom2, mom2);
-    UP(vflags, vflags);
-    UP(vmat, vmat);
-    UP(vsim, vsim);
-    UP(phase, phase);
-    UP(tempe, tempe);
-    UP(vlinks, vlinks);
-    UP(vext, vext);
-    UP(ixyz, ixyz);
-    UP(initpos, initpos);
-    if (any_cilia) {
-        UP(base_cilia, base_cilia);
-        UP(shift_cilia, shift_cilia);
-    }
     if (b->any_signals) {
         UP(smat_tab, smat_tab);
         plan.zeroed(&D.sig, 6 * nvox);
         plan.zeroed(&D.sprop, nvox);
     }
-    UP(lends, lends);
-    UP(lstate, lstate);
-    UP(lmat, lmat);
-    UP(lc4, lc4);
-    UP(vc4, vc4);
-    UP(lh2, lh2);
-    UP(lstrain, lstrain);
-    UP(larea, larea);
 #undef UP
     plan.zeroed(&D.lf2, 6 * LS);
     plan.zeroed(&D.com_part, chunks.size() * 6);
@@ -913,7 +944,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     // on-chip path for a single small collision-free body: its control words, flags, lane tables and the odd-parity pose
     // buffer are arena slices too
     PersistentTables ptab;
-    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost || b->any_signals, any_cilia, prop, lends.data(), vlinks.data(), ixyz.data(), ptab);
+    persistent_plan(b->pplan, b->simc, b->any_collide, b->any_detach || b->any_secondary || b->any_ghost || b->any_signals, any_cilia, prop, lends, vlinks, ixyz, ptab);
     if (b->pplan.ok) {
         plan.zeroed(&b->pplan.ctl, 4 + 2 * 8 * (size_t)b->pplan.grid);
         plan.zeroed(&b->pplan.flags, (size_t)b->pplan.grid * 32);
@@ -927,25 +958,13 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     plan.layout();
     lap("persistent plan + arena layout");
     int rc;
-    if ((rc = resources_acquire(device, plan.total, plan.up_bytes, b->res))) return cleanup(rc);
-    lap("acquire arena/staging");
-    b->stream = b->res.stream;
-    b->ev0 = b->res.ev0;
-    b->ev1 = b->res.ev1;
-    for (const ArenaPlan::Item &it : plan.up) *it.field = b->res.d + it.off;
-    if (plan.up_bytes < ((size_t)8 << 20)) {
-        for (const ArenaPlan::Item &it : plan.up) memcpy(b->res.h + it.off, it.src, it.bytes);
-    } else { // large batches: stage with several threads (one memcpy stream runs at a fraction of the host's memory bandwidth)
-        const int nt = (int)std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency()));
-        std::vector<std::thread> th;
-        for (int k = 0; k < nt; k++)
-            th.emplace_back([&, k]() {
-                for (const ArenaPlan::Item &it : plan.up) {
-                    const size_t a = it.bytes * k / nt, e = it.bytes * (k + 1) / nt;
-                    if (e > a) memcpy(b->res.h + it.off + a, (const char *)it.src + a, e - a);
-                }
-            });
-        for (auto &x : th) x.join();
+    if (plan.up_bytes > b->res.hcap) return cleanup(fail(VX3_ERR_INVALID, "internal: staging bound too small"));
+    if ((rc = resources_grow_device(b->res, plan.total))) return cleanup(rc);
+    lap("grow arena");
+    for (const ArenaPlan::Item &it : plan.placed) *it.field = b->res.d + it.off;
+    for (const ArenaPlan::Item &it : plan.up) {
+        *it.field = b->res.d + it.off;
+        memcpy(b->res.h + it.off, it.src, it.bytes); // the small tables
     }
     for (const ArenaPlan::Item &it : plan.zero) *it.field = b->res.d + it.off;
     if (D.cell_cnt) D.cell_ovf = D.cell_cnt + ((size_t)D.hmask + 1);
