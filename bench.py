@@ -199,14 +199,20 @@ def run_decomposed(args, lib, built, label, rank, local_rank, world):
         value = float(nvox) * S * K / (dev_ms_max * 1e-3)
         top = max(stats.items(), key=lambda kv: kv[1][0])
         n_l_local = body.batch.sizes[0][1]
-        alg_launch = 184.0 * n_l_local if top[0] == "k_links" else 228.0 * float(slab.owned.sum())
+        finfo = body.batch.fused_info()
+        if top[0] == "k_fused":
+            alg_launch = 228.0 * float(slab.owned.sum()) + 184.0 * finfo[2]
+        elif top[0] == "k_links_face":
+            alg_launch = 184.0 * finfo[3]
+        else:
+            alg_launch = 184.0 * n_l_local if top[0] == "k_links" else 228.0 * float(slab.owned.sum())
         avg_s = 1e-3 * top[1][0] / top[1][1]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms_max / K,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": label + ", cut into %d x-slabs with halo exchange over peer memory (NVLink)" % world, "voxels_total": nvox,
                            "links_total": nlinks, "voxels_owned_sum": int(cnt[1]), "voxels_held_sum_incl_ghosts": int(cnt[2]),
                            "face_voxels_rank0": {str(k): int(len(v)) for k, v in slab.send.items()}, "sim_steps_per_step": S,
-                           "total_sim_steps": S * K, "build": "-fmad=false (parity-grade)", "path": "streaming + k_halo",
+                           "total_sim_steps": S * K, "build": "-fmad=false (parity-grade)", "path": ("fused blocks" if finfo[0] else "streaming") + " + k_halo",
                            "l2": "working set per GPU %.0f MB" % ((nvox * 228 + nlinks * 184) / world / 1e6),
                            "alg_bytes_per_voxel_step": b_alg, "wall_ms_per_step": 1e3 * wall_max / K, "center_of_mass": com},
                 "roofline": {"bound": "hbm", "kernel": top[0], "achieved": alg_launch / avg_s / 1e9, "peak": peak, "unit": "GB/s",
@@ -233,6 +239,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fma", type=int, default=0, help="0 = the product (-fmad=false, parity-grade), 1 = FMA-contracted experimental build")
     ap.add_argument("--no-persistent", action="store_true", help="force the streaming kernels")
+    ap.add_argument("--fused", action="store_true", help="opt into the fused block step (VX3_FUSED=1) instead of the two-pass streaming kernels")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -284,9 +291,12 @@ def main():
         # step stream (strong scaling: the total work is fixed)
         return run_decomposed(args, lib, built, label, rank, local_rank, world)
 
+    if args.fused:
+        os.environ["VX3_FUSED"] = "1"
     batch = Batch(descs, fma=fma, device=local_rank)
     if args.no_persistent:
         batch.set_profiling(False, use_persistent=False)
+    finfo = batch.fused_info()
 
     def barrier():
         torch.cuda.synchronize()
@@ -329,6 +339,10 @@ def main():
         alg_bytes_launch = 184.0 * nlinks
     elif top[0] == "k_voxels":
         alg_bytes_launch = 228.0 * nvox
+    elif top[0] == "k_fused":  # all voxels + the links interior to a block (the face links run in k_links_face)
+        alg_bytes_launch = 228.0 * nvox + 184.0 * batch.fused_info()[2]
+    elif top[0] == "k_links_face":
+        alg_bytes_launch = 184.0 * batch.fused_info()[3]
     else:
         alg_bytes_launch = b_alg * nvox
     avg_launch_s = 1e-3 * top[1][0] / top[1][1]
@@ -396,6 +410,7 @@ def main():
                 "config": {"workload": label, "voxels_per_gpu": nvox, "links_per_gpu": nlinks, "sims_per_gpu": len(descs),
                            "sim_steps_per_step": S, "total_sim_steps": S * K, "build": "fma" if fma else "-fmad=false (parity-grade)",
                            "path": "streaming" if args.no_persistent else "auto",
+                           "fused_step": {"active": bool(finfo[0]), "blocks": finfo[1], "links_interior": finfo[2], "links_face_prepass": finfo[3]},
                            "l2": "state is mutated by every step (each step reads what the previous one wrote); working set "
                                  "%.1f MB %s the 126 MB L2" % ((nvox * 228 + nlinks * 184) / 1e6, "fits in" if nvox * 228 + nlinks * 184 < 100e6 else "exceeds"),
                            "alg_bytes_per_voxel_step": b_alg, "wall_ms_per_step": 1e3 * wall_max / K, "diverged_sims": int(total_div)},

@@ -339,6 +339,23 @@ int vx3_batch_last_timing(vx3_batch *b, double *ms, int64_t *launches);
 int vx3_batch_set_profiling(vx3_batch *b, int on, int use_persistent);
 int vx3_batch_kernel_stats(vx3_batch *b, int index, char *name, int name_cap, double *total_ms, int64_t *launches);
 
+/* Fused step (voxcraft-sim_b200/csrc/engine/vx3_fused.cuh), OPT-IN with environment VX3_FUSED=1 at batch creation: batches
+ * with a fixed link topology (no collisions / attach / detach / SecondaryExperiment / signals) are cut into spatial blocks
+ * and stored block by block; links interior to a block are evaluated and their voxels integrated by one CTA, the end
+ * forces passing through shared memory instead of HBM.  The ABI keeps the model's numbering and the results are
+ * bit-identical to the two-pass kernels.  One visible difference: the link force / moment arrays of vx3_batch_state are
+ * those of the LAST step of the last vx3_batch_step* call (only that step stores interior forces to HBM); after
+ * vx3_batch_run they are unspecified for a simulation that stopped before the end of a launch chunk.
+ *   set_fused(on = 0): run the two-pass kernels on a batch created with VX3_FUSED=1 (same storage order).
+ *   fused_info: out4 = {active (0/1), blocks, links interior to a block, links of the face pre-pass}. */
+int vx3_batch_set_fused(vx3_batch *b, int on);
+int vx3_batch_fused_info(vx3_batch *b, int32_t *out4);
+/* Host-only check of the block partition of `n` models (no device needed; test hook).  max_block_voxels <= 0: the
+ * engine's default.  out8 = {blocks, interior links, face links, live links, voxels, largest block, voxels covered
+ * exactly once (must equal voxels), links covered exactly once (must equal live links)}.  Returns VX3_ERR_INVALID when
+ * the models do not fit the block model. */
+int vx3_fused_plan_check(const vx3_model_desc *models, int n, int max_block_voxels, int64_t *out8);
+
 /* --- slab decomposition of ONE body over the GPUs of a box (BASELINE config 5; no reference twin: the reference only
  * spreads independent files over devices, src/Executables/vx3_node_worker.cu:88-93).  Each rank creates a batch of one
  * sub-model: the voxels of its slab, VX3_VOX_GHOST copies of the neighbour slabs' face voxels and every link with an

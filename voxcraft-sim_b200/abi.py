@@ -185,6 +185,9 @@ def declare_engine_api(lib):
     lib.vx3_batch_last_timing.argtypes = [vp, P(f64), P(i64)]
     lib.vx3_batch_set_profiling.argtypes = [vp, C.c_int, C.c_int]
     lib.vx3_batch_kernel_stats.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, P(f64), P(i64)]
+    lib.vx3_batch_set_fused.argtypes = [vp, C.c_int]
+    lib.vx3_batch_fused_info.argtypes = [vp, P(i32)]
+    lib.vx3_fused_plan_check.argtypes = [P(ModelDesc), C.c_int, C.c_int, P(i64)]
     lib.vx3_batch_halo_setup.argtypes = [vp, C.c_int, C.c_int, P(i32), C.c_int, P(i32)]
     lib.vx3_batch_halo_export.argtypes = [vp, C.c_int, vp]
     lib.vx3_batch_halo_connect.argtypes = [vp, C.c_int, vp, C.c_int]
@@ -206,7 +209,8 @@ def declare_engine_api(lib):
 
 ENGINE_SYMBOLS = ["vx3_batch_create", "vx3_batch_run", "vx3_batch_step", "vx3_batch_step_dt", "vx3_batch_sync",
                   "vx3_batch_state", "vx3_batch_results", "vx3_batch_positions", "vx3_batch_recommended_dt",
-                  "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_batch_halo_setup",
+                  "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_batch_set_fused",
+                  "vx3_batch_fused_info", "vx3_fused_plan_check", "vx3_batch_halo_setup",
                   "vx3_batch_halo_export", "vx3_batch_halo_connect", "vx3_batch_halo_connect_local", "vx3_batch_com_sums",
                   "vx3_batch_step_async", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_engine_trim", "vx3_last_error",
                   "vx3_abi_version"]

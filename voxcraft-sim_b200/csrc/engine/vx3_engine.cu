@@ -20,6 +20,7 @@
 #include "vx3_kernels.cuh"
 #include "vx3_persistent.cuh"
 #include "vx3_halo.cuh"
+#include "vx3_fused.cuh"
 #include "vx3_history.h"
 
 using namespace vx3;
@@ -47,9 +48,9 @@ extern "C" size_t vx3_abi_sizeof(const char *name) {
 }
 
 // ------------------------------------------------------------------ per-kernel timing (bench hook)
-enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_BUILD, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_SIGNALS, KC_COM, KC_TAIL, KC_PERSISTENT, KC_HALO, KC_COUNT };
+enum KernelClass { KC_LINKS = 0, KC_VOXELS, KC_GRID_BUILD, KC_CONTACT, KC_RESOLVE, KC_DETACH, KC_SURFACE, KC_SECONDARY, KC_SIGNALS, KC_COM, KC_TAIL, KC_PERSISTENT, KC_HALO, KC_FUSED, KC_LINKS_FACE, KC_COUNT };
 static const char *const kKernelNames[KC_COUNT] = {"k_links", "k_voxels", "k_grid_build", "k_contact", "k_resolve",
-                                                   "k_detach", "k_surface", "k_secondary", "k_signals", "k_com_partial", "k_tail", "k_persistent", "k_halo"};
+                                                   "k_detach", "k_surface", "k_secondary", "k_signals", "k_com_partial", "k_tail", "k_persistent", "k_halo", "k_fused", "k_links_face"};
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> ev; // pairs
@@ -296,6 +297,14 @@ struct vx3_batch {
     cudaEvent_t lq_ev[2] = {nullptr, nullptr};
     PersistentPlan pplan; // on-chip path for a single small collision-free body
     bool use_persistent = true;
+    FusedPlan fplan;      // fused link + voxel step over spatial blocks for fixed-topology batches (vx3_fused.cuh)
+    bool use_fused = true;
+    // storage order of a fused batch: model (ABI) index -> device index and back, global indices; empty = identity
+    std::vector<int> vperm, lperm, vinv, linv;
+    int vdev(size_t ext) const { return vperm.empty() ? (int)ext : vperm[ext]; }
+    int ldev(size_t ext) const { return lperm.empty() ? (int)ext : lperm[ext]; }
+    int vext(size_t dev) const { return vinv.empty() ? (int)dev : vinv[dev]; }
+    int lext(size_t dev) const { return linv.empty() ? (int)dev : linv[dev]; }
 
     template <class T> int alloc(T **p, size_t n, bool zero = true) {
         *p = nullptr;
@@ -530,6 +539,26 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         small_bound += sizeof(ExtC) * (size_t)(m.n_externals + 1) + sizeof(Chunk) * (size_t)(m.n_voxels / 4096 + 2);
     }
     big_bytes += 40 * 256; // alignment of the slices
+    // Fused step (vx3_fused.cuh): fixed link topology only, and OPT-IN (environment VX3_FUSED=1 at creation): it moves 40 % less
+    // DRAM traffic than the two-pass kernels but is slower on B200 — the step is bound by fp64 instruction latency at 16
+    // warps per SM, not by HBM, and the fused kernel's barriers expose more of it (profiles/r01_ncu_k_fused_*).
+    int fuse_bv = VX3_FUSE_BV;
+    if (const char *e = getenv("VX3_FUSE_BV")) fuse_bv = std::max(8, std::min(VX3_FUSE_BV, atoi(e))); // test hook: smaller blocks
+    const char *fenv = getenv("VX3_FUSED");
+    // (signals are excluded because k_signals defines its result by the voxels' index order, which the block layout permutes)
+    const bool fuse_eligible = fenv && fenv[0] == '1' && !b->any_collide && !b->any_detach && !b->any_secondary && !b->any_signals && nslots > 0;
+    FusedLayout lay;
+    const bool permuted = fuse_eligible && fused_layout_build(models, n, b->simc, fuse_bv, lay);
+    if (permuted) {
+        small_bound += nslots * (4 + 16) + (nvox / 6 + (size_t)n + 16) * 16 + 8 * 256;
+        b->vperm.swap(lay.vperm);
+        b->lperm.swap(lay.lperm);
+        b->vinv.resize(nvox);
+        b->linv.resize(nslots);
+        for (size_t v = 0; v < nvox; v++) b->vinv[b->vperm[v]] = (int)v;
+        for (size_t g = 0; g < nslots; g++) b->linv[b->lperm[g]] = (int)g;
+    }
+    lap("block layout");
     {
         int rc0 = resources_acquire(device, big_bytes + (6 * LS * 16) + small_bound, big_bytes + small_bound, b->res);
         if (rc0) return cleanup(rc0);
@@ -718,7 +747,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             if (any_target)
                 for (int i = 0; i < m.n_voxels; i++) {
                     if (m.vox_mat[i] < 0 || m.vox_mat[i] >= m.n_voxel_mats) continue; // validate_model has already vetted the indices
-                    if (m.voxel_mats[m.vox_mat[i]].is_target) targets.push_back(S.voff + i); // registerTargets
+                    if (m.voxel_mats[m.vox_mat[i]].is_target) targets.push_back(b->vdev((size_t)S.voff + i)); // registerTargets
                 }
         }
         S.ntgt = (int)targets.size() - S.tgt_off;
@@ -746,7 +775,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         const int vo = S.voff, ext_base = sb[s].ext_base;
         bool ghost = false;
         for (int i = i0; i < i1; i++) {
-            const size_t g = (size_t)vo + i;
+            const size_t g = (size_t)b->vdev((size_t)vo + i);
             pose[8 * g + 0] = m.pos[3 * i]; pose[8 * g + 1] = m.pos[3 * i + 1]; pose[8 * g + 2] = m.pos[3 * i + 2];
             if (m.orient) for (int k = 0; k < 4; k++) pose[8 * g + 3 + k] = m.orient[4 * i + k];
             else { pose[8 * g + 3] = 1.0; pose[8 * g + 4] = pose[8 * g + 5] = pose[8 * g + 6] = 0.0; }
@@ -765,7 +794,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             tempe[g] = m.temp ? m.temp[i] : 0.0f;
             for (int k = 0; k < 6; k++) {
                 int li = m.vox_links[6 * i + k];
-                vlinks[6 * g + k] = li >= 0 ? S.loff + li : -1;
+                vlinks[6 * g + k] = li >= 0 ? b->ldev((size_t)S.loff + li) : -1;
             }
             vext[g] = -1;
             if (m.vox_ext && m.vox_ext[i] >= 0) {
@@ -790,7 +819,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         const std::vector<int> &lg = b->lmat_global[s];
         const int vo = S.voff;
         for (int i = i0; i < i1; i++) {
-            const size_t g = (size_t)S.loff + i;
+            const size_t g = (size_t)b->ldev((size_t)S.loff + i);
             if (i >= m.n_links) { // spare pool slot (attach)
                 lends[g] = make_int2(-1, -1);
                 lc4[g] = make_int4(-1, -1, 0, 0);
@@ -802,9 +831,9 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 continue;
             }
             const int vn = m.link_vneg[i], vp = m.link_vpos[i], ax = m.link_axis[i];
-            lends[g] = make_int2(vo + vn, vo + vp);
+            lends[g] = make_int2(b->vdev((size_t)vo + vn), b->vdev((size_t)vo + vp));
             lmat[g] = lg[m.link_mat[i]];
-            lc4[g] = make_int4(vo + vn, vo + vp, lmat[g], s);
+            lc4[g] = make_int4(lends[g].x, lends[g].y, lmat[g], s);
             int st = (ax << LKS_AXIS_SHIFT);
             if (!m.link_small_angle || m.link_small_angle[i]) st |= LKS_SMALL;
             if (m.link_flags && (m.link_flags[i] & VX3_LINK_LOCAL_VELOCITY_VALID)) st |= LKS_VALID;
@@ -955,8 +984,28 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         plan.upload(&b->pplan.deps, ptab.deps);
         plan.upload(&b->pplan.ndeps, ptab.ndeps);
     }
+    std::vector<int> face_slot;
+    std::vector<int4> face_c4;
+    if (permuted) { // the face links of each simulation are one slot range after its blocks' interior links
+        FusedPlan &f = b->fplan;
+        f.ok = true;
+        f.nblocks = (int)lay.blk.size();
+        f.ninterior = (int)lay.ninterior;
+        f.nface = (int)lay.nface;
+        face_slot.reserve(f.nface);
+        face_c4.reserve(f.nface);
+        for (int s = 0; s < n; s++)
+            for (int k = 0; k < lay.face_range[s].y; k++) {
+                face_slot.push_back(lay.face_range[s].x + k);
+                face_c4.push_back(lc4[(size_t)lay.face_range[s].x + k]);
+            }
+        plan.upload(&f.blk, lay.blk);
+        plan.upload(&f.face_slot, face_slot);
+        plan.upload(&f.face_c4, face_c4);
+    }
+    lap("persistent + fused plans");
     plan.layout();
-    lap("persistent plan + arena layout");
+    lap("arena layout");
     int rc;
     if (plan.up_bytes > b->res.hcap) return cleanup(fail(VX3_ERR_INVALID, "internal: staging bound too small"));
     if ((rc = resources_grow_device(b->res, plan.total))) return cleanup(rc);
@@ -1072,6 +1121,21 @@ static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
     b->vox_tiles = cdiv(b->D.nvox, VX3_VOX_T);
     b->link_grid = std::max(1, std::min(b->link_tiles, nl * prop.multiProcessorCount));
     b->vox_grid = std::max(1, std::min(b->vox_tiles, nv * prop.multiProcessorCount));
+    FusedPlan &f = b->fplan;
+    if (f.ok) { // fused step: dynamic shared memory above the 48 KB default, one wave of CTAs striding over the blocks
+        f.smtab = b->link_smtab && b->vox_smtab;
+        f.smem = sizeof(FusedSmem);
+        const void *ks[4] = {(const void *)k_fused<true, false>, (const void *)k_fused<true, true>, (const void *)k_fused<false, false>, (const void *)k_fused<false, true>};
+        int nf = 0;
+        for (const void *k : ks) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f.smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nf, ks[f.smtab ? 0 : 2], VX3_FUSE_T, f.smem));
+        if (nf < 1) f.ok = false;
+        else {
+            f.grid = std::max(1, std::min(f.nblocks, nf * prop.multiProcessorCount));
+            f.face_tiles = cdiv(f.nface, VX3_LINK_T);
+            f.face_grid = std::max(1, std::min(f.face_tiles, nl * prop.multiProcessorCount));
+        }
+    }
     return VX3_OK;
 }
 
@@ -1116,10 +1180,28 @@ static void launch_links(vx3_batch *b) {
     }
 }
 
-static void launch_step(vx3_batch *b, bool check_stop) {
+// last: the final step of a stepping call — the fused kernel then also writes the end forces of interior links to HBM,
+// where a state read-back expects them
+static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     const Dev &D = b->D;
     cudaStream_t st = b->stream;
-    if (D.nlinkslots > 0) launch_links(b);
+    const bool fused = b->use_fused && b->fplan.ok;
+    if (fused) {
+        const FusedPlan &f = b->fplan;
+        if (f.nface > 0) {
+            if (b->link_smtab) LAUNCH_SM(KC_LINKS_FACE, (k_links<true, true>), f.face_grid, VX3_LINK_T, 0, D, f.face_tiles, f.face_slot, f.face_c4, f.nface);
+            else LAUNCH_SM(KC_LINKS_FACE, (k_links<false, true>), f.face_grid, VX3_LINK_T, 0, D, f.face_tiles, f.face_slot, f.face_c4, f.nface);
+        }
+        const FusedArgs a{f.blk, f.nblocks};
+        if (f.smtab) {
+            if (last) LAUNCH_SM(KC_FUSED, (k_fused<true, true>), f.grid, VX3_FUSE_T, f.smem, D, a);
+            else LAUNCH_SM(KC_FUSED, (k_fused<true, false>), f.grid, VX3_FUSE_T, f.smem, D, a);
+        } else {
+            if (last) LAUNCH_SM(KC_FUSED, (k_fused<false, true>), f.grid, VX3_FUSE_T, f.smem, D, a);
+            else LAUNCH_SM(KC_FUSED, (k_fused<false, false>), f.grid, VX3_FUSE_T, f.smem, D, a);
+        }
+    } else if (D.nlinkslots > 0)
+        launch_links(b);
     if (b->any_collide) {
         cudaMemsetAsync(D.cell_cnt, 0, 2 * sizeof(int32_t) * ((size_t)D.hmask + 1), st); // every bucket empty (counts and overflow heads)
         LAUNCH(KC_GRID_BUILD, k_grid_build, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
@@ -1130,7 +1212,8 @@ static void launch_step(vx3_batch *b, bool check_stop) {
     }
     if (b->any_detach && D.nlinkslots > 0) LAUNCH(KC_DETACH, k_detach, cdiv(D.nlinkslots, VX3_BLOCK), VX3_BLOCK, D);
     const bool com = com_step(b, b->hsteps + 1);
-    if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
+    if (fused) {
+    } else if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
     else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
     if (b->any_signals) LAUNCH(KC_SIGNALS, k_signals, b->nsims, 256, D); // end of timeStep (VX3_Voxel.cu:270-275), before removeVoxels
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
@@ -1173,7 +1256,7 @@ static int advance(vx3_batch *b, long long k, bool check_stop) {
                 continue;
             }
         }
-        launch_step(b, check_stop);
+        launch_step(b, check_stop, k == 1);
         k--;
     }
     return VX3_OK;
@@ -1356,6 +1439,102 @@ extern "C" int vx3_batch_kernel_stats(vx3_batch *b, int index, char *name, int n
     return VX3_OK;
 }
 
+extern "C" int vx3_batch_set_fused(vx3_batch *b, int on) {
+    if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
+    b->use_fused = on != 0;
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_fused_info(vx3_batch *b, int32_t *out4) {
+    if (!b || !out4) return fail(VX3_ERR_INVALID, "bad arguments");
+    out4[0] = b->use_fused && b->fplan.ok;
+    out4[1] = b->fplan.nblocks;
+    out4[2] = b->fplan.ninterior;
+    out4[3] = b->fplan.nface;
+    return VX3_OK;
+}
+
+// Host-only: the block layout of the models and its consistency counts (test hook, no device needed).
+extern "C" int vx3_fused_plan_check(const vx3_model_desc *models, int n, int max_block_voxels, int64_t *out8) {
+    if (!models || n <= 0 || !out8) return fail(VX3_ERR_INVALID, "bad arguments");
+    for (int i = 0; i < n; i++) {
+        int rc = validate_model(models[i], i);
+        if (rc) return rc;
+    }
+    std::vector<SimC> simc(n);
+    size_t nvox = 0, nslots = 0;
+    for (int s = 0; s < n; s++) {
+        memset(&simc[s], 0, sizeof(SimC));
+        simc[s].voff = (int)nvox;
+        simc[s].nvox = models[s].n_voxels;
+        simc[s].loff = (int)nslots;
+        simc[s].lcap = models[s].n_links;
+        nvox += models[s].n_voxels;
+        nslots += models[s].n_links;
+    }
+    FusedLayout L;
+    const int bv = max_block_voxels > 0 ? std::min(max_block_voxels, VX3_FUSE_BV) : VX3_FUSE_BV;
+    if (!fused_layout_build(models, n, simc, bv, L)) return fail(VX3_ERR_INVALID, "the models do not fit the block model");
+    // permutations: every device index of a simulation's range is hit exactly once
+    std::vector<int> vseen(nvox, 0), lseen(nslots, 0), blk_of_dev(nvox, -1);
+    int64_t bad = 0, largest = 0;
+    for (int s = 0; s < n; s++) {
+        for (int i = 0; i < simc[s].nvox; i++) {
+            const int d = L.vperm[(size_t)simc[s].voff + i];
+            if (d < simc[s].voff || d >= simc[s].voff + simc[s].nvox) bad++;
+            else vseen[d]++;
+        }
+        for (int i = 0; i < simc[s].lcap; i++) {
+            const int d = L.lperm[(size_t)simc[s].loff + i];
+            if (d < simc[s].loff || d >= simc[s].loff + simc[s].lcap) bad++;
+            else lseen[d]++;
+        }
+    }
+    // blocks: consecutive voxel ranges inside one simulation, within the size bound
+    int vnext = 0;
+    for (size_t b = 0; b < L.blk.size(); b++) {
+        const int4 d = L.blk[b];
+        const int nv = (d.z >> 16) & 0xFFFF;
+        largest = std::max<int64_t>(largest, nv);
+        if (d.x != vnext || nv > bv || d.x < simc[d.w].voff || d.x + nv > simc[d.w].voff + simc[d.w].nvox) bad++;
+        vnext = d.x + nv;
+        for (int k = 0; k < nv; k++) blk_of_dev[(size_t)d.x + k] = (int)b;
+    }
+    if (vnext != (int)nvox) bad++;
+    // links: a slot in a block's interior range joins two voxels of that block; a slot in a face range joins two blocks
+    std::vector<int> owner(nslots, -1); // block of an interior slot
+    int64_t ninterior = 0;
+    for (size_t b = 0; b < L.blk.size(); b++) {
+        const int4 d = L.blk[b];
+        for (int i = 0; i < (d.z & 0xFFFF); i++) owner[(size_t)d.y + i] = (int)b;
+        ninterior += d.z & 0xFFFF;
+    }
+    int64_t nface = 0;
+    for (int s = 0; s < n; s++) {
+        const vx3_model_desc &m = models[s];
+        nface += L.face_range[s].y;
+        for (int i = 0; i < m.n_links; i++) {
+            const int d = L.lperm[(size_t)simc[s].loff + i];
+            const int bn = blk_of_dev[L.vperm[(size_t)simc[s].voff + m.link_vneg[i]]], bp = blk_of_dev[L.vperm[(size_t)simc[s].voff + m.link_vpos[i]]];
+            const bool in_face = d >= L.face_range[s].x && d < L.face_range[s].x + L.face_range[s].y;
+            if (owner[d] >= 0 ? (bn != owner[d] || bp != owner[d] || in_face) : (bn == bp || !in_face)) bad++;
+        }
+    }
+    if (ninterior != L.ninterior || nface != L.nface) bad++;
+    int64_t vok = 0, lok = 0;
+    for (size_t v = 0; v < nvox; v++) vok += vseen[v] == 1;
+    for (size_t g = 0; g < nslots; g++) lok += lseen[g] == 1;
+    out8[0] = (int64_t)L.blk.size();
+    out8[1] = ninterior;
+    out8[2] = nface;
+    out8[3] = (int64_t)nslots;
+    out8[4] = (int64_t)nvox;
+    out8[5] = largest;
+    out8[6] = bad ? -bad : vok;
+    out8[7] = lok;
+    return VX3_OK;
+}
+
 extern "C" int vx3_batch_last_timing(vx3_batch *b, double *ms, int64_t *launches) {
     if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
     if (ms) *ms = b->last_ms;
@@ -1417,35 +1596,38 @@ extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
     if (nl > 0 && (rc = d2h(b, lf2, (const double2 *)D.lf2, 6 * l0, 6 * (l1 - l0)))) return rc;
     if ((rc = d2h(b, lstrain, D.lstrain, S.loff, nl))) return rc;
     CK(cudaStreamSynchronize(b->stream));
+    // the arrays are in the batch's storage order; the view is in the model's (vdev / ldev / vext / lext)
     for (int i = 0; i < nv; i++) {
+        const size_t vd = (size_t)(b->vdev((size_t)S.voff + i) - S.voff);
         for (int k = 0; k < 3; k++) {
-            if (w->pos) w->pos[3 * i + k] = pose[8 * (size_t)i + k];
-            const size_t vb = (size_t)S.voff + i - v0; // index relative to the copied blocks
+            if (w->pos) w->pos[3 * i + k] = pose[8 * vd + k];
+            const size_t vb = (size_t)S.voff + vd - v0; // index relative to the copied blocks
             const double mo[6] = {mom2[idx_mo(0, vb)].x, mom2[idx_mo(0, vb)].y, mom2[idx_mo(1, vb)].x, mom2[idx_mo(1, vb)].y, mom2[idx_mo(2, vb)].x, mom2[idx_mo(2, vb)].y};
             if (w->lin_mom) w->lin_mom[3 * i + k] = mo[k];
             if (w->ang_mom) w->ang_mom[3 * i + k] = mo[3 + k];
-            if (w->contact_force) w->contact_force[3 * i + k] = contact.empty() ? 0.0 : contact[3 * (size_t)i + k];
+            if (w->contact_force) w->contact_force[3 * i + k] = contact.empty() ? 0.0 : contact[3 * vd + k];
         }
-        if (w->orient) for (int k = 0; k < 4; k++) w->orient[4 * i + k] = pose[8 * (size_t)i + 3 + k];
-        if (w->vox_flags) w->vox_flags[i] = vflags[i] & VXF_BOOLSTATE_MASK;
-        if (w->temp) w->temp[i] = tempe[i];
-        if (w->signal) for (int k = 0; k < 6; k++) w->signal[6 * i + k] = sig.empty() ? 0.0 : sig[6 * (size_t)i + k];
-        if (w->vox_links) for (int k = 0; k < 6; k++) w->vox_links[6 * i + k] = vlinks[6 * (size_t)i + k] >= 0 ? vlinks[6 * (size_t)i + k] - S.loff : -1;
+        if (w->orient) for (int k = 0; k < 4; k++) w->orient[4 * i + k] = pose[8 * vd + 3 + k];
+        if (w->vox_flags) w->vox_flags[i] = vflags[vd] & VXF_BOOLSTATE_MASK;
+        if (w->temp) w->temp[i] = tempe[vd];
+        if (w->signal) for (int k = 0; k < 6; k++) w->signal[6 * i + k] = sig.empty() ? 0.0 : sig[6 * vd + k];
+        if (w->vox_links) for (int k = 0; k < 6; k++) w->vox_links[6 * i + k] = vlinks[6 * vd + k] >= 0 ? b->lext((size_t)vlinks[6 * vd + k]) - S.loff : -1;
     }
     // global link-material index -> the simulation's local index (attach-created materials follow the model's)
     std::map<int, int> lm_local;
     for (size_t i = 0; i < b->lmat_global[sim].size(); i++) lm_local.emplace(b->lmat_global[sim][i], (int)i);
     int next_local = (int)b->lmat_global[sim].size();
     for (int i = 0; i < nl; i++) {
-        if (w->link_vneg) w->link_vneg[i] = lends[i].x - S.voff;
-        if (w->link_vpos) w->link_vpos[i] = lends[i].y - S.voff;
-        if (w->link_axis) w->link_axis[i] = (lstate[i] & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
+        const size_t ld = (size_t)(b->ldev((size_t)S.loff + i) - S.loff);
+        if (w->link_vneg) w->link_vneg[i] = lends[ld].x >= 0 ? b->vext((size_t)lends[ld].x) - S.voff : lends[ld].x - S.voff;
+        if (w->link_vpos) w->link_vpos[i] = lends[ld].y >= 0 ? b->vext((size_t)lends[ld].y) - S.voff : lends[ld].y - S.voff;
+        if (w->link_axis) w->link_axis[i] = (lstate[ld] & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
         if (w->link_mat) {
-            auto it = lm_local.find(lmat[i]);
-            if (it == lm_local.end()) it = lm_local.emplace(lmat[i], next_local++).first;
+            auto it = lm_local.find(lmat[ld]);
+            if (it == lm_local.end()) it = lm_local.emplace(lmat[ld], next_local++).first;
             w->link_mat[i] = it->second;
         }
-        const size_t lb = (size_t)S.loff + i - l0;
+        const size_t lb = (size_t)S.loff + ld - l0;
         const double h[10] = {lh2[idx_lh(0, lb)].x, lh2[idx_lh(0, lb)].y, lh2[idx_lh(1, lb)].x, lh2[idx_lh(1, lb)].y, lh2[idx_lh(2, lb)].x, lh2[idx_lh(2, lb)].y,
                               lh2[idx_lh(3, lb)].x, lh2[idx_lh(3, lb)].y, lh2[idx_lh(4, lb)].x, lh2[idx_lh(4, lb)].y};
         double fn[6], fp[6];
@@ -1463,11 +1645,11 @@ extern "C" int vx3_batch_state(vx3_batch *b, int sim, vx3_state_view *w) {
             if (w->link_force_pos) w->link_force_pos[3 * i + k] = fp[k];
             if (w->link_moment_pos) w->link_moment_pos[3 * i + k] = fp[3 + k];
         }
-        if (w->link_strain) w->link_strain[i] = lstrain[i].x;
-        if (w->link_max_strain) w->link_max_strain[i] = lstrain[i].y;
-        if (w->link_strain_offset) w->link_strain_offset[i] = lstrain[i].z;
-        if (w->link_stress) w->link_stress[i] = lstrain[i].w;
-        if (w->link_flags) w->link_flags[i] = lstate[i] & LKS_PUBLIC_MASK;
+        if (w->link_strain) w->link_strain[i] = lstrain[ld].x;
+        if (w->link_max_strain) w->link_max_strain[i] = lstrain[ld].y;
+        if (w->link_strain_offset) w->link_strain_offset[i] = lstrain[ld].z;
+        if (w->link_stress) w->link_stress[i] = lstrain[ld].w;
+        if (w->link_flags) w->link_flags[i] = lstate[ld] & LKS_PUBLIC_MASK;
         if (w->link_rest_length) w->link_rest_length[i] = h[9];
     }
     return VX3_OK;
@@ -1537,9 +1719,18 @@ extern "C" int vx3_batch_positions(vx3_batch *b, int sim, double *init_pos, doub
     }
     CK(cudaStreamSynchronize(b->stream));
     if (pos)
-        for (size_t i = 0; i < nv; i++)
-            for (int k = 0; k < 3; k++) pos[3 * i + k] = pose_h[8 * i + k];
-    if (init_pos) memcpy(init_pos, ip_h, ip_bytes);
+        for (size_t i = 0; i < nv; i++) {
+            const size_t vd = (size_t)b->vdev(voff + i) - voff; // storage order -> model order
+            for (int k = 0; k < 3; k++) pos[3 * i + k] = pose_h[8 * vd + k];
+        }
+    if (init_pos) {
+        if (b->vperm.empty()) memcpy(init_pos, ip_h, ip_bytes);
+        else
+            for (size_t i = 0; i < nv; i++) {
+                const size_t vd = (size_t)b->vdev(voff + i) - voff;
+                for (int k = 0; k < 3; k++) init_pos[3 * i + k] = ip_h[3 * vd + k];
+            }
+    }
     if (mats) {
         size_t o = 0;
         for (int s = s0; s < s1; s++)
@@ -1575,6 +1766,8 @@ extern "C" int vx3_batch_halo_setup(vx3_batch *b, int side, int n_send, const in
     std::vector<int32_t> si(send_vox, send_vox + n_send), ri(recv_vox, recv_vox + n_recv);
     for (int v : si) if (v < 0 || v >= nv) return fail(VX3_ERR_INVALID, "halo send index out of range");
     for (int v : ri) if (v < 0 || v >= nv) return fail(VX3_ERR_INVALID, "halo receive index out of range");
+    for (int &v : si) v = b->vdev((size_t)v); // model index -> storage index (one simulation: voff = 0)
+    for (int &v : ri) v = b->vdev((size_t)v);
     int rc;
     if ((rc = b->upload(&h.send_idx, si))) return rc;
     if ((rc = b->upload(&h.recv_idx, ri))) return rc;

@@ -48,9 +48,10 @@ static int history_frame(vx3_batch *b, int sim, long long j, double t, const vx3
     if (o.record_voxel) {
         snprintf(buf, sizeof(buf), "<<<Step%d Time:%f>>>", (int)j, t);
         out += buf;
-        for (int i = 0; i < nv; i++) {
-            if (vflags[i] & (VX3_VOX_SURFACE | VXF_REMOVED)) continue; // interior (bit named SURFACE) or removed
-            const double *p = &pose[8 * (size_t)i];
+        for (int i = 0; i < nv; i++) { // model order; vd / li = position in the batch's storage order
+            const size_t vd = (size_t)(b->vdev((size_t)S.voff + i) - S.voff);
+            if (vflags[vd] & (VX3_VOX_SURFACE | VXF_REMOVED)) continue; // interior (bit named SURFACE) or removed
+            const double *p = &pose[8 * vd];
             const vx3_voxel_material &m = vm[b->vmat_local[sim][i]];
             const Q4 q(p[3], p[4], p[5], p[6]);
             snprintf(buf, sizeof(buf), "%.1f,%.1f,%.1f,", p[0] * vs, p[1] * vs, p[2] * vs);
@@ -63,19 +64,19 @@ static int history_frame(vx3_batch *b, int sim, long long j, double t, const vx3
                 const bool posLink = c == 1;
                 for (int a = 0; a < 3; a++) {
                     double strain = posLink ? 1.0 : -1.0;
-                    const int g = vlinks[6 * (size_t)i + 2 * a + (posLink ? 0 : 1)];
+                    const int g = vlinks[6 * vd + 2 * a + (posLink ? 0 : 1)];
                     if (g >= 0) {
                         const int li = g - S.loff;
                         const LinkMatC &lm = b->h_lmat_tab[lmat[li]];
                         const bool failed = lm.epsilonFail != -1.0f && lstrain[li].y > lm.epsilonFail;
                         if (!failed) {
-                            const float En = vm[b->vmat_local[sim][lends[li].x - S.voff]].E, Ep = vm[b->vmat_local[sim][lends[li].y - S.voff]].E;
+                            const float En = vm[b->vmat_local[sim][b->vext((size_t)lends[li].x) - S.voff]].E, Ep = vm[b->vmat_local[sim][b->vext((size_t)lends[li].y) - S.voff]].E;
                             const float ratio = Ep / En, st = lstrain[li].x; // strainRatio, strain
                             const float ax = posLink ? 2.0f * st * ratio / (1.0f + ratio) : 2.0f * st / (1.0f + ratio);
                             strain = (1 + ax) * (posLink ? 1 : -1);
                         }
                     }
-                    const double base = (m.nomSize * m.extScale[a]) * (1 + tempe[i] * m.alphaCTE);
+                    const double base = (m.nomSize * m.extScale[a]) * (1 + tempe[vd] * m.alphaCTE);
                     corner[c][a] = (float)((0.5 * base) * strain);
                 }
             }
@@ -84,7 +85,7 @@ static int history_frame(vx3_batch *b, int sim, long long j, double t, const vx3
             out += buf;
             snprintf(buf, sizeof(buf), "%d,", m.matid);
             out += buf;
-            snprintf(buf, sizeof(buf), "%.1f,", sig.empty() ? 0.0 : sig[6 * (size_t)i]); // localSignal (VX3_SimulationManager.cu:88)
+            snprintf(buf, sizeof(buf), "%.1f,", sig.empty() ? 0.0 : sig[6 * vd]); // localSignal (VX3_SimulationManager.cu:88)
             out += buf;
             out += ";";
         }
@@ -93,7 +94,8 @@ static int history_frame(vx3_batch *b, int sim, long long j, double t, const vx3
     if (o.record_link) {
         snprintf(buf, sizeof(buf), "|[[[%d]]]", (int)j);
         out += buf;
-        for (int i = 0; i < nl; i++) {
+        for (int ie = 0; ie < nl; ie++) {
+            const size_t i = (size_t)(b->ldev((size_t)S.loff + ie) - S.loff);
             if (lstate[i] & (LKS_REMOVED | LKS_DETACHED)) continue;
             const double *p1 = &pose[8 * (size_t)(lends[i].y - S.voff)], *p2 = &pose[8 * (size_t)(lends[i].x - S.voff)];
             snprintf(buf, sizeof(buf), "%.4f,%.4f,%.4f,%.4f,%.4f,%.4f,;", p1[0], p1[1], p1[2], p2[0], p2[1], p2[2]);

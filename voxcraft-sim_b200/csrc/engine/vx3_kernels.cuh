@@ -132,21 +132,37 @@ __device__ __forceinline__ int4 link_c4(const Dev &D, long long g) { return g < 
 // the fastest on any workload and was removed.)
 
 // SMTAB: the batch's material tables fit the shared-memory copies (the normal case); otherwise they are read from global
-template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles) {
+// LIST: the pass runs over a list of link slots (list_slot[i], with their index records list_c4[i]) instead of all slots —
+// the pre-pass of the fused step (vx3_fused.cuh), which evaluates only the links across block faces.
+template <bool SMTAB, bool LIST = false>
+__global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles, const int *__restrict__ list_slot = nullptr, const int4 *__restrict__ list_c4 = nullptr, int nlist = 0) {
     __shared__ LinkSmem sm;
     const int tid = threadIdx.x;
     const long long G = gridDim.x;
+    auto fetch = [&](long long i, int &slot) -> int4 { // index record and slot of item i (empty past the end)
+        if (LIST) {
+            if (i < nlist) {
+                slot = __ldg(list_slot + i);
+                return __ldg(list_c4 + i);
+            }
+            slot = 0;
+            return make_int4(-1, -1, 0, 0);
+        }
+        slot = (int)i;
+        return link_c4(D, i);
+    };
     if (SMTAB) {
         for (int i = tid; i < D.n_vmats * (int)(sizeof(VoxMatL) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.vm)[i] = reinterpret_cast<const int *>(D.vmatl_tab)[i];
         for (int i = tid; i < D.n_lmats * (int)(sizeof(LinkMatC) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.lm)[i] = reinterpret_cast<const int *>(D.lmat_tab)[i];
     }
     __syncthreads();
     long long tile = blockIdx.x;
-    int4 c4 = link_c4(D, tile * VX3_LINK_T + tid);
+    int gnext;
+    int4 c4 = fetch(tile * VX3_LINK_T + tid, gnext);
     for (; tile < ntiles; tile += G) {
         // ---- the next item's constant indices (consumed by the next iteration) ----
-        const int4 c4n = link_c4(D, (tile + G) * VX3_LINK_T + tid);
-        const int gc = (int)(tile * VX3_LINK_T + tid);
+        const int gc = gnext;
+        const int4 c4n = fetch((tile + G) * VX3_LINK_T + tid, gnext);
         const int4 c = c4;
         c4 = c4n;
         bool live = c.x >= 0; // empty pool slot / past the end

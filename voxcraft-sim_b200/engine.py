@@ -87,6 +87,15 @@ class Batch:
     def set_profiling(self, on=True, use_persistent=True):
         self._check(self.lib.vx3_batch_set_profiling(self.h, int(on), int(use_persistent)), "vx3_batch_set_profiling")
 
+    def set_fused(self, on=True):
+        self._check(self.lib.vx3_batch_set_fused(self.h, int(on)), "vx3_batch_set_fused")
+
+    def fused_info(self):
+        """(active, blocks, interior links, face links) of the fused step's block plan."""
+        out = (C.c_int32 * 4)()
+        self._check(self.lib.vx3_batch_fused_info(self.h, out), "vx3_batch_fused_info")
+        return tuple(out)
+
     def kernel_stats(self):
         out, i = {}, 0
         while True:
