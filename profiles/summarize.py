@@ -23,7 +23,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "launch__occupancy_limit_shared_mem", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
 def launches(path):

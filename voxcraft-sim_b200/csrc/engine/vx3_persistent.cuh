@@ -478,36 +478,38 @@ struct PersistentTables {
     std::vector<int> lk_slot, vx_id, vx_lane, deps, ndeps;
 };
 
-// recursive coordinate bisection: voxels idx[lo, hi) go to CTAs [c0, c0 + nc)
-inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, const int16_t *ixyz, int voff, std::vector<int> &cta_of, int depth = 0) {
+// recursive coordinate bisection: voxels idx[lo, hi) go to CTAs [c0, c0 + nc).  The selection runs on packed 64-bit keys
+// (coordinate along the cut axis, voxel index) in a scratch array: plain integer compares, no indirection — (coordinate,
+// index) is a strict total order, so the partition is unique whatever nth_element does inside.
+inline void persist_rcb(std::vector<int> &idx, int lo, int hi, int c0, int nc, const int16_t *ixyz, int voff, std::vector<int> &cta_of, std::vector<unsigned long long> &keys,
+                        int depth = 0) {
     if (nc == 1) {
         for (int i = lo; i < hi; i++) cta_of[idx[i]] = c0;
         return;
     }
     int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
-    for (int i = lo; i < hi; i++)
+    for (int i = lo; i < hi; i++) {
+        const int16_t *c = ixyz + 3 * ((size_t)voff + idx[i]);
         for (int a = 0; a < 3; a++) {
-            const int c = ixyz[3 * ((size_t)voff + idx[i]) + a];
-            mn[a] = std::min(mn[a], c);
-            mx[a] = std::max(mx[a], c);
+            mn[a] = std::min(mn[a], (int)c[a]);
+            mx[a] = std::max(mx[a], (int)c[a]);
         }
+    }
     int ax = 0;
     for (int a = 1; a < 3; a++)
         if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
-    // (coordinate, index) is a strict total order, so the partition below is unique whatever nth_element does inside
     const int ncl = nc / 2;
     const int mid = lo + (int)((long long)(hi - lo) * ncl / nc);
-    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int p, int q) {
-        const int cp = ixyz[3 * ((size_t)voff + p) + ax], cq = ixyz[3 * ((size_t)voff + q) + ax];
-        return cp != cq ? cp < cq : p < q;
-    });
-    if (depth < 2 && hi - lo > 2048) { // the two halves touch disjoint ranges of idx and cta_of: run the top levels on 4 threads
-        std::thread left([&]() { persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of, depth + 1); });
-        persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of, depth + 1);
+    for (int i = lo; i < hi; i++) keys[i] = ((unsigned long long)(unsigned)(ixyz[3 * ((size_t)voff + idx[i]) + ax] + 32768) << 32) | (unsigned)idx[i];
+    std::nth_element(keys.begin() + lo, keys.begin() + mid, keys.begin() + hi);
+    for (int i = lo; i < hi; i++) idx[i] = (int)(unsigned)keys[i];
+    if (depth < 2 && hi - lo > 16384) { // the two halves touch disjoint ranges of idx, keys and cta_of: run the top levels on 4 threads
+        std::thread left([&]() { persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of, keys, depth + 1); });
+        persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of, keys, depth + 1);
         left.join();
     } else {
-        persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of, depth + 1);
-        persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of, depth + 1);
+        persist_rcb(idx, lo, mid, c0, ncl, ixyz, voff, cta_of, keys, depth + 1);
+        persist_rcb(idx, mid, hi, c0 + ncl, nc - ncl, ixyz, voff, cta_of, keys, depth + 1);
     }
 }
 
@@ -526,7 +528,8 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     if (G < 1) G = 1;
     std::vector<int> idx(V), cta_of(V, 0);
     for (int i = 0; i < V; i++) idx[i] = i;
-    persist_rcb(idx, 0, V, 0, G, ixyz, voff, cta_of);
+    std::vector<unsigned long long> keys(V);
+    persist_rcb(idx, 0, V, 0, G, ixyz, voff, cta_of, keys);
     std::vector<std::vector<int>> vox(G), lnk(G);
     for (int i = 0; i < V; i++) vox[cta_of[i]].push_back(i); // ascending voxel index within a CTA
     for (int l = 0; l < L; l++) {
