@@ -53,7 +53,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
+
+    def begin(self):
+        """The timed region starts here: only samples from now on count (the process is started before the warm-up, so
+        that it is already streaming — nvidia-smi takes a few hundred ms to come up, longer than a short timed region)."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -71,6 +76,10 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if len(self.lines) <= self.first:  # a timed region shorter than the sampling period: take the sample that ends it
+            t0 = time.perf_counter()
+            while len(self.lines) <= self.first and time.perf_counter() - t0 < 0.5:
+                time.sleep(0.01)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -78,7 +87,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -167,11 +176,12 @@ def run_decomposed(args, lib, built, label, rank, local_rank, world):
         dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(Wm):
         body.step(S)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     dev_ms, launches = 0.0, 0
     t0 = time.perf_counter()
     for _ in range(K):
@@ -276,6 +286,7 @@ def main():
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     fma = bool(args.fma)
@@ -304,11 +315,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(Wm):
         batch.step(S)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     dev_ms, launches = 0.0, 0
     t_wall0 = time.perf_counter()
     for _ in range(K):

@@ -123,3 +123,29 @@ def test_config5_cross_section_link_variants_bit_identical():
         assert r0.status == 0 and np.isfinite(s0["pos"]).all()
     finally:
         lib.vx3_builder_destroy(b)
+
+
+def test_config3_full_run_fitness_matches_the_oracle():
+    """SURVEY §8(d), last gate: a config 3 robot run to its stop condition (t > 1 s, ~40,000 steps, floor contact and
+    stick/slip friction included) reports the oracle's step count and time exactly and its fitness within 1e-6 relative."""
+    lib = util.load_engine()
+    picks = [W.c3_spec(k) for k in (5, 12)]
+    built = [s.build(lib) for s in picks]
+    try:
+        eng = EngineBatch([d for _, d in built])
+        eng.run()
+        res = eng.results()
+        eng.close()
+        for (b, d), r in zip(built, res):
+            orc = OracleSim(d)
+            orc.run()
+            ro = orc.result(refresh=False)
+            rel = abs(r.fitness_score - ro.fitness_score) / max(abs(ro.fitness_score), 1e-30)
+            print("config 3 full run: %d voxels, %d steps, fitness %.9g (oracle %.9g, rel %.1e)" % (d.contents.n_voxels, r.steps, r.fitness_score, ro.fitness_score, rel))
+            assert r.status == ro.status == 1  # VX3_SIM_STOPPED
+            assert r.steps == ro.steps and r.current_time == ro.current_time
+            np.testing.assert_allclose(r.fitness_score, ro.fitness_score, rtol=1e-6)
+            np.testing.assert_allclose(list(r.current_com), list(ro.current_com), rtol=1e-6)
+    finally:
+        for b, _ in built:
+            lib.vx3_builder_destroy(b)

@@ -447,9 +447,31 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         tp0 = now;
     };
     if (prop.major < 10) return fail(VX3_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
-    for (int i = 0; i < n; i++) {
-        int rc = validate_model(models[i], i);
-        if (rc) return rc;
+    {
+        // the checks walk every index of every model: large batches are vetted by a few threads; the first failing model is
+        // vetted again on this thread so that its message lands in this thread's error slot
+        size_t items = 0;
+        for (int i = 0; i < n; i++) items += (size_t)std::max(models[i].n_voxels, 0) + (size_t)std::max(models[i].n_links, 0);
+        std::atomic<int> first_bad{n};
+        const int nt = (n >= 16 && items > 200000) ? (int)std::min<size_t>({(size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)8, (size_t)n}) : 1;
+        if (nt > 1) {
+            std::atomic<int> next{0};
+            auto worker = [&]() {
+                for (int i; (i = next.fetch_add(1)) < n;)
+                    if (validate_model(models[i], i)) {
+                        int cur = first_bad.load();
+                        while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {}
+                    }
+            };
+            std::vector<std::thread> th;
+            for (int k = 0; k < nt; k++) th.emplace_back(worker);
+            for (auto &x : th) x.join();
+            if (first_bad < n) return validate_model(models[first_bad], first_bad);
+        } else
+            for (int i = 0; i < n; i++) {
+                int rc = validate_model(models[i], i);
+                if (rc) return rc;
+            }
     }
     lap("validate");
     CK(cudaSetDevice(device));
@@ -558,7 +580,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         for (size_t v = 0; v < nvox; v++) b->vinv[b->vperm[v]] = (int)v;
         for (size_t g = 0; g < nslots; g++) b->linv[b->lperm[g]] = (int)g;
     }
-    lap("block layout");
+    lap("storage order");
     {
         int rc0 = resources_acquire(device, big_bytes + (6 * LS * 16) + small_bound, big_bytes + small_bound, b->res);
         if (rc0) return cleanup(rc0);
