@@ -121,6 +121,22 @@ __device__ __forceinline__ double2 ldv_if(const double2 *p, bool on) {
     return r;
 }
 
+// Gathers of records another kernel wrote (end poses in the link pass, end forces in the voxel pass): the qualifier is a
+// build-time choice so that L1-cached variants can be measured against the pinned volatile form (scripts/build_variants.sh).
+#ifndef VX3_GATHER_LD
+#define VX3_GATHER_LD "ld.volatile.global"
+#endif
+__device__ __forceinline__ double2 ldgat(const double2 *p) {
+    double2 r;
+    asm volatile(VX3_GATHER_LD ".v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ldgat_if(const double2 *p, bool on) {
+    double2 r = make_double2(0.0, 0.0);
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p " VX3_GATHER_LD ".v2.f64 {%0, %1}, [%2];\n\t}" : "+d"(r.x), "+d"(r.y) : "l"(p), "r"((int)on));
+    return r;
+}
+
 __device__ __forceinline__ int4 link_c4(const Dev &D, long long g) { return g < D.nlinkslots ? __ldg(D.lc4 + g) : make_int4(-1, -1, 0, 0); }
 
 // The large-angle branch of orientLink costs ~540 instructions on top of ~780, and in an actuated body a few percent of
@@ -178,8 +194,8 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
             const float2 ar = ldv(D.larea + gc);
             L.state = ldv(D.lstate + gc);
             const double2 *pa = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.x), *pb = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.y);
-            const double2 a0 = ldv(pa), a1 = ldv(pa + 1), a2 = ldv(pa + 2), a3 = ldv(pa + 3);
-            const double2 b0 = ldv(pb), b1 = ldv(pb + 1), b2 = ldv(pb + 2), b3 = ldv(pb + 3);
+            const double2 a0 = ldgat(pa), a1 = ldgat(pa + 1), a2 = ldgat(pa + 2), a3 = ldgat(pa + 3);
+            const double2 b0 = ldgat(pb), b1 = ldgat(pb + 1), b2 = ldgat(pb + 2), b3 = ldgat(pb + 3);
             const int vmN = ldv(D.vmat + c.x), vmP = ldv(D.vmat + c.y);
             const int4 *hp = reinterpret_cast<const int4 *>(D.simd + c.w);
             const int4 hot0 = ldv(hp), hot1 = ldv(hp + 1);
@@ -294,8 +310,8 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
             const float2 ar = ldv(D.larea + gc);
             L.state = ldv(D.lstate + gc);
             const double2 *pa = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.x), *pb = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.y);
-            const double2 a0 = ldv(pa), a1 = ldv(pa + 1), a2 = ldv(pa + 2), a3 = ldv(pa + 3);
-            const double2 b0 = ldv(pb), b1 = ldv(pb + 1), b2 = ldv(pb + 2), b3 = ldv(pb + 3);
+            const double2 a0 = ldgat(pa), a1 = ldgat(pa + 1), a2 = ldgat(pa + 2), a3 = ldgat(pa + 3);
+            const double2 b0 = ldgat(pb), b1 = ldgat(pb + 1), b2 = ldgat(pb + 2), b3 = ldgat(pb + 3);
             const int vmN = ldv(D.vmat + c.x), vmP = ldv(D.vmat + c.y);
             const int4 *hp = reinterpret_cast<const int4 *>(D.simd + c.w);
             const int4 hot0 = ldv(hp), hot1 = ldv(hp + 1);
@@ -397,8 +413,8 @@ __device__ __forceinline__ VoxIdx vox_idx(const Dev &D, long long v) {
 }
 // the voxel is the negative end of the links in its even (+axis) slots and the positive end of those in its odd slots
 #define VX3_LOAD_END_FORCE(dir, slot)                                                                                   \
-    const double2 fa##dir = ldv_if(D.lf(3 * (dir & 1), slot), slot >= 0), fb##dir = ldv_if(D.lf(3 * (dir & 1) + 1, slot), slot >= 0),                \
-                  fc##dir = ldv_if(D.lf(3 * (dir & 1) + 2, slot), slot >= 0);
+    const double2 fa##dir = ldgat_if(D.lf(3 * (dir & 1), slot), slot >= 0), fb##dir = ldgat_if(D.lf(3 * (dir & 1) + 1, slot), slot >= 0),                \
+                  fc##dir = ldgat_if(D.lf(3 * (dir & 1) + 2, slot), slot >= 0);
 #define VX3_ADD_END_FORCE(dir, cond)                                                                                    \
     if (cond) {                                                                                                         \
         F += V3(fa##dir.x, fa##dir.y, fb##dir.x);                                                                       \
