@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
@@ -526,10 +527,19 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     if ((long long)V > (long long)G * VX3_PERSIST_MAX_RO || (long long)L > (long long)G * VX3_PERSIST_MAX_BLOCK) return; // cannot fit: skip the partitioning
     if ((V + 15) / 16 < G) G = (V + 15) / 16; // at least ~16 voxels per CTA
     if (G < 1) G = 1;
+    const bool lapt = getenv("VX3_CREATE_TIMING") != nullptr;
+    auto lt0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!lapt) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[create timing]   plan: %-20s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - lt0).count());
+        lt0 = now;
+    };
     std::vector<int> idx(V), cta_of(V, 0);
     for (int i = 0; i < V; i++) idx[i] = i;
     std::vector<unsigned long long> keys(V);
     persist_rcb(idx, 0, V, 0, G, ixyz, voff, cta_of, keys);
+    lap("bisection");
     std::vector<std::vector<int>> vox(G), lnk(G);
     for (int i = 0; i < V; i++) vox[cta_of[i]].push_back(i); // ascending voxel index within a CTA
     for (int l = 0; l < L; l++) {
@@ -546,11 +556,13 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     const int ro = (mostv + 31) / 32 * 32; // voxel lanes per role (translate / rotate / temperature)
     int T = (std::max(most, 3 * ro) + 31) / 32 * 32;
     if (T > VX3_PERSIST_MAX_BLOCK || ro > VX3_PERSIST_MAX_RO) return; // blocks too large for one item per thread: streaming path
+    lap("block lists");
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_persistent, T, 0) != cudaSuccess || nb < 1) {
         cudaGetLastError();
         return;
     }
+    lap("occupancy query");
     tb.lk_slot.assign((size_t)G * T, -1);
     tb.vx_id.assign((size_t)G * T, -1);
     tb.vx_lane.assign((size_t)G * T * 6, -1);
@@ -587,6 +599,7 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
         }
         for (size_t k = 0; k < lnk[c].size(); k++) lane_of[lnk[c][k] & ~VX3_PERSIST_DUP] = -1;
     }
+    lap("lane tables");
     p.timing = getenv("VX3_PERSIST_TIMING") != nullptr;
     p.grid = G;
     p.block = T;
