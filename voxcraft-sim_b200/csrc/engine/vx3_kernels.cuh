@@ -717,14 +717,18 @@ struct ContactSelf {
     bool have_links;
     int vl[6], vo[6]; // own links and their other ends (loaded when the first candidate passes the envelope test)
 };
+// the 64-byte record in two 256-bit requests (sm_100 LDG.E.ENL2.256) instead of four 128-bit ones: a contact sweep looks at
+// ~90 candidate records per surface voxel, and the phase is bound by the number of memory requests it issues
 __device__ __forceinline__ ContactRec load_crec(const Dev &D, int v) {
     ContactRec r;
-    const int4 *s = reinterpret_cast<const int4 *>(D.crec + v);
-    const int4 a = s[0], b = s[1], c = s[2], d = s[3];
-    r.cx = a.x; r.cy = a.y; r.cz = a.z; r.bucket = a.w;
-    r.px = __hiloint2double(b.y, b.x); r.py = __hiloint2double(b.w, b.z);
-    r.pz = __hiloint2double(c.y, c.x); r.bs = __hiloint2double(c.w, c.z);
-    r.sim = d.x; r.mat = d.y; r.fixed = d.z; r._pad = 0;
+    unsigned long long a0, a1, a2, a3, b0, b1, b2, b3;
+    const ContactRec *s = D.crec + v;
+    asm("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(s));
+    asm("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(reinterpret_cast<const char *>(s) + 32));
+    r.cx = (int)(unsigned)a0; r.cy = (int)(a0 >> 32); r.cz = (int)(unsigned)a1; r.bucket = (int)(a1 >> 32);
+    r.px = __longlong_as_double((long long)a2); r.py = __longlong_as_double((long long)a3);
+    r.pz = __longlong_as_double((long long)b0); r.bs = __longlong_as_double((long long)b1);
+    r.sim = (int)(unsigned)b2; r.mat = (int)(b2 >> 32); r.fixed = (int)(unsigned)b3; r._pad = 0;
     return r;
 }
 __device__ __forceinline__ void contact_self(const Dev &D, int v, ContactSelf &c) {
@@ -775,9 +779,9 @@ __device__ __forceinline__ void prefetch_crec(const Dev &D, int u) { asm volatil
 template <class F> __device__ __forceinline__ void bucket_for_each(const Dev &D, int b, F fn) {
     const int n = D.cell_cnt[b];
     if (n == 0) return;
-    const int4 *it = reinterpret_cast<const int4 *>(D.cell_items + VX3_CELL_SLOTS * (size_t)b);
-    const int4 i0 = it[0], i1 = it[1];
-    const int ids[VX3_CELL_SLOTS] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    unsigned long long i0, i1, i2, i3; // the bucket's 8 inline slots: one 256-bit request (written by atomics in k_grid_build, an earlier kernel)
+    asm("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(i0), "=l"(i1), "=l"(i2), "=l"(i3) : "l"(D.cell_items + VX3_CELL_SLOTS * (size_t)b));
+    const int ids[VX3_CELL_SLOTS] = {(int)(unsigned)i0, (int)(i0 >> 32), (int)(unsigned)i1, (int)(i1 >> 32), (int)(unsigned)i2, (int)(i2 >> 32), (int)(unsigned)i3, (int)(i3 >> 32)};
     const int m = n < VX3_CELL_SLOTS ? n : VX3_CELL_SLOTS;
 #pragma unroll
     for (int k = 0; k < VX3_CELL_SLOTS; k++)
@@ -910,7 +914,10 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
 // test incl. the depth-5 neighbour search), and lane 0 adds the forces up in ascending partner index — the same sums in the
 // same order as the one-thread version above.
 #define VX3_CONTACT_WARPS 4
-__global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS) k_contact(Dev D) {
+#ifndef VX3_CONTACT_MIN_CTAS
+#define VX3_CONTACT_MIN_CTAS 8 // 64 registers: the phase is a chain of dependent loads per warp, so resident warps are what counts (6 / 8 / 10 / 12 CTAs: 59.9 / 52.4 / 62.2 / 69.6 us on config 4)
+#endif
+__global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) k_contact(Dev D) {
     __shared__ int sList[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS], sSorted[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS];
     __shared__ double sForce[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS][3];
     __shared__ int sCnt[VX3_CONTACT_WARPS];
