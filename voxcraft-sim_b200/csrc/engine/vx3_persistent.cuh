@@ -273,9 +273,9 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
         const double *Pr = (s & 1) ? P1 : P0;
         double *Pw = (s & 1) ? P0 : P1;
         if (dep_flag) {
-            while (ld_acquire_u32(dep_flag) < (unsigned int)s) {
-                if (ld_relaxed_u32(divword)) break; // the producer may have left: the simulation is over
-            }
+            // (the divergence word is looked at every 8th poll only: behind the acquire it would cost a second L2 round trip per poll)
+            for (int spins = 0; ld_acquire_u32(dep_flag) < (unsigned int)s;)
+                if ((++spins & 7) == 0 && ld_relaxed_u32(divword)) break; // the producer may have left: the simulation is over
         }
         if (tid == 0) s_div = (int)ld_relaxed_u32(divword);
         __syncthreads();
