@@ -57,6 +57,17 @@ VXHD V3 operator*(double f, const V3 &v) { return v * f; }
 #define VX3_SMALL_ANGLE_RAD 1.732e-2
 #define VX3_SLTHRESH_ACOS2SQRT 2.4e-3
 
+// sin and cos of one argument: on the device one libdevice call (shared argument reduction; same results as sin() and cos(),
+// one dependent chain instead of two on the latency-bound paths that call it)
+VXHD void sin_cos(double a, double &s, double &c) {
+#ifdef __CUDA_ARCH__
+    sincos(a, &s, &c);
+#else
+    s = sin(a);
+    c = cos(a);
+#endif
+}
+
 struct Q4 {
     double w, x, y, z;
     VXHD Q4() : w(1), x(0), y(0), z(0) {}
@@ -81,9 +92,10 @@ struct Q4 {
             w = 1.0 - 0.5 * thetaMag2;
             s = 1.0 - thetaMag2 / 6.0;
         } else {
-            double thetaMag = sqrt(thetaMag2);
-            w = cos(thetaMag);
-            s = sin(thetaMag) / thetaMag;
+            double thetaMag = sqrt(thetaMag2), sn, cs;
+            sin_cos(thetaMag, sn, cs);
+            w = cs;
+            s = sn / thetaMag;
         }
         x = theta.x * s;
         y = theta.y * s;
@@ -109,8 +121,9 @@ struct Q4 {
         }
         const double AxisMagInv = 1.0 / sqrt(RotFromNorm.z * RotFromNorm.z + RotFromNorm.y * RotFromNorm.y);
         const double a = 0.5 * theta;
-        const double s = sin(a);
-        w = cos(a);
+        double s, c;
+        sin_cos(a, s, c);
+        w = c;
         x = 0;
         y = RotFromNorm.z * AxisMagInv * s;
         z = -RotFromNorm.y * AxisMagInv * s;
