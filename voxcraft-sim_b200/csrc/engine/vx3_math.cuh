@@ -101,8 +101,11 @@ struct Q4 {
         y = theta.y * s;
         z = theta.z * s;
     }
-    VXHD void FromAngleToPosX(const V3 &RotateFrom) {
-        if (V3(0, 0, 0) == RotateFrom) return;
+    // len_out (optional): |RotateFrom| when the general branch computed it for the normalisation (the caller needs the same
+    // sqrt(x*x + y*y + z*z) right after, VX3_Link.cu:119: one IEEE sqrt sequence instead of two on the large-angle chain);
+    // returns whether it did
+    VXHD bool FromAngleToPosX(const V3 &RotateFrom, double *len_out = nullptr) {
+        if (V3(0, 0, 0) == RotateFrom) return false;
         double YoverX = RotateFrom.y / RotateFrom.x;
         double ZoverX = RotateFrom.z / RotateFrom.x;
         if (YoverX < VX3_SMALL_ANGLE_RAD && YoverX > -VX3_SMALL_ANGLE_RAD && ZoverX < VX3_SMALL_ANGLE_RAD && ZoverX > -VX3_SMALL_ANGLE_RAD) {
@@ -110,14 +113,21 @@ struct Q4 {
             y = 0.5 * ZoverX;
             z = -0.5 * YoverX;
             w = 1 + 0.5 * (-y * y - z * z);
-            return;
+            return false;
         }
         V3 RotFromNorm = RotateFrom;
-        RotFromNorm.NormalizeFast();
+        { // NormalizeFast(), keeping the length
+            const double l = sqrt(RotFromNorm.x * RotFromNorm.x + RotFromNorm.y * RotFromNorm.y + RotFromNorm.z * RotFromNorm.z);
+            if (len_out) *len_out = l;
+            if (l > 0) {
+                const double li = 1.0 / l;
+                RotFromNorm.x *= li; RotFromNorm.y *= li; RotFromNorm.z *= li;
+            }
+        }
         double theta = acos(RotFromNorm.x);
         if (theta > VX3_Q_PI - VX3_DISCARD_ANGLE_RAD) {
             w = 0; x = 0; y = 1; z = 0;
-            return;
+            return true;
         }
         const double AxisMagInv = 1.0 / sqrt(RotFromNorm.z * RotFromNorm.z + RotFromNorm.y * RotFromNorm.y);
         const double a = 0.5 * theta;
@@ -127,6 +137,7 @@ struct Q4 {
         x = 0;
         y = RotFromNorm.z * AxisMagInv * s;
         z = -RotFromNorm.y * AxisMagInv * s;
+        return true;
     }
     VXHD V3 RotateVec3D(const V3 &f) const {
         double fx = f.x, fy = f.y, fz = f.z;

@@ -210,9 +210,10 @@ __device__ __forceinline__ void link_stage_a(LinkRegs &L, const V3 &posN, const 
 
 __device__ __forceinline__ void link_stage_large(V3 &pos2, Q4 &angle1, Q4 &angle2, V3 &angle1v, double rest) {
     angle1 = Q4();
-    angle1.FromAngleToPosX(pos2);
+    double len;
+    const bool have_len = angle1.FromAngleToPosX(pos2, &len);
     angle2 = angle1 * angle2;
-    pos2 = V3(pos2.Length() - rest, 0, 0);
+    pos2 = V3((have_len ? len : pos2.Length()) - rest, 0, 0);
     angle1v = angle1.ToRotationVector();
 }
 
