@@ -84,7 +84,7 @@ __device__ __forceinline__ void stcg2(double *p, double a, double b) { __stcg(re
 __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, long long nsteps, int check_stop, int timing, PersistArgs A) {
     __shared__ int s_stop, s_div;
     __shared__ SimC sS;                                    // per-simulation constants on chip
-    __shared__ double sF[VX3_PERSIST_MAX_BLOCK][12];       // end forces of the CTA's links: Fneg, Mneg, Fpos, Mpos
+    __shared__ double sF[VX3_PERSIST_MAX_BLOCK][13];       // end forces of the CTA's links: Fneg, Mneg, Fpos, Mpos (+1: a 12-double record stride maps every 4th lane to the same banks)
     const int T = blockDim.x, tid = threadIdx.x;
     for (int i = tid; i < (int)(sizeof(SimC) / 4); i += T) reinterpret_cast<int *>(&sS)[i] = reinterpret_cast<const int *>(&D.simc[0])[i];
     __syncthreads();
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
     for (int k = 0; k < 12; k++) sF[tid][k] = 0.0;
 
     // ---- my voxel and my role in its step: 0 translate, 1 rotate, 2 temperature ----
-    __shared__ double sOrient[2][VX3_PERSIST_MAX_RO][4]; // orientation by step parity: the rotate role writes the new one while the translate role reads the old
+    __shared__ double sOrient[2][VX3_PERSIST_MAX_RO][5]; // orientation by step parity: the rotate role writes the new one while the translate role reads the old
     __shared__ float sTemp[VX3_PERSIST_MAX_RO];          // this step's temperature (temperature role -> translate role)
     __shared__ int sZero[2][VX3_PERSIST_MAX_RO];         // translate role -> rotate role, by step parity: on the floor in static friction, clear angMom (VX3_Voxel.cu:259-264)
     const int role = tid / A.ro, vk = tid - role * A.ro;
