@@ -306,7 +306,9 @@ __global__ void __launch_bounds__(VX3_PERSIST_MAX_BLOCK, 1) k_persistent(Dev D, 
             double *f = sF[tid];
             f[0] = o.forceNeg.x; f[1] = o.forceNeg.y; f[2] = o.forceNeg.z; f[3] = o.momentNeg.x; f[4] = o.momentNeg.y; f[5] = o.momentNeg.z;
             f[6] = o.forcePos.x; f[7] = o.forcePos.y; f[8] = o.forcePos.z; f[9] = o.momentPos.x; f[10] = o.momentPos.y; f[11] = o.momentPos.z;
-            if (!dup) { // the streaming path and the state read-back see the end forces in global memory
+            // a state read-back sees the end forces in global memory: only the last step's matter (any step's when a stop condition
+            // may end the launch) — 18 KB of stores per CTA and step that the release fence of the publish would otherwise wait for
+            if (!dup && (check_stop || s == nsteps - 1)) {
                 *D.lf(0, g) = make_double2(o.forceNeg.x, o.forceNeg.y);
                 *D.lf(1, g) = make_double2(o.forceNeg.z, o.momentNeg.x);
                 *D.lf(2, g) = make_double2(o.momentNeg.y, o.momentNeg.z);
