@@ -34,6 +34,25 @@ METRIC = "voxel-steps/sec"
 UNIT = "voxel-steps/s"
 
 
+# stdout carries exactly ONE line, the JSON result: native libraries write banners to file descriptor 1 (NCCL prints its version
+# there under NCCL_DEBUG=VERSION/WARN), so descriptor 1 is pointed at stderr for the whole run and the line goes to a saved copy
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -230,7 +249,7 @@ def run_decomposed(args, lib, built, label, rank, local_rank, world):
                              "kernel_ms": {k: round(v[0], 4) for k, v in stats.items()}, "kernel_launches": {k: v[1] for k, v in stats.items()}},
                 "hbm_roofline_equiv_frac": value * b_alg / (peak * 1e9 * world), "cpu_baseline": None, "clocks": clocks,
                 "gpu_launches": int(cnt[0]), "e2e": None}
-        print(json.dumps(line))
+        emit(line)
     body.batch.close()
     for b, _ in built:
         lib.vx3_builder_destroy(b)
@@ -254,6 +273,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank, local_rank, world = env_rank()
     K, Wm = args.steps, max(args.warmup, 0)
     graft.load_package()
@@ -265,7 +285,7 @@ def main():
             return 0
         base = reference_cpu_throughput(specs[0], max(5.0, args.cpu_seconds))
         if base is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (reference sources are not on this box)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref is not built (reference sources are not on this box)"})
             return 0
         line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": Wm,
                 "ms_per_step": 1e3 * base["seconds"] / base["steps"] * args.sim_steps, "higher_is_better": True, "scaling": "weak",
@@ -273,7 +293,7 @@ def main():
                 "config": {"workload": label, "sim_steps_per_step": args.sim_steps, "note": "CPU reference (src/old) has no per-voxel phase actuation"},
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -433,7 +453,7 @@ def main():
             ev = float(nvox) * S * e2e["steps"] * world / e2e_max
             line["e2e"] = {"value": ev, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "steps": e2e["steps"], "what": "vx3_batch_create from host arrays + vx3_batch_step + vx3_batch_results/positions + destroy per step"}
-        print(json.dumps(line))
+        emit(line)
     batch.close()
     for b, _ in built:
         lib.vx3_builder_destroy(b)
