@@ -75,8 +75,13 @@ class ClockSampler:
         self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def begin(self):
-        """The timed region starts here: only samples from now on count (the process is started before the warm-up, so
-        that it is already streaming — nvidia-smi takes a few hundred ms to come up, longer than a short timed region)."""
+        """The timed region starts here: only samples from now on count.  The process is started before the warm-up and this
+        call waits for its first sample: nvidia-smi takes a few hundred ms to come up, and while it initialises it holds
+        driver locks that stall kernel launches — inside a short timed region that nearly doubled the measured step time."""
+        if self.proc:
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.02)
         self.first = len(self.lines)
 
     def start(self):
