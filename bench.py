@@ -85,9 +85,13 @@ class ClockSampler:
         self.first = len(self.lines)
 
     def start(self):
+        # one sampler per job (rank 0's GPU): every nvidia-smi query takes driver locks that stall kernel launches on the whole
+        # box — eight samplers at 100 ms cost the launch-heavy config 3 run 13 % at 8 GPUs
+        if env_rank()[0] != 0:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -99,7 +103,7 @@ class ClockSampler:
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable" if env_rank()[0] == 0 else "sampled on rank 0"]}
         if len(self.lines) <= self.first:  # a timed region shorter than the sampling period: take the sample that ends it
             t0 = time.perf_counter()
             while len(self.lines) <= self.first and time.perf_counter() - t0 < 0.5:
