@@ -83,6 +83,25 @@ const double DISCARD_ANGLE_RAD = 1e-7;
 const double SMALL_ANGLE_RAD = 1.732e-2;
 const double SLTHRESH_ACOS2SQRT = 2.4e-3;
 
+// ---- libm error model (test hook, vx3o_set_libm_jitter): the GPU's libdevice sin / cos / acos are within 1 ulp of the
+// correctly rounded result, glibc's too, but not identically rounded.  With a non-zero seed every sin / cos / acos result
+// of the physics path is moved by -1, 0 or +1 ulp at (seeded) random: running a few such replicas next to the exact one
+// gives the envelope inside which ANY 1-ulp libm's trajectory must lie — the yardstick of the GPU tolerance gates.
+static unsigned long long g_libm_jitter = 0; // 0 = off
+static inline double jitter_ulp(double v) {
+    if (!g_libm_jitter) return v;
+    g_libm_jitter += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = g_libm_jitter;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const unsigned r = (unsigned)(z >> 33) % 3u;
+    return r == 0 ? v : nextafter(v, r == 1 ? INFINITY : -INFINITY);
+}
+static inline double m_sin(double x) { return jitter_ulp(sin(x)); }
+static inline double m_cos(double x) { return jitter_ulp(cos(x)); }
+static inline double m_acos(double x) { return jitter_ulp(acos(x)); }
+
 struct Q4 {
     double w = 1, x = 0, y = 0, z = 0;
     Q4() {}
@@ -93,13 +112,13 @@ struct Q4 {
                   w * f.y - x * f.z + y * f.w + z * f.x, w * f.z + x * f.y - y * f.x + z * f.w);
     }
     Q4 Conjugate() const { return Q4(w, -x, -y, -z); }
-    double Angle() const { return 2.0 * acos(w > 1 ? 1 : w); }
+    double Angle() const { return 2.0 * m_acos(w > 1 ? 1 : w); }
     double AngleDegrees() const { return Angle() * 57.29577951308232; }
     V3 ToRotationVector() const { // VX3_Quat3D.h:344-359
         if (w >= 1.0 || w <= -1.0) return V3(0, 0, 0);
         double squareLength = 1.0 - w * w;
         if (squareLength < SLTHRESH_ACOS2SQRT) return V3(x, y, z) * 2.0 * sqrt((2 - 2 * w) / squareLength);
-        else return V3(x, y, z) * 2.0 * acos(w) / sqrt(squareLength);
+        else return V3(x, y, z) * 2.0 * m_acos(w) / sqrt(squareLength);
     }
     void FromRotationVector(const V3 &VecIn) { // VX3_Quat3D.h:361-377
         V3 theta = VecIn / 2;
@@ -109,8 +128,8 @@ struct Q4 {
             s = 1.0 - thetaMag2 / 6.0;
         } else {
             double thetaMag = sqrt(thetaMag2);
-            w = cos(thetaMag);
-            s = sin(thetaMag) / thetaMag;
+            w = m_cos(thetaMag);
+            s = m_sin(thetaMag) / thetaMag;
         }
         x = theta.x * s;
         y = theta.y * s;
@@ -129,15 +148,15 @@ struct Q4 {
         }
         V3 RotFromNorm = RotateFrom;
         RotFromNorm.NormalizeFast();
-        double theta = acos(RotFromNorm.x);
+        double theta = m_acos(RotFromNorm.x);
         if (theta > Q_PI - DISCARD_ANGLE_RAD) {
             w = 0; x = 0; y = 1; z = 0;
             return;
         }
         const double AxisMagInv = 1.0 / sqrt(RotFromNorm.z * RotFromNorm.z + RotFromNorm.y * RotFromNorm.y);
         const double a = 0.5 * theta;
-        const double s = sin(a);
-        w = cos(a);
+        const double s = m_sin(a);
+        w = m_cos(a);
         x = 0;
         y = RotFromNorm.z * AxisMagInv * s;
         z = -RotFromNorm.y * AxisMagInv * s;
@@ -754,7 +773,7 @@ struct vx3o_sim {
             if (v.removed) continue;
             if (m.m.thermal_on_after_s > currentTime) continue;
             if (m.m.fixed) continue;
-            double currentTemperature = opt.temp_amplitude * sin(2 * 3.1415926f * (currentTime / opt.temp_period + v.phaseOffset));
+            double currentTemperature = opt.temp_amplitude * m_sin(2 * 3.1415926f * (currentTime / opt.temp_period + v.phaseOffset));
             if (!opt.enable_expansion) {
                 if (currentTemperature > 0) currentTemperature = 0;
             }
@@ -1328,6 +1347,9 @@ int vx3o_surface(vx3o_sim *s, int *out, int cap) {
     for (int i = 0; i < n && i < cap; i++) out[i] = s->surface[i];
     return n;
 }
+
+// libm error model: seed != 0 moves every sin / cos / acos result of the physics path by -1 / 0 / +1 ulp (see jitter_ulp); 0 = exact
+void vx3o_set_libm_jitter(unsigned long long seed) { g_libm_jitter = seed; }
 
 double vx3o_eval(const vx3_token *tok, int n, const double *vars9) {
     std::vector<vx3_token> p(tok, tok + n);

@@ -1,0 +1,121 @@
+"""GPU parity over every named scenario of tests/scenarios.py — the same models on which the CPU oracle is pinned bit for
+bit to the reference's own VX3 code (tests/test_oracle_vs_vx3ref.py, fixtures tests/golden/vx3_*.json) — through the C ABI.
+
+Gates (stated once, used everywhere):
+  * integer state — link topology (ends, axis, material), voxel link slots, voxel / link flags incl. the isNewLink
+    countdown, collision and event counts, signal state — BIT-EXACT;
+  * floating-point state — element-wise |gpu - oracle| <= max(1e-9 * max|oracle|, 8 x libm envelope): the product is built
+    with -fmad=false, so the only arithmetic that may differ from the oracle's is libdevice vs glibc sin / cos / acos
+    (each within 1 ulp, not identically rounded); the envelope is the oracle's own spread when exactly those results are
+    jittered by +-1 ulp (util.libm_envelope).  Kinematic state passes the flat 1e-9 bar on the small scenarios; the envelope
+    term matters for momenta / link forces (differences of large terms) and for chaotic scenarios (hundreds of attach /
+    detach events).
+"""
+import numpy as np
+import pytest
+
+import util
+from scenarios import SCENARIOS, scenario
+from util import KIN, LINKF, LINKS, EngineBatch, OracleSim, gate_within_envelope, libm_envelope
+from voxcraft_sim_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+INT_KEYS = ["vox_flags", "vox_links", "link_vneg", "link_vpos", "link_axis", "link_flags"]
+FLOAT_KEYS = KIN + LINKF + LINKS + ["link_rest_length"]
+F32_EXACTISH = ["link_strain", "link_max_strain", "link_strain_offset", "link_stress", "temp"]
+
+
+def run_scenario(name, persistent=True, fused=False):
+    sc = scenario(name)
+    spec = sc["spec"]()
+    lib = util.load_engine()
+    b, d = spec.build(lib)
+    if sc["link_capacity"]:
+        d.contents.link_capacity = sc["link_capacity"]
+    try:
+        orc0 = OracleSim(d)
+        dt = float(np.float32(0.9 * orc0.recommended_dt())) if sc["dt"] == "fixed" else -1.0
+        checkpoints = list(range(sc["chunk"], sc["steps"] + 1, sc["chunk"]))
+        exact, envs = libm_envelope(d, sc["steps"], dt, checkpoints, keys=FLOAT_KEYS + F32_EXACTISH)
+        eng = EngineBatch([d])
+        eng.set_profiling(False, use_persistent=persistent)
+        done, worst, states = 0, {}, []
+        link_cap = sc["link_capacity"] or None
+        orc = OracleSim(d)
+        for c, so, env in zip(checkpoints, exact, envs):
+            eng.step(c - done, dt) if dt > 0 else eng.step(c - done)
+            assert orc.step(c - done, dt) == c - done
+            done = c
+            se = eng.state(0, link_cap=link_cap)
+            what = "%s after %d steps" % (name, c)
+            for k in INT_KEYS:
+                np.testing.assert_array_equal(se[k], so[k], err_msg="%s: %s" % (what, k))
+            np.testing.assert_array_equal(se["signal"], so["signal"], err_msg=what + ": signal state")
+            w = gate_within_envelope(se, so, env, FLOAT_KEYS, what)
+            # strain / stress / temperature are STORED as float: a 1e-16 relative difference in the double they are rounded from
+            # can flip the rounding, so their floor is one float ulp at the array's scale
+            w.update(gate_within_envelope(se, so, env, F32_EXACTISH, what, rel_floor=1.2e-7))
+            for k, v in w.items():
+                worst[k] = max(worst.get(k, 0.0), v)
+            re, ro = eng.results()[0], orc.result()
+            assert (re.steps, re.num_links, re.collision_count, re.num_close_pairs, re.num_measured_voxel) == \
+                   (ro.steps, ro.num_links, ro.collision_count, ro.num_close_pairs, ro.num_measured_voxel), what
+            np.testing.assert_allclose([re.current_time, re.target_closeness, re.recent_angle], [ro.current_time, ro.target_closeness, ro.recent_angle],
+                                       rtol=1e-9, atol=1e-12, err_msg=what)
+            np.testing.assert_allclose(list(re.current_com) + list(re.initial_com), list(ro.current_com) + list(ro.initial_com), rtol=1e-9, atol=1e-15,
+                                       err_msg=what)
+            np.testing.assert_allclose(re.fitness_score, ro.fitness_score, rtol=1e-9, atol=1e-15, err_msg=what)
+            states.append(se)
+        eng.close()
+        print(name, "worst err/tol:", {k: "%.2g" % v for k, v in sorted(worst.items()) if v > 0.05})
+        return states
+    finally:
+        lib.vx3_builder_destroy(b)
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_scenario_matches_oracle(name):
+    run_scenario(name)
+
+
+FIXED_TOPOLOGY = ["act333", "ragged", "cantilever", "forcefield", "bilinear", "bilinear_fail", "datamat", "datamat_fail", "linfail",
+                  "poisson_lin", "poisson_bilinear", "poisson_data"]
+BITS = KIN + LINKF + LINKS + ["link_flags", "vox_flags", "temp", "link_rest_length", "link_strain", "link_max_strain", "link_strain_offset", "link_stress"]
+
+
+@pytest.mark.parametrize("name", FIXED_TOPOLOGY)
+def test_three_step_paths_are_bit_identical(name, monkeypatch):
+    """Persistent on-chip kernel, two-pass streaming kernels and the fused block step run the same physics code: identical
+    bits on every scenario with a fixed link topology, nonlinear materials and nu != 0 included."""
+    a = run_scenario(name, persistent=True)
+    b = run_scenario(name, persistent=False)
+    monkeypatch.setenv("VX3_FUSED", "1")
+    c = run_scenario(name, persistent=False)
+    for sa, sb, sc_ in zip(a, b, c):
+        util.assert_bit_equal(sa, sb, BITS, name + ": persistent vs streaming")
+        util.assert_bit_equal(sc_, sb, [k for k in BITS if k not in LINKF], name + ": fused vs streaming")
+
+
+def test_fitness_program_with_all_24_operators():
+    """vx3_batch_run with a fitness formula that uses every math-tree operator (VX3_MathTree.h:50-192) and every variable,
+    against the oracle (whose evaluator is pinned bit for bit on VX3_MathTree::eval)."""
+    from scenarios import closeness_spec
+    from test_oracle_vs_vx3ref import ALL_OPS_EXPR
+    spec = closeness_spec()
+    spec.set_program(abi.PROG_FITNESS, ALL_OPS_EXPR)
+    spec.set_program(abi.PROG_STOP, ("SUB", ("VAR", "t"), ("CONST", 0.03)))
+    lib = util.load_engine()
+    b, d = spec.build(lib)
+    try:
+        eng, orc = EngineBatch([d]), OracleSim(d)
+        eng.run()
+        orc.run()
+        re, ro = eng.results()[0], orc.result(refresh=False)
+        assert re.status == ro.status == abi.SIM_STOPPED and re.steps == ro.steps
+        assert ro.fitness_score == ro.fitness_score and abs(ro.fitness_score) > 1e-3
+        np.testing.assert_allclose(re.fitness_score, ro.fitness_score, rtol=1e-9)
+        assert re.num_close_pairs == ro.num_close_pairs > 0
+        eng.close()
+    finally:
+        lib.vx3_builder_destroy(b)

@@ -24,6 +24,17 @@ CASES = {
     "ragged": dict(n=(5, 4, 3), seed=5, actuated=False, holes=0.3, lift=1),
     "tower": dict(n=(2, 2, 6), seed=9, actuated=False),
     "static_temp": dict(n=(3, 2, 2), seed=13, actuated=False, static_temp=7.5),
+    # MatModel 2 / 3 next to a linear material: every pair goes through the springs-in-series blend (VX_MaterialLink.cpp:72-104);
+    # soft enough that the body's own weight + the drop drive links past the yield points (loading, unloading, reloading)
+    "nonlinear_mix": dict(n=(3, 3, 4), seed=17, actuated=False, lift=1, nonlinear=True),
+}
+# builder-only cases (the CPU library re-evaluates the transverse strains of a nu != 0 material every step, VX_Link.cpp:154;
+# VX3 freezes them, VX3_Link.cu:147-150, and so does the oracle — stepping with nu != 0 is pinned on the VX3 code instead,
+# tests/test_oracle_vs_vx3ref.py::poisson_*)
+BUILD_ONLY = {
+    "poisson_mix": dict(n=(3, 3, 3), seed=19, actuated=False, poisson=True),
+    "poisson_nonlinear": dict(n=(3, 3, 3), seed=23, actuated=False, poisson=True, nonlinear=True),
+    "poisson_off": dict(n=(2, 2, 2), seed=29, actuated=False, poisson=True, volume_effects=False),
 }
 
 
@@ -33,9 +44,18 @@ LINKMAT_UNSET = {"matid"}
 
 
 def make_spec(name):
-    kw = dict(CASES[name])
+    kw = dict(CASES[name] if name in CASES else BUILD_ONLY[name])
     st = kw.pop("static_temp", None)
+    nonlinear, poisson, volume = kw.pop("nonlinear", False), kw.pop("poisson", False), kw.pop("volume_effects", True)
     spec = cube_spec(name=name, **kw)
+    if nonlinear:
+        spec.materials[1].update(mat_model=2, elastic_mod=4e4, plastic_mod=8e3, yield_stress=12.0, fail_stress=400.0)
+        spec.materials[2].update(mat_model=3, elastic_mod=0.0, strain_data=[0.0, 0.0004, 0.01, 0.05, 0.3], stress_data=[0.0, 12.0, 150.0, 300.0, 500.0])
+        spec.materials[0].update(elastic_mod=3e4)
+    if poisson:
+        for m, nu in zip(spec.materials, (0.3, 0.2, 0.0)):
+            m["poissons_ratio"] = nu
+        spec.set_env(volume_effects_enabled=int(volume))
     if st is not None:  # constant (non-varying) temperature: applied once at Import by both libraries
         spec.set_env(temp_enabled=1, vary_temp_enabled=0, temp_amplitude=st, temp_base=25.0)
     return spec
@@ -50,7 +70,7 @@ def demo_spec():
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built (no reference tree on this box)")
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(BUILD_ONLY))
 def test_builder_equals_reference_import(name):
     spec = make_spec(name)
     lib = util.load_engine()

@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "libvx3_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libvxref.so")
 REF_OMP_SO = os.path.join(ROOT, "oracle", "_ref", "libvxref_omp.so")
+REF_VX3_SO = os.path.join(ROOT, "oracle", "_ref", "libvxref_vx3.so")  # the reference's VX3 device sources compiled for the host
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 REFERENCE_TREE = "/root/reference"
 
@@ -44,6 +45,7 @@ def load_oracle():
         lib.vx3o_surface.argtypes = [vp, P(C.c_int), C.c_int]
         lib.vx3o_eval.argtypes = [P(abi.Token), C.c_int, P(C.c_double)]
         lib.vx3o_eval.restype = C.c_double
+        lib.vx3o_set_libm_jitter.argtypes = [C.c_ulonglong]
         _libs["oracle"] = lib
     return _libs["oracle"]
 
@@ -88,34 +90,95 @@ def ref_load_spec(spec, omp=False):
     return lib, h
 
 
+def have_ref_vx3():
+    return os.path.exists(REF_VX3_SO)
+
+
+def load_ref_vx3():
+    if "ref_vx3" not in _libs:
+        lib = C.CDLL(REF_VX3_SO)
+        vp = C.c_void_p
+        lib.vx3ref_create.argtypes = [C.c_char_p, P(abi.ModelDesc)]
+        lib.vx3ref_create.restype = vp
+        lib.vx3ref_ok.argtypes = [vp]
+        lib.vx3ref_message.argtypes = [vp]
+        lib.vx3ref_message.restype = C.c_char_p
+        lib.vx3ref_init.argtypes = [vp]
+        lib.vx3ref_recommended_dt.argtypes = [vp]
+        lib.vx3ref_recommended_dt.restype = C.c_double
+        lib.vx3ref_step.argtypes = [vp, C.c_long, C.c_float]
+        lib.vx3ref_step.restype = C.c_long
+        lib.vx3ref_run_simulation.argtypes = [vp]
+        lib.vx3ref_run_simulation.restype = C.c_long
+        lib.vx3ref_output.argtypes = [vp]
+        lib.vx3ref_output.restype = C.c_char_p
+        lib.vx3ref_eval.argtypes = [P(abi.Token), C.c_int, P(C.c_double)]
+        lib.vx3ref_eval.restype = C.c_double
+        lib.vx3ref_counts.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int)]
+        lib.vx3ref_surface.argtypes = [vp, P(C.c_int), C.c_int]
+        lib.vx3ref_result.argtypes = [vp, P(abi.Result), C.c_int]
+        lib.vx3ref_state.argtypes = [vp, P(abi.StateView)]
+        lib.vx3ref_voxel_extras.argtypes = [vp, P(C.c_int32), P(C.c_int32)]
+        _libs["ref_vx3"] = lib
+    return _libs["ref_vx3"]
+
+
+class Vx3RefSim:
+    """The reference's own VX3 step loop (src/VX3/*.cu compiled for the host, oracle/ref_vx3) on a ModelSpec: the VXA text
+    goes through CVX_Sim, the VX3-only settings come from the flat model `desc` (see vx3ref_harness.cpp)."""
+
+    def __init__(self, spec, desc):
+        self.lib = load_ref_vx3()
+        with tempfile.NamedTemporaryFile("w", suffix=".vxa", delete=False) as f:
+            f.write(spec.to_vxa())
+            path = f.name
+        self.h = self.lib.vx3ref_create(path.encode(), desc)
+        os.unlink(path)
+        assert self.lib.vx3ref_ok(self.h), self.lib.vx3ref_message(self.h)
+
+    def recommended_dt(self):
+        return self.lib.vx3ref_recommended_dt(self.h)
+
+    def step(self, k, dt=-1.0):
+        return self.lib.vx3ref_step(self.h, k, dt)
+
+    def run_simulation(self):
+        """CUDA_Simulation itself; returns what it printed (history frames included)."""
+        self.lib.vx3ref_run_simulation(self.h)
+        return self.lib.vx3ref_output(self.h)
+
+    def counts(self):
+        nv, nl, ns, nm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.vx3ref_counts(self.h, nv, nl, ns, nm)
+        return dict(n_voxels=nv.value, n_links=nl.value, n_surface=ns.value, n_link_mats=nm.value)
+
+    def surface(self):
+        c = self.counts()
+        out = (C.c_int * max(c["n_surface"], 1))()
+        n = self.lib.vx3ref_surface(self.h, out, c["n_surface"])
+        return list(out[:n])
+
+    def state(self):
+        c = self.counts()
+        sb = StateBuffers(c["n_voxels"], c["n_links"])
+        assert self.lib.vx3ref_state(self.h, C.byref(sb.view)) == 0
+        return sb.result()
+
+    def result(self, refresh=True):
+        r = abi.Result()
+        self.lib.vx3ref_result(self.h, C.byref(r), int(refresh))
+        return r
+
+    def voxel_extras(self):
+        n = self.counts()["n_voxels"]
+        ea, rm = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.lib.vx3ref_voxel_extras(self.h, ea.ctypes.data_as(P(C.c_int32)), rm.ctypes.data_as(P(C.c_int32)))
+        return ea, rm
+
+
 # ------------------------------------------------------------------ model factories
 from voxcraft_sim_b200.workloads import add_abc_materials, splitmix64  # noqa: E402
-
-
-def cube_spec(n=(3, 3, 3), seed=42, actuated=True, lift=0, holes=0.0, name="cube", collisions=0, damping=(1.0, 0.8, 0.01)):
-    """Multi-material (A/B/C) body of nx*ny*nz voxels, `lift` empty layers below, optional random holes."""
-    nx, ny, nz = n
-    spec = ModelSpec(0.01, name)
-    add_abc_materials(spec)
-    spec.set_env(bond_damping_z=damping[0], col_damping_z=damping[1], slow_damping_z=damping[2],
-                 temp_enabled=1, vary_temp_enabled=int(actuated), temp_amplitude=20.0 if actuated else 0.0, temp_period=0.2)
-    spec.set_options(enable_collision=collisions)
-    r = splitmix64(seed)
-    r2 = splitmix64(seed + 1)
-    r3 = splitmix64(seed + 2)
-    st = np.zeros((nz + lift, ny, nx), np.uint8)
-    ph = np.zeros((nz + lift, ny, nx))
-    for z in range(nz):
-        for y in range(ny):
-            for x in range(nx):
-                m = 1 + r() % 3
-                p = (r2() >> 11) / float(1 << 53)
-                keep = ((r3() >> 11) / float(1 << 53)) >= holes
-                if keep:
-                    st[z + lift, y, x] = m
-                ph[z + lift, y, x] = p
-    spec.set_structure(st, phase_offset=ph if actuated else None)
-    return spec
+from scenarios import cube_spec  # noqa: E402,F401  (kept importable from util)
 
 
 # ------------------------------------------------------------------ runners
@@ -198,6 +261,74 @@ def max_rel_err(a, b, scale=None):
         return 0.0
     s = scale if scale is not None else max(np.max(np.abs(b)), 1e-300)
     return float(np.max(np.abs(a - b)) / s)
+
+
+def libm_envelope(desc_ptr, steps, dt, checkpoints=None, seeds=(11, 23, 37), keys=None):
+    """Element-wise spread of the oracle's state under a 1-ulp libm error model (vx3o_set_libm_jitter): the exact run plus
+    len(seeds) replicas whose sin / cos / acos results are moved by -1 / 0 / +1 ulp at random.  Returns
+    (exact_states, envelopes): one dict per checkpoint (steps, cumulative), envelope[k] = max over replicas of
+    |replica - exact| (None where a replica's array shape differs, i.e. the topology itself is sensitive at the ulp level)."""
+    lib = load_oracle()
+    checkpoints = checkpoints or [steps]
+    keys = keys or (KIN + LINKF + LINKS)
+
+    def run(seed):
+        lib.vx3o_set_libm_jitter(seed)
+        try:
+            o = OracleSim(desc_ptr)
+            out, done = [], 0
+            for c in checkpoints:
+                assert o.step(c - done, dt) == c - done
+                done = c
+                out.append(o.state())
+            return out
+        finally:
+            lib.vx3o_set_libm_jitter(0)
+    exact = run(0)
+    reps = [run(s) for s in seeds]
+    envs = []
+    for i, ex in enumerate(exact):
+        env = {}
+        for k in keys:
+            a = np.asarray(ex[k], np.float64)
+            e = np.zeros_like(a)
+            for r in reps:
+                b = np.asarray(r[i][k], np.float64)
+                if b.shape != a.shape:
+                    e = None
+                    break
+                e = np.maximum(e, np.abs(b - a))
+            env[k] = e
+        envs.append(env)
+    return exact, envs
+
+
+def gate_within_envelope(se, so, env, keys, what="", factor=8.0, rel_floor=1e-9):
+    """The tolerance gate of the GPU parity tests, element-wise:  |gpu - oracle| <= max(rel_floor * scale, factor * env)
+    where scale = max |oracle| over the array (so zeros are handled) and env is the element's spread under the 1-ulp libm
+    error model (libm_envelope), smoothed by the array's median spread.  rel_floor = 1e-9 is BASELINE.md's bar; the
+    envelope term only ever loosens it where a 1-ulp difference in sin / cos / acos PROVABLY moves the oracle itself by
+    more than that (momenta and link forces are differences of large terms).  Returns the worst ratio err / tol per key."""
+    worst = {}
+    for k in keys:
+        a, b = np.asarray(se[k], np.float64), np.asarray(so[k], np.float64)
+        assert a.shape == b.shape, "%s: %s shape %s vs %s" % (what, k, a.shape, b.shape)
+        if a.size == 0:
+            continue
+        scale = max(np.max(np.abs(b)), 1e-300)
+        tol = np.full(a.shape, rel_floor * scale)
+        if env is not None and env.get(k) is not None:
+            e = env[k]
+            tol = np.maximum(tol, factor * np.maximum(e, np.median(e)))
+        err = np.abs(a - b)
+        ratio = float(np.max(err / tol))
+        worst[k] = ratio
+        if ratio > 1.0:
+            i = np.unravel_index(np.argmax(err / tol), a.shape)
+            raise AssertionError("%s: %s[%s] = %r vs oracle %r: |diff| %.3e > tol %.3e (1e-9 * scale = %.3e, libm envelope there %.3e)" %
+                                 (what, k, i, a[i], b[i], err[i], tol[i], rel_floor * scale,
+                                  0.0 if env is None or env.get(k) is None else env[k][i]))
+    return worst
 
 
 def compare_states(sa, sb, keys, tol, what=""):

@@ -4,8 +4,9 @@ Outputs (git-ignored, shipped to the GPU box by gpurun):
   voxcraft-sim_b200/lib/libvx3_b200.so      the product: compiled with -fmad=false so every fp64/fp32 operation rounds
                                             like the reference's x86-64 build (which does not contract) — the
                                             parity-grade build, and the one bench.py measures
-  voxcraft-sim_b200/lib/libvx3_b200_fma.so  same sources with FMA contraction on (nvcc default): kept to measure
-                                            what contraction would buy; NOT parity-grade
+  voxcraft-sim_b200/lib/libvx3_b200_fma.so  (only with `build.py --fma`) same sources with FMA contraction on (nvcc default): an
+                                            experiment to measure what contraction would buy; NOT parity-grade,
+                                            not built, loaded or tested by default
 """
 import os
 import shutil
@@ -104,18 +105,21 @@ def build_oracle(force=False, verbose=False):
             _run(["make", "-C", odir, "-j8", "ref_omp", "REF=" + ref], verbose)
         except RuntimeError:
             print("note: OpenMP reference build unavailable (no libgomp for this g++)")
+        # the reference's VX3 device sources compiled for the host (oracle/ref_vx3): pins the oracle's VX3-only behaviour
+        _run(["make", "-C", odir, "-j8", "ref_vx3", "REF=" + ref], verbose)
     return os.path.join(odir, "libvx3_oracle.so")
 
 
-def build_all(force=False, verbose=False):
+def build_all(force=False, verbose=False, fma=False):
     a = build_lib(fma=False, force=force, verbose=verbose)
-    b = build_lib(fma=True, force=force, verbose=verbose)
     build_exes(force=force, verbose=verbose)
-    return a, b
+    if fma:
+        return a, build_lib(fma=True, force=force, verbose=verbose)
+    return (a,)
 
 
 if __name__ == "__main__":
     v = "-v" in sys.argv
     f = "-f" in sys.argv
-    print(build_all(force=f, verbose=v))
+    print(build_all(force=f, verbose=v, fma="--fma" in sys.argv))
     print(build_oracle(verbose=v))

@@ -18,6 +18,7 @@
 #include "../../../include/vx3_abi.h"
 #include "../../../include/vx3_model.h"
 #include "vx3_kernels.cuh"
+#include "../host/vx3_materials.h"
 #include "vx3_persistent.cuh"
 #include "vx3_halo.cuh"
 #include "vx3_fused.cuh"
@@ -334,45 +335,21 @@ struct vx3_batch {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop);
 
-// VX3_MaterialLink(mat, mat) for attach-created links between two voxels of the same material:
-// updateAll (src/VX3/VX3_MaterialLink.cu:53-127; only the linear model can be blended on the device,
-// VX3_Material.cu:234) + updateDerived (:129-149).
-static void make_self_linkmat(const vx3_voxel_material &a, LinkMatC &o, std::vector<float> &sd, std::vector<float> &ss) {
-    const vx3_voxel_material &b = a;
-    memset(&o, 0, sizeof(o));
-    const double nomSize = 0.5 * (a.nomSize + b.nomSize);
-    float stressFail, f1 = a.sigmaFail, f2 = b.sigmaFail;
-    if (f1 == -1.0f) stressFail = f2;
-    else if (f2 == -1.0f) stressFail = f1;
-    else stressFail = f1 < f2 ? f1 : f2;
-    const float youngsModulus = 2.0f * a.E * b.E / (a.E + b.E);
-    float tmpfailureStress = stressFail;
-    if (tmpfailureStress == -1) tmpfailureStress = 1000000;
-    const float tmpfailStrain = tmpfailureStress / youngsModulus;
-    sd = {0.0f, 0.0f, tmpfailStrain}; // device layout: duplicated leading 0 (VX3_Material.cu:463-477)
-    ss = {0.0f, 0.0f, tmpfailureStress};
-    o.linear = 1;
-    o.E = youngsModulus;
-    o.epsilonFail = (stressFail == -1) ? -1 : tmpfailStrain;
-    if (a.nu == 0 && b.nu == 0) o.nu = 0;
-    else {
-        float tmpEHat = 2 * a.eHat * b.eHat / (a.eHat + b.eHat);
-        float tmpE = o.E;
-        float c2 = (tmpEHat - tmpE) / (2 * tmpEHat) + 0.0625;
-        o.nu = sqrt(c2) - 0.25;
+// Device record of a link material (the strain/stress points in the device layout: syncVectors pushes a 0 in front of the
+// host data, which itself starts with 0 — VX3_Material.cu:463-477).
+static void device_linkmat(const vx3_link_material &in, LinkMatC &lm, std::vector<float> &sd, std::vector<float> &ss) {
+    memset(&lm, 0, sizeof(lm));
+    lm.E = in.m.E; lm.nu = in.m.nu; lm.eHat = in.m.eHat; lm.epsilonFail = in.m.epsilonFail;
+    lm.a1 = in.a1; lm.a2 = in.a2; lm.b1 = in.b1; lm.b2 = in.b2; lm.b3 = in.b3;
+    lm.sqA1 = in.sqA1; lm.sqA2xIp = in.sqA2xIp; lm.sqB1 = in.sqB1; lm.sqB2xFMp = in.sqB2xFMp; lm.sqB3xIp = in.sqB3xIp;
+    lm.linear = in.m.linear;
+    sd.assign(1, 0.0f);
+    ss.assign(1, 0.0f);
+    for (int k = 0; k < in.m.n_data; k++) {
+        sd.push_back(in.m.strain_data ? in.m.strain_data[k] : 0.0f);
+        ss.push_back(in.m.stress_data ? in.m.stress_data[k] : 0.0f);
     }
-    o.eHat = o.E / ((1 - 2 * o.nu) * (1 + o.nu));
-    const float L = (float)nomSize, E = o.E, nu = o.nu;
-    o.a1 = E * L;
-    o.a2 = E * L * L * L / (12.0f * (1 + nu));
-    o.b1 = E * L;
-    o.b2 = E * L * L / 2.0f;
-    o.b3 = E * L * L * L / 6.0f;
-    o.sqA1 = sqrtf(o.a1);
-    o.sqA2xIp = sqrtf(o.a2 * L * L / 6.0f);
-    o.sqB1 = sqrtf(o.b1);
-    o.sqB2xFMp = sqrtf(o.b2 * L / 2.0f);
-    o.sqB3xIp = sqrtf(o.b3 * L * L / 6.0f);
+    while (sd.size() < 2) { sd.push_back(0.0f); ss.push_back(0.0f); }
 }
 
 static std::string blob(const void *p, size_t n) { return std::string((const char *)p, n); }
@@ -641,19 +618,9 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         std::vector<int> &lg = b->lmat_global[s];
         lg.resize(m.n_link_mats);
         for (int i = 0; i < m.n_link_mats; i++) {
-            const vx3_link_material &in = m.link_mats[i];
             LinkMatC lm;
-            memset(&lm, 0, sizeof(lm));
-            lm.E = in.m.E; lm.nu = in.m.nu; lm.eHat = in.m.eHat; lm.epsilonFail = in.m.epsilonFail;
-            lm.a1 = in.a1; lm.a2 = in.a2; lm.b1 = in.b1; lm.b2 = in.b2; lm.b3 = in.b3;
-            lm.sqA1 = in.sqA1; lm.sqA2xIp = in.sqA2xIp; lm.sqB1 = in.sqB1; lm.sqB2xFMp = in.sqB2xFMp; lm.sqB3xIp = in.sqB3xIp;
-            lm.linear = in.m.linear;
-            std::vector<float> sd{0.0f}, ss{0.0f}; // syncVectors pushes a 0, then the host data (which starts with 0)
-            for (int k = 0; k < in.m.n_data; k++) {
-                sd.push_back(in.m.strain_data ? in.m.strain_data[k] : 0.0f);
-                ss.push_back(in.m.stress_data ? in.m.stress_data[k] : 0.0f);
-            }
-            while (sd.size() < 2) { sd.push_back(0.0f); ss.push_back(0.0f); }
+            std::vector<float> sd, ss;
+            device_linkmat(m.link_mats[i], lm, sd, ss);
             lg[i] = add_linkmat(lm, sd, ss);
         }
         std::vector<int> &vm_global = sb[s].vm_global;
@@ -690,10 +657,15 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 int found = -1;
                 for (int k = 0; k < m.n_link_mats && found < 0; k++)
                     if (m.link_mats[k].vox1_mat == i && m.link_mats[k].vox2_mat == i) found = lg[k];
-                if (found < 0) {
+                if (found < 0) { // VX3_MaterialLink(mat, mat) of an attach-created link (VX3_MaterialLink.cu:24-149): the same blend the
+                                 // host builder applies to the model's own links (csrc/host/vx3_materials.cpp)
+                    vx3_link_material self;
+                    std::vector<std::vector<float>> pool;
+                    pool.reserve(2);
+                    vx3::link_constants(in, in, i, i, &self, &pool);
                     LinkMatC lm;
                     std::vector<float> sd, ss;
-                    make_self_linkmat(in, lm, sd, ss);
+                    device_linkmat(self, lm, sd, ss);
                     found = add_linkmat(lm, sd, ss);
                 }
                 vm.self_lmat = found;

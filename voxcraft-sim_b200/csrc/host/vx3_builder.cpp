@@ -6,6 +6,8 @@
 #include "../../../include/vx3_model.h"
 #include "vx3_materials.h"
 
+#include <cfloat>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -37,8 +39,7 @@ struct vx3_builder {
 
     // ---- build outputs (own the memory referenced by `desc`) ----
     vx3_model_desc desc;
-    std::vector<VoxelMat> vmats;
-    std::vector<LinkMat> lmats;
+    std::vector<MaterialInput> vmats; // palette materials as configured (inputs of voxel_constants)
     std::vector<vx3_voxel_material> o_vmats;
     std::vector<vx3_link_material> o_lmats;
     std::vector<std::vector<float>> o_data; // strain/stress arrays kept alive
@@ -153,84 +154,55 @@ extern "C" int vx3_builder_set_external(vx3_builder *b, int voxel_index, const v
     return VX3_OK;
 }
 
-// CVX_Sim::CopyMat, src/VXA/VX_Sim.cpp:368-420
-static void copy_mat(const vx3_material_params &o, const std::vector<double> &sd, const std::vector<double> &ss, int matid,
-                     const vx3_env_params &env, VoxelMat &n) {
+// One palette entry -> the inputs of voxel_constants().  Same outcome as Vx.addMaterial() defaults (E = 1e6 Pa, rho = 1e3,
+// Voxelyze.h:88) overridden by CVX_Sim::CopyMat (src/VXA/VX_Sim.cpp:368-420): a model whose parameters fail validation
+// leaves the default law in place, like the reference's setters that return false.
+static MaterialInput palette_material(const vx3_material_params &o, const std::vector<double> &sd, const std::vector<double> &ss, int matid,
+                                      const vx3_env_params &env, float grav_mult) {
+    MaterialInput n;
+    StressLaw::hooke(1e6f, -1, &n.law);
+    n.grav_mult = grav_mult;
     n.matid = matid;
-    n.isPaceMaker = o.is_pacemaker != 0;
-    n.PaceMakerPeriod = o.pacemaker_period;
-    n.isElectricalActive = o.is_electrical_active != 0;
-    n.signalValueDecay = o.signal_value_decay;
-    n.signalTimeDelay = o.signal_time_delay;
-    n.inactivePeriod = o.inactive_period;
-    n.isMeasured = o.is_measured;
-    n.RemoveAfter = o.remove_after_s;
-    n.ThermalOnAfter = o.thermal_on_after_s;
-    n.CiliaOnAfter = o.cilia_on_after_s;
-    n.isTarget = o.is_target != 0;
+    n.is_pacemaker = o.is_pacemaker != 0;
+    n.pacemaker_period = o.pacemaker_period;
+    n.is_electrical_active = o.is_electrical_active != 0;
+    n.signal_value_decay = o.signal_value_decay;
+    n.signal_time_delay = o.signal_time_delay;
+    n.inactive_period = o.inactive_period;
+    n.is_measured = o.is_measured;
+    n.remove_after_s = o.remove_after_s;
+    n.thermal_on_after_s = o.thermal_on_after_s;
+    n.cilia_on_after_s = o.cilia_on_after_s;
+    n.is_target = o.is_target != 0;
     n.fixed = o.fixed != 0;
     n.sticky = o.sticky != 0;
-    n.Cilia = o.cilia;
+    n.cilia = o.cilia;
     // GetRedi() = (int)(Red*255), src/VXA/VX_Object.h:419-425
-    n.setColor((int)(o.red * 255), (int)(o.green * 255), (int)(o.blue * 255), (int)(o.alpha * 255));
+    n.r = clamp_colour((int)(o.red * 255)); n.g = clamp_colour((int)(o.green * 255));
+    n.b = clamp_colour((int)(o.blue * 255)); n.a = clamp_colour((int)(o.alpha * 255));
+    StressLaw law;
+    bool ok = false;
     switch (o.mat_model) {
-    case 0: n.setModelLinear((float)o.elastic_mod); break;
-    case 1: n.setModelLinear((float)o.elastic_mod, (float)o.fail_stress); break;
-    case 2: n.setModelBilinear((float)o.elastic_mod, (float)o.plastic_mod, (float)o.yield_stress, (float)o.fail_stress); break;
+    case 0: ok = StressLaw::hooke((float)o.elastic_mod, -1, &law); break;
+    case 1: ok = StressLaw::hooke((float)o.elastic_mod, (float)o.fail_stress, &law); break;
+    case 2: ok = StressLaw::bilinear((float)o.elastic_mod, (float)o.plastic_mod, (float)o.yield_stress, (float)o.fail_stress, &law); break;
     case 3: {
-        std::vector<float> tmpStress, tmpStrain;
-        for (size_t i = 0; i < sd.size(); i++) {
-            tmpStress.push_back((float)ss[i]);
-            tmpStrain.push_back((float)sd[i]);
-        }
-        if (!tmpStrain.empty()) n.setModel((int)tmpStrain.size(), &tmpStrain[0], &tmpStress[0]);
+        std::vector<float> eps(sd.begin(), sd.end()), sig(ss.begin(), ss.end());
+        ok = !eps.empty() && StressLaw::tabulated((int)eps.size(), eps.data(), sig.data(), &law);
         break;
     }
     }
-    n.setPoissonsRatio((float)o.poissons_ratio);
-    n.setDensity((float)o.density);
-    n.alphaCTE = (float)o.cte;
-    n.setStaticFriction((float)o.u_static);
-    n.setKineticFriction((float)o.u_dynamic);
-    n.setGlobalDamping((float)env.slow_damping_z);
-    n.setInternalDamping((float)env.bond_damping_z);
-    n.setCollisionDamping((float)env.col_damping_z);
-}
-
-static void export_vmat(const VoxelMat &m, vx3_voxel_material &o, std::vector<std::vector<float>> &keep) {
-    memset(&o, 0, sizeof(o));
-    o.matid = m.matid;
-    o.fixed = m.fixed;
-    o.sticky = m.sticky;
-    o.is_target = m.isTarget;
-    o.is_measured = m.isMeasured;
-    o.linear = m.linear;
-    o.is_pacemaker = m.isPaceMaker;
-    o.is_electrical_active = m.isElectricalActive;
-    o.r = m.r; o.g = m.g; o.b = m.b; o.a = m.a;
-    o.E = m.E; o.sigmaYield = m.sigmaYield; o.sigmaFail = m.sigmaFail;
-    o.epsilonYield = m.epsilonYield; o.epsilonFail = m.epsilonFail;
-    o.nu = m.nu; o.rho = m.rho; o.alphaCTE = m.alphaCTE; o.muStatic = m.muStatic; o.muKinetic = m.muKinetic;
-    o.zetaInternal = m.zetaInternal; o.zetaGlobal = m.zetaGlobal; o.zetaCollision = m.zetaCollision;
-    o.eHat = m.eHat;
-    o.gravMult = m.gravMult; o.mass = m.mass; o.massInverse = m.massInverse; o.sqrtMass = m.sqrtMass;
-    o.firstMoment = m.firstMoment; o.momentInertia = m.momentInertia; o.momentInertiaInverse = m.momentInertiaInverse;
-    o._2xSqMxExS = m.c2xSqMxExS; o._2xSqIxExSxSxS = m.c2xSqIxExSxSxS;
-    keep.push_back(m.strainData);
-    o.strain_data = keep.back().data();
-    keep.push_back(m.stressData);
-    o.stress_data = keep.back().data();
-    o.n_data = (int)m.strainData.size();
-    o.nomSize = m.nomSize;
-    for (int k = 0; k < 3; k++) o.extScale[k] = m.extScale[k];
-    o.cilia = m.Cilia;
-    o.pacemaker_period = m.PaceMakerPeriod;
-    o.signal_value_decay = m.signalValueDecay;
-    o.signal_time_delay = m.signalTimeDelay;
-    o.inactive_period = m.inactivePeriod;
-    o.remove_after_s = m.RemoveAfter;
-    o.thermal_on_after_s = m.ThermalOnAfter;
-    o.cilia_on_after_s = m.CiliaOnAfter;
+    if (ok) n.law = law;
+    n.nu = clamp_poisson((float)o.poissons_ratio);
+    n.rho = clamp_density((float)o.density);
+    n.cte = (float)o.cte;
+    auto nonneg = [](float v) { return v <= 0 ? 0.0f : v; };
+    n.mu_static = nonneg((float)o.u_static);
+    n.mu_kinetic = nonneg((float)o.u_dynamic);
+    n.zeta_global = nonneg((float)env.slow_damping_z);
+    n.zeta_internal = nonneg((float)env.bond_damping_z);
+    n.zeta_collision = nonneg((float)env.col_damping_z);
+    return n;
 }
 
 extern "C" const vx3_model_desc *vx3_builder_build(vx3_builder *b) {
@@ -250,18 +222,17 @@ extern "C" const vx3_model_desc *vx3_builder_build(vx3_builder *b) {
 
     // ---- materials (VX_Sim.cpp:72-86) then setVoxelSize (:89) ----
     b->vmats.clear();
-    std::vector<float> muMemory;
     for (int i = 0; i < nPal; i++) {
-        VoxelMat m(1e6f, 1e3f, 0.001); // Vx.addMaterial() defaults, Voxelyze.h:88 / DEFAULT_VOXEL_SIZE
-        m.gravMult = grav;             // addMaterial: pMat->setGravityMultiplier(grav)
-        copy_mat(b->palette[i], b->paletteStrain[i], b->paletteStress[i], i + 1, env, m);
-        m.setInternalDamping((float)env.bond_damping_z);
-        m.setGlobalDamping((float)env.slow_damping_z);
-        m.setCollisionDamping((float)env.col_damping_z);
-        muMemory.push_back((float)b->palette[i].poissons_ratio);
+        MaterialInput m = palette_material(b->palette[i], b->paletteStrain[i], b->paletteStress[i], i + 1, env, grav);
+        m.nom_size = voxSize <= 0 ? (double)FLT_MIN : voxSize; // Vx.setVoxelSize, VX_MaterialVoxel.cpp:82-87
+        // EnableVolumeEffects at the end of Import (VX_Sim.cpp:148,445-458): Poisson's ratio is forced to 0 unless the feature is on
+        if (!env.volume_effects_enabled) m.nu = 0.0f;
         b->vmats.push_back(m);
     }
-    for (auto &m : b->vmats) m.setNominalSize(voxSize);
+    b->o_data.clear();
+    b->o_data.reserve(2 * (size_t)nPal * (nPal + 2) + 4); // the records point into o_data: it must never reallocate
+    b->o_vmats.resize(nPal);
+    for (int i = 0; i < nPal; i++) voxel_constants(b->vmats[i], &b->o_vmats[i], &b->o_data);
 
     // ---- voxels + links in lattice scan order (VX_Sim.cpp:92-107; Voxelyze.cpp:439-461) ----
     const int nx = b->nx, ny = b->ny, nz = b->nz;
@@ -270,7 +241,7 @@ extern "C" const vx3_model_desc *vx3_builder_build(vx3_builder *b) {
     b->ix.clear(); b->iy.clear(); b->iz.clear(); b->vmat.clear(); b->vflags.clear(); b->vlinks.clear(); b->vext.clear();
     b->pos.clear(); b->orient.clear(); b->linmom.clear(); b->angmom.clear(); b->phase.clear(); b->bcil.clear(); b->scil.clear();
     b->temp.clear();
-    b->lneg.clear(); b->lpos.clear(); b->laxis.clear(); b->lmat.clear(); b->lmats.clear();
+    b->lneg.clear(); b->lpos.clear(); b->laxis.clear(); b->lmat.clear();
     std::vector<std::pair<int, int>> lmatKey; // (vox1Mat, vox2Mat) in creation order
 
     auto combined = [&](int m1, int m2) -> int { // Voxelyze.cpp:626-641
@@ -364,17 +335,10 @@ extern "C" const vx3_model_desc *vx3_builder_build(vx3_builder *b) {
         for (int v = 0; v < nV; v++) b->temp[v] = t;
     }
 
-    // ---- EnableVolumeEffects (VX_Sim.cpp:148,445-458): nu forced to 0 unless the feature is on ----
-    for (int i = 0; i < nPal; i++) b->vmats[i].setPoissonsRatio(env.volume_effects_enabled ? muMemory[i] : 0.0f);
-
-    // ---- link materials: final updateAll after every voxel material is final ----
-    b->lmats.resize(lmatKey.size());
-    for (size_t k = 0; k < lmatKey.size(); k++) {
-        LinkMat &lm = b->lmats[k];
-        lm.vox1 = lmatKey[k].first;
-        lm.vox2 = lmatKey[k].second;
-        lm.updateAll(b->vmats[lm.vox1], b->vmats[lm.vox2]);
-    }
+    // ---- link materials: one per distinct material pair, in creation order (Voxelyze.cpp:626-641) ----
+    b->o_lmats.resize(lmatKey.size());
+    for (size_t k = 0; k < lmatKey.size(); k++)
+        link_constants(b->o_vmats[lmatKey[k].first], b->o_vmats[lmatKey[k].second], lmatKey[k].first, lmatKey[k].second, &b->o_lmats[k], &b->o_data);
 
     // ---- link state = CVX_Link::reset() (VX_Link.cpp:56-70) ----
     b->lpos2.assign(3 * (size_t)nL, 0.0); b->la1v.assign(3 * (size_t)nL, 0.0); b->la2v.assign(3 * (size_t)nL, 0.0);
@@ -382,7 +346,7 @@ extern "C" const vx3_model_desc *vx3_builder_build(vx3_builder *b) {
     b->lflags.assign(nL, 0); b->lsmall.assign(nL, 1);
     b->lrest.resize(nL); b->larea.resize(nL); b->ltsum.assign(nL, 0.0f); b->lratio.resize(nL);
     for (int l = 0; l < nL; l++) {
-        const VoxelMat &mn = b->vmats[b->vmat[b->lneg[l]]], &mp = b->vmats[b->vmat[b->lpos[l]]];
+        const vx3_voxel_material &mn = b->o_vmats[b->vmat[b->lneg[l]]], &mp = b->o_vmats[b->vmat[b->lpos[l]]];
         int ax = b->laxis[l];
         b->lratio[l] = mp.E / mn.E;
         // baseSize(axis) = mat->size()[axis]*(1+temp*alphaCTE), VX_Voxel.h:91 (bracket is float)
@@ -394,19 +358,6 @@ extern "C" const vx3_model_desc *vx3_builder_build(vx3_builder *b) {
     }
 
     // ---- export ----
-    b->o_data.clear();
-    b->o_data.reserve(2 * (b->vmats.size() + b->lmats.size()) + 4);
-    b->o_vmats.resize(b->vmats.size());
-    for (size_t i = 0; i < b->vmats.size(); i++) export_vmat(b->vmats[i], b->o_vmats[i], b->o_data);
-    b->o_lmats.resize(b->lmats.size());
-    for (size_t i = 0; i < b->lmats.size(); i++) {
-        const LinkMat &m = b->lmats[i];
-        vx3_link_material &o = b->o_lmats[i];
-        export_vmat(m, o.m, b->o_data);
-        o.vox1_mat = m.vox1; o.vox2_mat = m.vox2;
-        o.a1 = m.a1; o.a2 = m.a2; o.b1 = m.b1; o.b2 = m.b2; o.b3 = m.b3;
-        o.sqA1 = m.sqA1; o.sqA2xIp = m.sqA2xIp; o.sqB1 = m.sqB1; o.sqB2xFMp = m.sqB2xFMp; o.sqB3xIp = m.sqB3xIp;
-    }
 
     vx3_model_desc &d = b->desc;
     memset(&d, 0, sizeof(d));

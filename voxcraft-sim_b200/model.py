@@ -17,7 +17,8 @@ MAT_DEFAULTS = dict(mat_model=0, elastic_mod=0.0, plastic_mod=0.0, yield_stress=
                     is_pacemaker=0, is_measured=1, is_electrical_active=0, is_target=0, fixed=0, sticky=0,
                     pacemaker_period=0.0, signal_value_decay=0.9, signal_time_delay=0.03, inactive_period=0.03,
                     remove_after_s=0.0, thermal_on_after_s=0.0, cilia_on_after_s=0.0, cilia=0.0,
-                    red=0.5, green=0.5, blue=0.5, alpha=1.0, name="Default")
+                    red=0.5, green=0.5, blue=0.5, alpha=1.0, name="Default",
+                    n_data=0, strain_data=None, stress_data=None)  # MatModel 3 (MDL_DATA): <SSData> points, first one (0, 0)
 
 # (VXA tag, spec key) for the <Mechanical> block, in the order the writer emits them
 _MECH_TAGS = [("MatModel", "mat_model"), ("Elastic_Mod", "elastic_mod"), ("Plastic_Mod", "plastic_mod"),
@@ -152,9 +153,14 @@ class ModelSpec:
             p = abi.MaterialParams()
             lib.vx3_material_params_default(C.byref(p))
             for k, v in m.items():
-                if k == "name":
+                if k in ("name", "strain_data", "stress_data", "n_data"):
                     continue
                 setattr(p, k, v)
+            if m["strain_data"] is not None:
+                n = len(m["strain_data"])
+                sd, ss = (C.c_double * n)(*m["strain_data"]), (C.c_double * n)(*m["stress_data"])
+                self._keep += [sd, ss]
+                p.n_data, p.strain_data, p.stress_data = n, sd, ss
             lib.vx3_builder_add_material(b, C.byref(p))
         e = abi.EnvParams()
         lib.vx3_env_params_default(C.byref(e))
@@ -251,6 +257,10 @@ class ModelSpec:
             s.append("      <Display><Red>%s</Red><Green>%s</Green><Blue>%s</Blue><Alpha>%s</Alpha></Display>\n"
                      % tuple(g(float(m[k])) for k in ("red", "green", "blue", "alpha")))
             s.append("      <Mechanical>\n")
+            if m["strain_data"] is not None:
+                s.append("        <SSData><NumDataPts>%d</NumDataPts><StrainData>%s</StrainData><StressData>%s</StressData></SSData>\n"
+                         % (len(m["strain_data"]), "".join("<Strain>%s</Strain>" % g(float(v)) for v in m["strain_data"]),
+                            "".join("<Stress>%s</Stress>" % g(float(v)) for v in m["stress_data"])))
             for tag, key in _MECH_TAGS:
                 s.append("        <%s>%s</%s>\n" % (tag, g(m[key]), tag))
             s.append("      </Mechanical>\n    </Material>\n")
