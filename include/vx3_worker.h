@@ -34,6 +34,20 @@ int vx3_worker_run_files(const char *base_vxa, const char *input_dir, const char
 /* Report writer alone (report.inputdir / bestfit / detail.<name>..., src/Executables/vx3_node_worker.cu:98-141). */
 int vx3_write_report(const char *vxr_path, const char *input_dir, const vx3_result *sorted, int n);
 
+/* Per-voxel outputs of one result (collectResults, src/VX3/VX3_SimulationManager.cu:445-466), written by the report as
+ * <init_pos> / <pos> ("x,y,z;" with std::to_string = %f) and <mats> ("id;") when the simulation's VXA sets
+ * SavePositionOfAllVoxels (src/Executables/vx3_node_worker.cu:122-139).  n_voxels = 0: nothing to write for that result. */
+typedef struct vx3_voxel_positions {
+    int32_t n_voxels;
+    int32_t _pad;
+    const double *init_pos; /* [n_voxels][3] */
+    const double *pos;      /* [n_voxels][3] */
+    const int32_t *mats;    /* [n_voxels] matid */
+} vx3_voxel_positions;
+
+/* vx3_write_report with the per-voxel entries: positions is NULL or one record per result, in the same (sorted) order. */
+int vx3_write_report_positions(const char *vxr_path, const char *input_dir, const vx3_result *sorted, const vx3_voxel_positions *positions, int n);
+
 #ifdef __cplusplus
 }
 #endif

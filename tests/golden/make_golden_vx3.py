@@ -46,3 +46,34 @@ for name in sorted(SCENARIOS):
         json.dump(out, f, separators=(",", ":"))
     print(name, ref.counts(), n_float)
     lib.vx3_builder_destroy(b)
+
+
+# ---- the stdout of the reference's CUDA_Simulation kernel (history frames, real_stepsize line, start / end lines) ----
+def history_case(tag, spec, desc, vxa_text=None):
+    ref = util.Vx3RefSim(spec, desc, vxa_text=vxa_text)
+    out = ref.run_simulation()
+    r = ref.result(refresh=False)
+    with open(os.path.join(HERE, "vx3_stdout_%s.txt" % tag), "wb") as f:
+        f.write(out)
+    res = {"steps": int(r.steps), "current_time": float(r.current_time).hex(), "fitness_score": float(r.fitness_score).hex(),
+           "current_com": [float(x).hex() for x in r.current_com], "initial_com": [float(x).hex() for x in r.initial_com],
+           "num_voxel": int(r.num_voxel), "source": "reference CUDA_Simulation (VX3_SimulationManager.cu:11-121) compiled for the host"}
+    with open(os.path.join(HERE, "vx3_stdout_%s.json" % tag), "w") as f:
+        json.dump(res, f)
+    print(tag, len(out), "bytes of stdout,", r.steps, "steps")
+
+
+from scenarios import history_spec  # noqa: E402
+
+lib = util.load_engine()
+spec = history_spec()
+b, d = spec.build(lib)
+history_case("runner", spec, d)
+lib.vx3_builder_destroy(b)
+# BASELINE config 1: the reference's own demos/basic (byte copy under tests/golden/demo_basic/), VXD merged by the product reader
+demo = os.path.join(HERE, "demo_basic")
+b = lib.vx3_vxa_load(os.path.join(demo, "base.vxa").encode(), os.path.join(demo, "robot.vxd").encode())
+assert b, lib.vx3_model_last_error()
+d = lib.vx3_builder_build(b)
+history_case("demo_basic", None, d, vxa_text=open(os.path.join(demo, "base.vxa")).read())
+lib.vx3_builder_destroy(b)

@@ -93,6 +93,14 @@ def runner_spec():
     return spec
 
 
+def history_spec():
+    """runner_spec with the history recorder on: voxel frames and link frames, the CUDA_Simulation stdout is the fixture."""
+    spec = runner_spec()
+    spec.name = "runner.vxd"
+    spec.set_options(record_step_size=200, record_voxel=1, record_link=1)
+    return spec
+
+
 def signal_body_spec(shape=(5, 4, 3), all_pacemakers=False, delay=0.004, cilia=False, seed=3, name="sig"):
     spec = ModelSpec(0.01, name)
     common = dict(elastic_mod=1e6, density=1e3, u_static=1.0, u_dynamic=0.8, inactive_period=0.006)

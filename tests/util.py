@@ -127,10 +127,10 @@ class Vx3RefSim:
     """The reference's own VX3 step loop (src/VX3/*.cu compiled for the host, oracle/ref_vx3) on a ModelSpec: the VXA text
     goes through CVX_Sim, the VX3-only settings come from the flat model `desc` (see vx3ref_harness.cpp)."""
 
-    def __init__(self, spec, desc):
+    def __init__(self, spec, desc, vxa_text=None):
         self.lib = load_ref_vx3()
         with tempfile.NamedTemporaryFile("w", suffix=".vxa", delete=False) as f:
-            f.write(spec.to_vxa())
+            f.write(vxa_text if vxa_text is not None else spec.to_vxa())
             path = f.name
         self.h = self.lib.vx3ref_create(path.encode(), desc)
         os.unlink(path)
@@ -263,7 +263,7 @@ def max_rel_err(a, b, scale=None):
     return float(np.max(np.abs(a - b)) / s)
 
 
-def libm_envelope(desc_ptr, steps, dt, checkpoints=None, seeds=(11, 23, 37), keys=None):
+def libm_envelope(desc_ptr, steps, dt, checkpoints=None, seeds=(11, 23, 37, 41, 59), keys=None):
     """Element-wise spread of the oracle's state under a 1-ulp libm error model (vx3o_set_libm_jitter): the exact run plus
     len(seeds) replicas whose sin / cos / acos results are moved by -1 / 0 / +1 ulp at random.  Returns
     (exact_states, envelopes): one dict per checkpoint (steps, cumulative), envelope[k] = max over replicas of
@@ -306,7 +306,8 @@ def libm_envelope(desc_ptr, steps, dt, checkpoints=None, seeds=(11, 23, 37), key
 def gate_within_envelope(se, so, env, keys, what="", factor=8.0, rel_floor=1e-9):
     """The tolerance gate of the GPU parity tests, element-wise:  |gpu - oracle| <= max(rel_floor * scale, factor * env)
     where scale = max |oracle| over the array (so zeros are handled) and env is the element's spread under the 1-ulp libm
-    error model (libm_envelope), smoothed by the array's median spread.  rel_floor = 1e-9 is BASELINE.md's bar; the
+    error model (libm_envelope; a handful of replicas, so an element's own spread is raised to the array's 90th percentile
+    where that is larger).  rel_floor = 1e-9 is BASELINE.md's bar; the
     envelope term only ever loosens it where a 1-ulp difference in sin / cos / acos PROVABLY moves the oracle itself by
     more than that (momenta and link forces are differences of large terms).  Returns the worst ratio err / tol per key."""
     worst = {}
@@ -319,7 +320,7 @@ def gate_within_envelope(se, so, env, keys, what="", factor=8.0, rel_floor=1e-9)
         tol = np.full(a.shape, rel_floor * scale)
         if env is not None and env.get(k) is not None:
             e = env[k]
-            tol = np.maximum(tol, factor * np.maximum(e, np.median(e)))
+            tol = np.maximum(tol, factor * np.maximum(e, np.quantile(e, 0.9)))
         err = np.abs(a - b)
         ratio = float(np.max(err / tol))
         worst[k] = ratio

@@ -214,7 +214,7 @@ ENGINE_SYMBOLS = ["vx3_batch_create", "vx3_batch_run", "vx3_batch_step", "vx3_ba
                   "vx3_batch_halo_export", "vx3_batch_halo_connect", "vx3_batch_halo_connect_local", "vx3_batch_com_sums",
                   "vx3_batch_step_async", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_engine_trim", "vx3_last_error",
                   "vx3_abi_version"]
-WORKER_SYMBOLS = ["vx3_worker_run_vxt", "vx3_worker_run_files", "vx3_write_report"]
+WORKER_SYMBOLS = ["vx3_worker_run_vxt", "vx3_worker_run_files", "vx3_write_report", "vx3_write_report_positions"]
 MODEL_SYMBOLS = ["vx3_material_params_default", "vx3_env_params_default", "vx3_sim_options_default", "vx3_builder_create",
                  "vx3_builder_destroy", "vx3_builder_add_material", "vx3_builder_set_env", "vx3_builder_set_options",
                  "vx3_builder_set_name", "vx3_builder_set_program", "vx3_builder_set_structure", "vx3_builder_set_external",

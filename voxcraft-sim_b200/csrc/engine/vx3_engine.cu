@@ -1332,21 +1332,38 @@ extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history
     // history frame cadence (VX3_SimulationManager.cu:56,71)
     std::vector<long long> frame_every(b->nsims, 0);
     HistoryWriter hw;
+    // CurStepCount at the start of this run: the loop index j of CUDA_Simulation restarts at 0 with every run, the device
+    // counter does not (earlier vx3_batch_step / _run calls)
+    std::vector<long long> steps0(b->nsims);
+    for (int s = 0; s < b->nsims; s++) steps0[s] = h[s].steps;
+    std::vector<char> announced_end(b->nsims, 0);
+    char line[768];
     if (history) {
+        // the stdout of CUDA_Simulation up to its step loop, per simulation (VX3_SimulationManager.cu:25, :40-50, :56-58)
         for (int s = 0; s < b->nsims; s++) {
             const vx3_sim_options &o = b->opts[s];
-            if (o.record_step_size > 0) {
-                double rec = b->simc[s].optimal_dt; // recommendedTimeStep()
-                frame_every[s] = (long long)(int)(o.record_step_size / (10000.0 * rec * o.dt_frac)) + 1;
-                std::string hdr = hw.header(b->matid[s], b->matcolor[s], o.vox_size);
-                cb(user, s, hdr.data(), hdr.size());
+            std::string pre;
+            snprintf(line, sizeof(line), "\033[0;32m%d) Simulation %d runs: %s.\n\033[0m", b->device, s, b->names[s].c_str());
+            pre += line;
+            const double rec = b->simc[s].optimal_dt; // recommendedTimeStep()
+            const int real_stepsize = (int)(o.record_step_size / (10000 * rec * o.dt_frac)) + 1;
+            if (o.record_step_size) {
+                frame_every[s] = real_stepsize;
+                pre += hw.header(b->matid[s], b->matcolor[s], o.vox_size);
             }
+            // recommendedTimeStep() warns on a model without links every time it is called (VX3_VoxelyzeKernel.cu:189-191): twice
+            // around this line, once more from the first doTimeStep (:245-247)
+            if (b->simc[s].nhostlinks == 0) pre += "WARNING: No links.\nWARNING: No links.\n";
+            snprintf(line, sizeof(line), "real_stepsize: %d ; recommendedTimeStep %f; d_v3->DtFrac %f . \n", real_stepsize, rec, o.dt_frac);
+            pre += line;
+            cb(user, s, pre.data(), pre.size());
         }
     }
     CK(cudaEventRecord(b->ev0, b->stream));
     k_sim_update<<<cdiv(b->nsims, 128), 128, 0, b->stream>>>(b->D, 2); // StopConditionMet() before the first step
     b->launches++;
     long long j = 0; // loop index of CUDA_Simulation (:62); all simulations start this run at j = 0
+    bool first_chunk = true;
     if (chunk <= 0) {
         long long perstep = std::max<long long>(1, (long long)b->D.nvox + b->D.nlinkslots);
         chunk = (int)std::max<long long>(16, std::min<long long>(4096, 40000000 / perstep));
@@ -1372,6 +1389,11 @@ extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history
             if (h[s].err) return fail(h[s].err, "simulation " + std::to_string(s) + ": device-side capacity/consistency error");
             running |= h[s].status == VX3_SIM_RUNNING;
         }
+        if (history && first_chunk) {
+            for (int s = 0; s < b->nsims; s++)
+                if (b->simc[s].nhostlinks == 0 && h[s].steps > steps0[s]) cb(user, s, "WARNING: No links.\n", 19);
+        }
+        first_chunk = false;
         if (history) {
             for (int s = 0; s < b->nsims; s++) {
                 if (frame_every[s] <= 0) continue;
@@ -1379,13 +1401,21 @@ extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history
                 // and the simulation executed that step (it breaks out of the loop before printing otherwise)
                 const long long jj = j - 1;
                 if (jj % frame_every[s] != 0) continue;
-                if (h[s].steps != j) continue; // stopped or diverged earlier
+                if (h[s].steps != steps0[s] + j) continue; // stopped or diverged earlier
                 if (h[s].status == VX3_SIM_DIVERGED) continue;
                 std::string fr;
                 rc = history_frame(b, s, jj, h[s].t, hw, fr);
                 if (rc) return rc;
                 cb(user, s, fr.data(), fr.size());
             }
+        }
+        if (history) { // "Diverged" is printed inside the loop, at the step that failed (:65-69)
+            for (int s = 0; s < b->nsims; s++)
+                if (h[s].status == VX3_SIM_DIVERGED && !announced_end[s]) {
+                    announced_end[s] = 1;
+                    snprintf(line, sizeof(line), "\033[1;31m\n\n%d) Simulation %d Diverged: %s.\n\033[0m", b->device, s, b->names[s].c_str());
+                    cb(user, s, line, strlen(line));
+                }
         }
         if (!running) break;
     }
@@ -1394,6 +1424,15 @@ extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history
         b->launches++;
     }
     run_com(b, 1); // updateCurrentCenterOfMass + computeFitness (:116-117)
+    if (history) { // the closing line of CUDA_Simulation (:118-119)
+        rc = fetch_simd(b, h);
+        if (rc) return rc;
+        for (int s = 0; s < b->nsims; s++) {
+            snprintf(line, sizeof(line), "\033[0;34m%d) Simulation %d ends: %s Time: %f, angleSampleTimes: %d.\n\033[0m", b->device, s, b->names[s].c_str(),
+                     h[s].t, h[s].angle_samples);
+            cb(user, s, line, strlen(line));
+        }
+    }
     CK(cudaEventRecord(b->ev1, b->stream));
     CK(cudaEventSynchronize(b->ev1));
     CK(cudaGetLastError());

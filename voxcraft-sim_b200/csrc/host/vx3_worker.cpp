@@ -2,6 +2,7 @@
 // of the engine (include/vx3_abi.h), so this file is also a reference consumer of that ABI.
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -45,6 +46,10 @@ std::string base_name(const std::string &p) {
 } // namespace
 
 extern "C" int vx3_write_report(const char *vxr_path, const char *input_dir, const vx3_result *r, int n) {
+    return vx3_write_report_positions(vxr_path, input_dir, r, nullptr, n);
+}
+
+extern "C" int vx3_write_report_positions(const char *vxr_path, const char *input_dir, const vx3_result *r, const vx3_voxel_positions *vp, int n) {
     if (!vxr_path || !r || n <= 0) return VX3_ERR_INVALID;
     FILE *f = fopen(vxr_path, "w");
     if (!f) return VX3_ERR_INVALID;
@@ -66,6 +71,22 @@ extern "C" int vx3_write_report(const char *vxr_path, const char *input_dir, con
         s += "<initialCenterOfMass><x>" + fmt_double(r[i].initial_com[0]) + "</x><y>" + fmt_double(r[i].initial_com[1]) + "</y><z>" + fmt_double(r[i].initial_com[2]) + "</z></initialCenterOfMass>";
         s += "<currentCenterOfMass><x>" + fmt_double(r[i].current_com[0]) + "</x><y>" + fmt_double(r[i].current_com[1]) + "</y><z>" + fmt_double(r[i].current_com[2]) + "</z></currentCenterOfMass>";
         s += "<total_distance_of_all_voxels>" + fmt_double(r[i].total_distance_of_all_voxels) + "</total_distance_of_all_voxels>";
+        if (vp && vp[i].n_voxels > 0) { // SavePositionOfAllVoxels (vx3_node_worker.cu:122-139): std::to_string(double) is "%f"
+            auto triples = [&](const double *p) {
+                std::string t;
+                char buf[128];
+                for (int v = 0; v < vp[i].n_voxels; v++) {
+                    snprintf(buf, sizeof(buf), "%f,%f,%f;", p[3 * v], p[3 * v + 1], p[3 * v + 2]);
+                    t += buf;
+                }
+                return t;
+            };
+            s += "<init_pos>" + triples(vp[i].init_pos) + "</init_pos>";
+            s += "<pos>" + triples(vp[i].pos) + "</pos>";
+            std::string mats;
+            for (int v = 0; v < vp[i].n_voxels; v++) mats += std::to_string(vp[i].mats[v]) + ";";
+            s += "<mats>" + mats + "</mats>";
+        }
         s += "</" + nm + ">";
     }
     s += "</detail></report>\n";
@@ -97,6 +118,11 @@ extern "C" int vx3_worker_run_files(const char *base_vxa, const char *input_dir,
     if (base_only) files.push_back("");
     const int total = (int)files.size();
     std::vector<vx3_result> all(total);
+    struct Dump { // per-voxel outputs of a simulation whose VXA sets SavePositionOfAllVoxels
+        std::vector<double> init_pos, pos;
+        std::vector<int32_t> mats;
+    };
+    std::vector<Dump> dumps(total);
     std::vector<int> rc(ndev, VX3_OK);
     std::vector<std::string> errs(ndev);
     std::vector<std::thread> threads;
@@ -127,10 +153,6 @@ extern "C" int vx3_worker_run_files(const char *base_vxa, const char *input_dir,
                 }
                 builders.push_back(b);
                 descs.push_back(*d);
-                if (verbose) {
-                    std::lock_guard<std::mutex> lk(g_out_mutex);
-                    printf("%d) Simulation %d runs: %s.\n", dev, (int)descs.size() - 1, name.c_str());
-                }
             }
             vx3_batch *batch = nullptr;
             int r = vx3_batch_create(dev, descs.data(), (int)descs.size(), &batch);
@@ -143,6 +165,15 @@ extern "C" int vx3_worker_run_files(const char *base_vxa, const char *input_dir,
             }
             std::vector<vx3_result> res(descs.size());
             if (r == VX3_OK) r = vx3_batch_results(batch, res.data());
+            for (size_t k = 0; k < mine.size() && r == VX3_OK; k++) {
+                if (!descs[k].opt.save_position_of_all_voxels) continue;
+                Dump &dp = dumps[mine[k]];
+                const size_t nv = (size_t)descs[k].n_voxels;
+                dp.init_pos.resize(3 * nv);
+                dp.pos.resize(3 * nv);
+                dp.mats.resize(nv);
+                r = vx3_batch_positions(batch, (int)k, dp.init_pos.data(), dp.pos.data(), dp.mats.data());
+            }
             if (r != VX3_OK) {
                 rc[dev] = r;
                 errs[dev] = vx3_last_error();
@@ -158,9 +189,27 @@ extern "C" int vx3_worker_run_files(const char *base_vxa, const char *input_dir,
             vx3_model_set_error("device " + std::to_string(dev) + ": " + errs[dev]);
             return rc[dev];
         }
-    vx3_sort_results(all.data(), total); // sortResults
-    if (results_out) memcpy(results_out, all.data(), sizeof(vx3_result) * total);
-    if (vxr_path && *vxr_path) return vx3_write_report(vxr_path, input_dir, all.data(), total);
+    // sortResults: fitness descending, NaN last (the rule of vx3_sort_results), applied to an index so that the per-voxel
+    // dumps follow their results
+    std::vector<int> order(total);
+    for (int i = 0; i < total; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const double fa = all[a].fitness_score, fb = all[b].fitness_score;
+        if (std::isnan(fa)) return false;
+        if (std::isnan(fb)) return true;
+        return fa > fb;
+    });
+    std::vector<vx3_result> sorted(total);
+    std::vector<vx3_voxel_positions> vps(total);
+    bool any_dump = false;
+    for (int i = 0; i < total; i++) {
+        sorted[i] = all[order[i]];
+        const Dump &dp = dumps[order[i]];
+        vps[i] = vx3_voxel_positions{(int32_t)dp.mats.size(), 0, dp.init_pos.data(), dp.pos.data(), dp.mats.data()};
+        any_dump |= !dp.mats.empty();
+    }
+    if (results_out) memcpy(results_out, sorted.data(), sizeof(vx3_result) * total);
+    if (vxr_path && *vxr_path) return vx3_write_report_positions(vxr_path, input_dir, sorted.data(), any_dump ? vps.data() : nullptr, total);
     return VX3_OK;
 }
 
