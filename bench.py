@@ -9,6 +9,12 @@ At N=1 the workload is BASELINE.json's config 2 (single 20x20x20 actuated body, 
 path shards by independent simulation: every rank steps its own copy of the per-GPU workload,
 no data-path collective, scaling = weak; the only cross-rank traffic is the end-of-run gather of fitness results.
 
+The same run also measures, in the same process group and with the same timing rules, the two multi-GPU workloads
+north_star names, and reports them as sub-objects of the one JSON line (`--skip-extra` leaves them out):
+  "config3"  the vx3_node_worker batch: 512 random 10^3 robots PER GPU (4096 over 8), weak scaling, streaming kernels
+  "config5"  ONE 200x200x100 body: undivided at N=1, cut into N x-slabs with halo exchange over peer memory at N>1
+             (strong scaling), with a bit-exact self-check of the slab run against the undivided body on rank 0
+
 Timing: W untimed warm-up steps, then exactly K steps between barrier+synchronize, device-timed with CUDA events
 on the engine's own stream (vx3_batch_last_timing), max over ranks.  `value` starts with the model resident in
 HBM; `e2e` re-creates the batch from HOST arrays every step (H2D), steps, and reads results + positions back
@@ -183,17 +189,19 @@ def reference_cpu_throughput(spec, target_seconds, omp=True):
             "seconds": el, "steps": done, "voxels": sim.nv}
 
 
-def run_decomposed(args, lib, built, label, rank, local_rank, world):
+def run_decomposed(args, lib, built, label, rank, local_rank, world, K, Wm, S, selfcheck_steps=20):
     """Config 5 on N GPUs: every rank builds the full model on the host, keeps its slab (+ ghost faces), wires the halo
-    exchange with its neighbours and steps in lock step; value = voxels of the WHOLE body x steps / max device time."""
+    exchange with its neighbours and steps in lock step; value = voxels of the WHOLE body x steps / max device time.
+    Returns the result line on rank 0 (None elsewhere)."""
+    import hashlib
     import numpy as np
     import torch
     import torch.distributed as dist
     from voxcraft_sim_b200 import parallel
+    from voxcraft_sim_b200.engine import Batch
     from voxcraft_sim_b200.workloads import alg_bytes_per_voxel_step
     _, d = built[0]
     nvox, nlinks = d.contents.n_voxels, d.contents.n_links
-    K, Wm, S = args.steps, max(args.warmup, 0), args.sim_steps
     dt = float(np.float32(d.contents.opt.dt_frac * lib.vx3_model_recommended_dt(d)))
     slab = parallel.partition_slabs(d, world, rank, axis=0)
     body = parallel.DecomposedBody(slab, dt, device=local_rank, fma=bool(args.fma))
@@ -203,6 +211,26 @@ def run_decomposed(args, lib, built, label, rank, local_rank, world):
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- self-check: the first steps of the slab run against the UNDIVIDED body stepped on rank 0, bit for bit ----
+    selfcheck = None
+    if selfcheck_steps > 0:
+        body.step(selfcheck_steps)
+        pos = body.batch.positions(0)[1]
+        mine = hashlib.sha256(np.ascontiguousarray(pos[slab.owned]).tobytes()).hexdigest()
+        table = [None] * world
+        dist.all_gather_object(table, mine)
+        if rank == 0:
+            whole = Batch([d], device=local_rank)
+            whole.set_profiling(False, use_persistent=False)
+            whole.step(selfcheck_steps, dt)
+            wpos = whole.positions(0)[1]
+            whole.close()
+            owner = parallel.slab_owner(d, world, axis=0)
+            want = [hashlib.sha256(np.ascontiguousarray(wpos[owner == r]).tobytes()).hexdigest() for r in range(world)]
+            selfcheck = {"steps": selfcheck_steps, "what": "sha256 of every slab's owned voxel positions == the same voxels of the undivided body stepped on rank 0",
+                         "bit_exact": want == table}
+        barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -230,6 +258,7 @@ def run_decomposed(args, lib, built, label, rank, local_rank, world):
     cnt = torch.tensor([float(launches), float(slab.owned.sum()), float(len(slab.voxels))], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         b_alg = alg_bytes_per_voxel_step(nvox, nlinks)
@@ -243,8 +272,9 @@ def run_decomposed(args, lib, built, label, rank, local_rank, world):
         elif top[0] == "k_links_face":
             alg_launch = 184.0 * finfo[3]
         else:
-            alg_launch = 184.0 * n_l_local if top[0] == "k_links" else 228.0 * float(slab.owned.sum())
+            alg_launch = 184.0 * n_l_local if top[0].startswith("k_links") else 228.0 * float(slab.owned.sum())
         avg_s = 1e-3 * top[1][0] / top[1][1]
+        halo_ms = sum(v[0] for k, v in stats.items() if k.startswith("k_halo"))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms_max / K,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": label + ", cut into %d x-slabs with halo exchange over peer memory (NVLink)" % world, "voxels_total": nvox,
@@ -253,17 +283,75 @@ def run_decomposed(args, lib, built, label, rank, local_rank, world):
                            "total_sim_steps": S * K, "build": "-fmad=false (parity-grade)", "path": ("fused blocks" if finfo[0] else "streaming") + " + k_halo",
                            "l2": "working set per GPU %.0f MB" % ((nvox * 228 + nlinks * 184) / world / 1e6),
                            "alg_bytes_per_voxel_step": b_alg, "wall_ms_per_step": 1e3 * wall_max / K, "center_of_mass": com},
+                "selfcheck": selfcheck, "k_halo_ms_per_sim_step": halo_ms / prof_steps, "k_halo_share_of_step": halo_ms / (sum(v[0] for v in stats.values()) or 1.0),
                 "roofline": {"bound": "hbm", "kernel": top[0], "achieved": alg_launch / avg_s / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": alg_launch / avg_s / 1e9 / peak, "traffic": None, "peak_source": peak_src, "rank": 0,
                              "kernel_ms": {k: round(v[0], 4) for k, v in stats.items()}, "kernel_launches": {k: v[1] for k, v in stats.items()}},
                 "hbm_roofline_equiv_frac": value * b_alg / (peak * 1e9 * world), "cpu_baseline": None, "clocks": clocks,
                 "gpu_launches": int(cnt[0]), "e2e": None}
-        emit(line)
     body.batch.close()
+    return line
+
+
+def measure_resident(batch, S, K, Wm, barrier, persistent=True):
+    """W warm-up + K timed bench steps of S doTimeStep calls each on a resident batch; device time from the engine's own
+    CUDA events; then one profiled pass for the per-kernel times.  Returns (dev_ms, launches, wall_s, kernel stats, prof_steps)."""
+    for _ in range(Wm):
+        batch.step(S)
+    barrier()
+    dev_ms, launches = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(K):
+        batch.step(S)
+        ms, nl = batch.timing()
+        dev_ms += ms
+        launches += nl
+    barrier()
+    wall = time.perf_counter() - t0
+    batch.set_profiling(True, use_persistent=persistent)
+    prof_steps = min(S, 100)
+    batch.step(prof_steps)
+    stats = {k: v for k, v in batch.kernel_stats().items() if v[1] > 0}
+    batch.set_profiling(False, use_persistent=persistent)
+    return dev_ms, launches, wall, stats, prof_steps
+
+
+def extra_resident(tag, specs, label, scaling, lib, rank, local_rank, world, barrier, S, K, Wm):
+    """One of the extra workloads on a resident batch per rank (config 3 at any N, config 5 at N = 1): same timing rules as
+    the headline (barrier + synchronize around exactly K steps, CUDA events, max over ranks, work summed over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from voxcraft_sim_b200.engine import Batch
+    from voxcraft_sim_b200.workloads import alg_bytes_per_voxel_step
+    built = [s.build(lib) for s in specs]
+    descs = [d for _, d in built]
+    nvox = sum(d.contents.n_voxels for d in descs)
+    nlinks = sum(d.contents.n_links for d in descs)
+    batch = Batch(descs, device=local_rank)
+    dev_ms, launches, wall, stats, prof_steps = measure_resident(batch, S, K, Wm, barrier)
+    res = batch.results()
+    diverged = sum(1 for r in res if r.status == 2)
+    batch.close()
     for b, _ in built:
         lib.vx3_builder_destroy(b)
-    dist.destroy_process_group()
-    return 0
+    tt = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(nvox) * S * K, float(launches), float(diverged)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    peak, _ = measured_peak_hbm()
+    b_alg = alg_bytes_per_voxel_step(nvox, nlinks)
+    dev_ms_max = float(tt[0])
+    value = float(work[0]) / (dev_ms_max * 1e-3)
+    total = sum(v[0] for v in stats.values()) or 1.0
+    return {"workload": label, "value": value, "unit": UNIT, "n_gpus": world, "scaling": scaling, "steps": K, "warmup": Wm, "sim_steps_per_step": S,
+            "ms_per_step": dev_ms_max / K, "us_per_sim_step": 1e3 * dev_ms_max / (K * S), "sims_per_gpu": len(descs), "voxels_per_gpu": nvox,
+            "links_per_gpu": nlinks, "alg_bytes_per_voxel_step": b_alg, "hbm_roofline_equiv_frac": value * b_alg / (peak * 1e9 * world),
+            "kernel_us_per_sim_step": {k: round(1e3 * v[0] / prof_steps, 3) for k, v in stats.items()},
+            "kernel_share": {k: round(v[0] / total, 4) for k, v in stats.items()}, "gpu_launches": int(work[1]), "diverged_sims": int(work[2]),
+            "wall_ms_per_step": 1e3 * float(tt[1]) / K}
 
 
 def main():
@@ -281,6 +369,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-extra", action="store_true", help="config 2 headline only: leave out the config 3 / config 5 sub-measurements")
     args = ap.parse_args()
     claim_stdout()
     rank, local_rank, world = env_rank()
@@ -329,7 +418,13 @@ def main():
     if args.workload == "c5" and world > 1:
         # config 5 at N > 1: ONE body cut into slabs along x, one slab per GPU, halo exchange over peer memory inside the
         # step stream (strong scaling: the total work is fixed)
-        return run_decomposed(args, lib, built, label, rank, local_rank, world)
+        line = run_decomposed(args, lib, built, label, rank, local_rank, world, K, Wm, S)
+        if rank == 0:
+            emit(line)
+        for b, _ in built:
+            lib.vx3_builder_destroy(b)
+        dist.destroy_process_group()
+        return 0
 
     if args.fused:
         os.environ["VX3_FUSED"] = "1"
@@ -396,7 +491,10 @@ def main():
             traffic, traffic_src = ent["bytes_per_launch"], ent["capture"] + (" (" + ent["note"] + ")" if ent.get("note") else "")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    on_chip = top[0] == "k_persistent"
+    roofline = {"bound": "latency (on-chip: state lives in registers / shared memory, DRAM traffic ~0; achieved / frac are the HBM-EQUIVALENT of the "
+                         "algorithmic bytes, not HBM traffic)" if on_chip else "hbm",
+                "equivalent": on_chip, "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_share_of_step": top[1][0] / total_prof,
                 "alg_bytes_per_launch": alg_bytes_launch, "avg_launch_us": 1e6 * avg_launch_s,
                 "kernel_ms": {k: round(v[0], 4) for k, v in stats.items()}, "kernel_launches": {k: v[1] for k, v in stats.items()}}
@@ -437,6 +535,24 @@ def main():
     dev_ms_max, wall_max, e2e_max = [float(x) for x in tt.tolist()]
     total_work, total_launches, total_div = [float(x) for x in work.tolist()]
 
+    # ---- the multi-GPU workloads north_star names, measured in the same run (sub-objects of the one line) ----
+    extras = {}
+    if args.workload == "c2" and not args.skip_extra:
+        batch.close()
+        batch = None
+        from voxcraft_sim_b200 import workloads as W
+        c3_specs = [W.c3_spec(k) for k in range(args.sims_per_gpu)]
+        extras["config3"] = extra_resident("c3", c3_specs, "config3: batch of %d random 10x10x10 robots per GPU (vx3_node_worker fitness eval), %d in all"
+                                           % (args.sims_per_gpu, args.sims_per_gpu * world), "weak", lib, rank, local_rank, world, barrier, 200, 10, 3)
+        c5_specs, c5_label = build_workload("c5", None, 0)
+        if world > 1:
+            c5_built = [sp.build(lib) for sp in c5_specs]
+            extras["config5"] = run_decomposed(args, lib, c5_built, c5_label, rank, local_rank, world, 4, 2, 50)
+            for b5, _ in c5_built:
+                lib.vx3_builder_destroy(b5)
+        else:
+            extras["config5"] = extra_resident("c5", c5_specs, c5_label, "strong", lib, rank, local_rank, world, barrier, 50, 4, 3)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu_baseline = reference_cpu_throughput(specs[0], args.cpu_seconds)
@@ -462,8 +578,14 @@ def main():
             ev = float(nvox) * S * e2e["steps"] * world / e2e_max
             line["e2e"] = {"value": ev, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                            "steps": e2e["steps"], "what": "vx3_batch_create from host arrays + vx3_batch_step + vx3_batch_results/positions + destroy per step"}
+        if total_div > 0:
+            line["invalid"] = "%d simulation(s) diverged inside the timed region: their voxel-steps are counted but not computed" % int(total_div)
+        for k, v in extras.items():
+            if v is not None:
+                line[k] = v
         emit(line)
-    batch.close()
+    if batch is not None:
+        batch.close()
     for b, _ in built:
         lib.vx3_builder_destroy(b)
     if world > 1:

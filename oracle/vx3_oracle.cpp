@@ -85,9 +85,10 @@ const double SLTHRESH_ACOS2SQRT = 2.4e-3;
 
 // ---- libm error model (test hook, vx3o_set_libm_jitter): the GPU's libdevice sin / cos / acos are within 1 ulp of the
 // correctly rounded result, glibc's too, but not identically rounded.  With a non-zero seed every sin / cos / acos result
-// of the physics path is moved by -1, 0 or +1 ulp at (seeded) random: running a few such replicas next to the exact one
+// of the physics path (and every transcendental of a math-tree program) is moved by -1, 0 or +1 ulp at (seeded) random: running a few such replicas next to the exact one
 // gives the envelope inside which ANY 1-ulp libm's trajectory must lie — the yardstick of the GPU tolerance gates.
 static unsigned long long g_libm_jitter = 0; // 0 = off
+static int g_libm_jitter_mode = 0;           // +1 / -1: every result moved one ulp up / down; 0: random per call
 static inline double jitter_ulp(double v) {
     if (!g_libm_jitter) return v;
     g_libm_jitter += 0x9E3779B97F4A7C15ull;
@@ -95,6 +96,9 @@ static inline double jitter_ulp(double v) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
+    // seeds 1 and 2 model a libm that is CONSISTENTLY off in one direction (always +1 / always -1 ulp): a systematic bias adds up
+    // linearly over the steps where random jitter adds up like a random walk
+    if (g_libm_jitter_mode) return nextafter(v, g_libm_jitter_mode > 0 ? INFINITY : -INFINITY);
     const unsigned r = (unsigned)(z >> 33) % 3u;
     return r == 0 ? v : nextafter(v, r == 1 ? INFINITY : -INFINITY);
 }
@@ -206,18 +210,18 @@ double mt_eval(const std::vector<vx3_token> &buff, double x, double y, double z,
             else if (v < 7.5) out = numClosePairs;
             else if (v < 8.5) out = num_voxel;
             break;
-        case VX3_OP_SIN: out = sin(p[0]); process_cursor++; break;
-        case VX3_OP_COS: out = cos(p[0]); process_cursor++; break;
-        case VX3_OP_TAN: out = tan(p[0]); process_cursor++; break;
-        case VX3_OP_ATAN: out = atan(p[0]); process_cursor++; break;
-        case VX3_OP_LOG: out = log(p[0]); process_cursor++; break;
+        case VX3_OP_SIN: out = jitter_ulp(sin(p[0])); process_cursor++; break;
+        case VX3_OP_COS: out = jitter_ulp(cos(p[0])); process_cursor++; break;
+        case VX3_OP_TAN: out = jitter_ulp(tan(p[0])); process_cursor++; break;
+        case VX3_OP_ATAN: out = jitter_ulp(atan(p[0])); process_cursor++; break;
+        case VX3_OP_LOG: out = jitter_ulp(log(p[0])); process_cursor++; break;
         case VX3_OP_INT: out = rint(p[0]); process_cursor++; break;
-        case VX3_OP_NORMALCDF: out = 0.5 * erfc(-p[0] * M_SQRT1_2); process_cursor++; break; // normcdf
+        case VX3_OP_NORMALCDF: out = jitter_ulp(0.5 * erfc(-p[0] * M_SQRT1_2)); process_cursor++; break; // normcdf
         case VX3_OP_ADD: out = p[1] + p[0]; process_cursor += 2; break;
         case VX3_OP_SUB: out = p[1] - p[0]; process_cursor += 2; break;
         case VX3_OP_MUL: out = p[1] * p[0]; process_cursor += 2; break;
         case VX3_OP_DIV: out = p[1] / p[0]; process_cursor += 2; break;
-        case VX3_OP_POW: out = pow(p[1], p[0]); process_cursor += 2; break;
+        case VX3_OP_POW: out = jitter_ulp(pow(p[1], p[0])); process_cursor += 2; break;
         case VX3_OP_SQRT: out = sqrt(p[0]); process_cursor++; break;
         case VX3_OP_ABS: out = fabs(p[0]); process_cursor++; break;
         case VX3_OP_NOT: out = !p[0]; process_cursor++; break;
@@ -1349,7 +1353,10 @@ int vx3o_surface(vx3o_sim *s, int *out, int cap) {
 }
 
 // libm error model: seed != 0 moves every sin / cos / acos result of the physics path by -1 / 0 / +1 ulp (see jitter_ulp); 0 = exact
-void vx3o_set_libm_jitter(unsigned long long seed) { g_libm_jitter = seed; }
+void vx3o_set_libm_jitter(unsigned long long seed) {
+    g_libm_jitter = seed;
+    g_libm_jitter_mode = seed == 1 ? 1 : (seed == 2 ? -1 : 0);
+}
 
 double vx3o_eval(const vx3_token *tok, int n, const double *vars9) {
     std::vector<vx3_token> p(tok, tok + n);

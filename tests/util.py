@@ -263,9 +263,10 @@ def max_rel_err(a, b, scale=None):
     return float(np.max(np.abs(a - b)) / s)
 
 
-def libm_envelope(desc_ptr, steps, dt, checkpoints=None, seeds=(11, 23, 37, 41, 59), keys=None):
+def libm_envelope(desc_ptr, steps, dt, checkpoints=None, seeds=(1, 2, 11, 23, 37), keys=None):
     """Element-wise spread of the oracle's state under a 1-ulp libm error model (vx3o_set_libm_jitter): the exact run plus
-    len(seeds) replicas whose sin / cos / acos results are moved by -1 / 0 / +1 ulp at random.  Returns
+    len(seeds) replicas whose sin / cos / acos results are moved by one ulp: seed 1 = always up, seed 2 = always down (a
+    consistently biased libm), other seeds = -1 / 0 / +1 at random per call.  Returns
     (exact_states, envelopes): one dict per checkpoint (steps, cumulative), envelope[k] = max over replicas of
     |replica - exact| (None where a replica's array shape differs, i.e. the topology itself is sensitive at the ulp level)."""
     lib = load_oracle()

@@ -1091,6 +1091,10 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_secondary(Dev D) {
     const int flags = D.vflags[v];
     if (!(flags & VXF_REMOVED) && m.remove_after > 0 && m.remove_after < t) {
         D.vflags[v] = flags | VXF_REMOVED;
+        // gpu_update_temperature skips removed voxels (:632-633): the temperature freezes at THIS step's value — the voxel pass
+        // has already put the next step's into the pose record, take it back
+        double *tp = D.pose + 8 * (size_t)v + 7;
+        *tp = pack_tp(D.tempe[v], unpack_pd(*tp));
         for (int k = 0; k < 6; k++) {
             const int li = D.vlinks[6 * (size_t)v + k];
             if (li < 0) continue;

@@ -110,6 +110,13 @@ def slab_bounds(coord, world):
     return bounds
 
 
+def slab_owner(desc, world, axis=0):
+    """Owning rank of every voxel of the full model under partition_slabs' rule (host-side check helper)."""
+    d = desc.contents if hasattr(desc, "contents") else desc
+    coord = _view([d.ix, d.iy, d.iz][axis], d.n_voxels, _np.int16).astype(_np.int64)
+    return _np.searchsorted(_np.asarray(slab_bounds(coord, world)[1:-1]), coord, side="right")
+
+
 class SlabModel:
     """One rank's sub-model of a decomposed body: ``desc`` (a vx3_model_desc whose arrays this object keeps alive), the
     global ids of its voxels (``voxels``) and which of them it owns, and per neighbour the pose records to send / receive
