@@ -457,6 +457,7 @@ def main():
     clocks = sampler.stop()
     res = batch.results()
     diverged = sum(1 for r in res if r.status == 2)
+    counters = batch.counters(0) if args.workload == "c4" else None
 
     # ---- roofline of the dominant kernel: a profiled pass (CUDA events around every launch, same stream) ----
     batch.set_profiling(True, use_persistent=not args.no_persistent)
@@ -570,7 +571,8 @@ def main():
                            "fused_step": {"active": bool(finfo[0]), "blocks": finfo[1], "links_interior": finfo[2], "links_face_prepass": finfo[3]},
                            "l2": "state is mutated by every step (each step reads what the previous one wrote); working set "
                                  "%.1f MB %s the 126 MB L2" % ((nvox * 228 + nlinks * 184) / 1e6, "fits in" if nvox * 228 + nlinks * 184 < 100e6 else "exceeds"),
-                           "alg_bytes_per_voxel_step": b_alg, "wall_ms_per_step": 1e3 * wall_max / K, "diverged_sims": int(total_div)},
+                           "alg_bytes_per_voxel_step": b_alg, "wall_ms_per_step": 1e3 * wall_max / K, "diverged_sims": int(total_div),
+                           "collision_counters_sim0": counters},
                 "roofline": roofline,
                 "hbm_roofline_equiv_frac": value * b_alg / (peak * 1e9 * world),
                 "cpu_baseline": cpu_baseline, "clocks": clocks, "gpu_launches": int(total_launches)}

@@ -372,6 +372,10 @@ int vx3_batch_halo_export(vx3_batch *b, int side, void *handle64);
 int vx3_batch_halo_connect(vx3_batch *b, int side, const void *peer_handle64, int peer_n_recv);
 int vx3_batch_halo_connect_local(vx3_batch *b, int side, vx3_batch *peer); /* both slabs driven by this process */
 int vx3_batch_com_sums(vx3_batch *b, int sim, double *out6);
+/* Event counters of one simulation (test / diagnostics hook; no reference twin): out8 = {attach events, detach events, live link
+ * slots in use, 0 (reserved), largest number of attach candidates one step produced, largest number of links one step put on the
+ * failed list, 0, 0}. */
+int vx3_batch_counters(vx3_batch *b, int sim, int64_t *out8);
 /* Queue k steps (explicit dt, or dt < 0 like vx3_batch_step) without waiting; vx3_batch_sync waits.  For one host thread
  * that drives several batches whose step streams wait for each other (slabs of a decomposed body): queue the slabs in
  * rounds of a few dozen steps — a round that overflows the driver's launch queue (~1000 launches) blocks the host on one

@@ -836,11 +836,30 @@ struct vx3o_sim {
     void handle_collision_attachment(int i1, int i2); // VX3_VoxelyzeKernel.cu:682-831
     void updateAttach() { // VX3_VoxelyzeKernel.cu:401-459,833-843 in the canonical order
         const int S = (int)surface.size();
-        for (int first = 0; first < S; first++)
+        // The pair order is the reference's (first ascending, second < first).  Positions, temperatures and materials do not
+        // change during the sweep, so the axis tests that open handle_collision_attachment (:687-695, all side-effect free) are
+        // evaluated here on flat copies — same expressions, same comparisons — and only the pairs that pass them enter the
+        // function (which repeats them).  Pure speed-up of the checker: 4e8 pair tests per step for config 4 at full size.
+        std::vector<double> px(S), py(S), pz(S), bs(S);
+        for (int i = 0; i < S; i++) {
+            const OVoxel &v = vox[surface[i]];
+            px[i] = v.pos.x; py[i] = v.pos.y; pz[i] = v.pos.z;
+            bs[i] = baseSizeAverage(v);
+        }
+        for (int first = 0; first < S; first++) {
+            const double fx = px[first], fy = py[first], fz = pz[first], fb = bs[first];
             for (int second = 0; second < first; second++) {
+                const double w = (fb + bs[second]) * COLLISION_ENVELOPE_RADIUS;
+                const double dx = fx - px[second];
+                if (dx > w || dx < -w) continue;
+                const double dy = fy - py[second];
+                if (dy > w || dy < -w) continue;
+                const double dz = fz - pz[second];
+                if (dz > w || dz < -w) continue;
                 if (vox[surface[first]].removed || vox[surface[second]].removed) continue;
                 handle_collision_attachment(surface[first], surface[second]);
             }
+        }
     }
     void updateDetach() { // VX3_VoxelyzeKernel.cu:461-475,946-968
         for (int li = 0; li < (int)links.size(); li++) {

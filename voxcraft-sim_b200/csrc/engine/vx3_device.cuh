@@ -25,8 +25,9 @@ namespace vx3 {
 #define LKS_AXIS_SHIFT 4
 #define LKS_AXIS_MASK (3 << LKS_AXIS_SHIFT)
 #define LKS_JUST_CREATED (1 << 6) // attached during the current step (cleared by the next link pass)
+#define LKS_FAILED (1 << 7)       // on the simulation's failed-link list of this step (EnableDetach): detached by k_resolve_detach
 #define LKS_NEWLINK_SHIFT VX3_LINKSTATE_NEWLINK_SHIFT
-#define LKS_PUBLIC_MASK (~(LKS_AXIS_MASK | LKS_JUST_CREATED))
+#define LKS_PUBLIC_MASK (~(LKS_AXIS_MASK | LKS_JUST_CREATED | LKS_FAILED))
 
 #define VX3_DEV_MAX_TOKENS 128 // per-voxel programs (force field, attach conditions) on the device evaluator
 #define VX3_MAX_PARTNERS 96    // contact partners of one voxel inside the collision envelope
@@ -88,6 +89,8 @@ struct SimC {
     int32_t prog_off[VX3_PROG_COUNT], prog_n[VX3_PROG_COUNT];
     int32_t tgt_off, ntgt;
     int32_t chunk_off, nchunks; // CoM reduction chunks
+    int32_t cand_off, cand_cap; // this simulation's region of the attach-candidate array (cand_cap is a power of two; 0 = cannot attach)
+    int32_t fail_off, fail_cap; // this simulation's region of the failed-link list (EnableDetach)
     int32_t secondary_experiment, enable_signals;
     double reinit_after; // ReinitializeInitialPositionAfterThisManySeconds
     double temp_amp, temp_period;
@@ -103,6 +106,7 @@ struct SimC {
 #define SHF_FORCE_FIELD (1 << 3)
 #define SHF_ATTACH_COND (1 << 4)
 #define SHF_SIGNALS (1 << 5)
+#define SHF_DETACH (1 << 6)      // EnableDetach: the link pass lists the links whose failure strain is passed
 
 // per-simulation dynamic scalars (VX3_VoxelyzeKernel members that change during the run).  The first 48 bytes are the
 // "hot" block every link / voxel of the simulation needs each step; the streaming kernels prefetch it with three
@@ -129,6 +133,9 @@ struct alignas(16) SimD {
     double total_dist;
     int32_t n_measured;
     int32_t initpos_reinitialized; // InitialPositionReinitialized
+    int32_t cand_count;            // attach candidates appended by the contact phase of this step
+    int32_t fail_count;            // failed links appended by the link pass of this step
+    int32_t cand_peak, fail_peak;  // largest counts a step has produced (diagnostics)
 };
 
 struct Chunk { int32_t sim, vstart, vcount, _pad; };
@@ -141,6 +148,13 @@ struct alignas(64) ContactRec {
     double bs;                  // baseSizeAverage() at this step's temperature (VX3_Voxel.h:101-104)
     int32_t sim, mat;           // simulation, global voxel-material index
     int32_t fixed, _pad;
+};
+
+// One slot of a grid bucket: the voxel and its position rounded to float — enough for a conservative first cut of the envelope
+// test without touching the voxel's 64-byte ContactRec (a bucket's 8 slots are one 128-byte line).
+struct alignas(16) CellItem {
+    float x, y, z;
+    int32_t v;
 };
 
 struct Cand { // attach candidate (VX3_VoxelyzeKernel.cu:729-812), sorted by (hi, lo) before resolution
@@ -208,14 +222,14 @@ struct Dev {
     double2 *lf2;
     // collision grid (hashed uniform grid, per-bucket lists)
     int32_t hmask;
-    // bucket b: cell_cnt[b] voxels; the first VX3_CELL_SLOTS of them inline in cell_items[b][], the rest (rare) chained
+    // bucket b: cell_cnt[b] voxels; the first VX3_CELL_SLOTS of them inline in cell_items[b][] (voxel + float position), the rest (rare) chained
     // through cell_ovf[b] (voxel + 1, 0 = none) / cell_next[].  cell_cnt and cell_ovf are one allocation, zeroed every step
-    int32_t *cell_cnt, *cell_ovf, *cell_items, *cell_next;
+    int32_t *cell_cnt, *cell_ovf, *cell_next;
+    CellItem *cell_items;
     struct ContactRec *crec; // [nvox] what the contact phase needs of a voxel, in one 64-byte record (written by k_grid_build)
     int32_t *uf;      // [nvox] union-find parents over the voxels (NULL unless a simulation can attach), see uf_find
-    Cand *cands;
-    int32_t *cand_count;
-    int32_t cand_cap;
+    Cand *cands;        // per-simulation regions (SimC::cand_off / cand_cap), counts in SimD::cand_count
+    int32_t *fail_list; // per-simulation regions (SimC::fail_off / fail_cap) of link slots, counts in SimD::fail_count
     // CoM partials [nchunks][6]: sum m*x, m*y, m*z, m, sum dist, n_measured
     double *com_part;
 #ifdef __CUDACC__

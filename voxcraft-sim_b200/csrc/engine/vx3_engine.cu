@@ -214,6 +214,11 @@ extern "C" void vx3_engine_trim(void) {
         resources_free(q);
     }
     cudaSetDevice(cur);
+    {
+        PersistentPlanCache &pc = PersistentPlanCache::get();
+        std::lock_guard<std::mutex> lk(pc.mu);
+        pc.entries.clear();
+    }
 }
 
 // std::vector without the serial zero fill of resize(): the batch builder's threads write every element themselves
@@ -300,6 +305,11 @@ struct vx3_batch {
     bool use_persistent = true;
     FusedPlan fplan;      // fused link + voxel step over spatial blocks for fixed-topology batches (vx3_fused.cuh)
     bool use_fused = true;
+    // CUDA-Graph stretches of the streaming path (advance): VX3_GRAPH_STEPS plain steps captured once, replayed while no
+    // centre-of-mass sampling step falls inside; one executable graph per value of check_stop
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    long long graph_launches[2] = {0, 0};
+    bool graph_failed = false, capturing = false;
     // storage order of a fused batch: model (ABI) index -> device index and back, global indices; empty = identity
     std::vector<int> vperm, lperm, vinv, linv;
     int vdev(size_t ext) const { return vperm.empty() ? (int)ext : vperm[ext]; }
@@ -720,7 +730,8 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.dt_frac = m.opt.dt_frac;
         S.optimal_dt = vx3_model_recommended_dt(&m);
         dy.hot_flags = ((S.vary_temp && S.temp_period > 0) ? SHF_THERMAL : 0) | (S.enable_expansion ? SHF_EXPANSION : 0) | (S.enable_cilia ? SHF_CILIA : 0) |
-                       (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0);
+                       (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0) |
+                       (S.enable_detach ? SHF_DETACH : 0);
         dy.temp_amp = S.temp_amp;
         dy.temp_period = S.temp_period;
         b->vmat_local[s].assign(m.vox_mat, m.vox_mat + m.n_voxels);
@@ -939,7 +950,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         D.hmask = H - 1;
         plan.zeroed(&D.contact, nvox * 3);
         plan.zeroed(&D.cell_cnt, 2 * (size_t)H); // counts, then overflow heads
-        plan.zeroed(&D.cell_items, (size_t)H * VX3_CELL_SLOTS);
+        plan.zeroed(&D.cell_items, (size_t)H * VX3_CELL_SLOTS); // CellItem[H][8]: 128 bytes per bucket
         plan.zeroed(&D.cell_next, nvox);
         plan.zeroed(&D.crec, nvox);
         if (b->any_sticky) { // connected components of the models' link graphs (roots = smallest voxel index), for uf_find
@@ -960,9 +971,33 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             for (size_t v = 0; v < nvox; v++) uf_host[v] = find((int)v);
             plan.upload(&D.uf, uf_host);
         }
-        D.cand_cap = 2048;
-        plan.zeroed(&D.cands, (size_t)D.cand_cap);
-        plan.zeroed(&D.cand_count, 1);
+    }
+    {
+        // per-simulation regions: attach candidates (a power-of-two capacity of at least 4 per voxel, so that the candidate sort
+        // can pad in place) and the failed-link list of EnableDetach (every slot could fail at once)
+        size_t ncand = 0, nfail = 0;
+        for (int s = 0; s < n; s++) {
+            SimC &S = b->simc[s];
+            const vx3_model_desc &m = models[s];
+            bool sticky = false;
+            for (int i = 0; i < m.n_voxel_mats; i++) sticky |= m.voxel_mats[i].sticky != 0;
+            S.cand_off = S.cand_cap = S.fail_off = S.fail_cap = 0;
+            if ((m.opt.enable_collision || m.opt.enable_attach) && sticky && S.lcap > S.nhostlinks) {
+                size_t cap = 256;
+                while (cap < 4 * (size_t)S.nvox + 256) cap <<= 1;
+                S.cand_off = (int)ncand;
+                S.cand_cap = (int)cap;
+                ncand += cap;
+            }
+            if (m.opt.enable_detach && S.lcap > 0) {
+                S.fail_off = (int)nfail;
+                S.fail_cap = S.lcap;
+                nfail += (size_t)S.lcap;
+            }
+        }
+        if (ncand > 0x7FFFFFF0 || nfail > 0x7FFFFFF0) return cleanup(fail(VX3_ERR_INVALID, "batch too large for 32-bit indices"));
+        if (ncand) plan.zeroed(&D.cands, ncand);
+        if (nfail) plan.zeroed(&D.fail_list, nfail);
     }
     // on-chip path for a single small collision-free body: its control words, flags, lane tables and the odd-parity pose
     // buffer are arena slices too
@@ -1034,12 +1069,14 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     return VX3_OK;
 }
 
+static void graph_invalidate(vx3_batch *b);
 extern "C" void vx3_batch_destroy(vx3_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     for (int sd = 0; sd < 2; sd++)
         if (b->halo.side[sd].peer_open) cudaIpcCloseMemHandle(b->halo.side[sd].peer_flag);
+    graph_invalidate(b);
     for (auto &e : b->prof.ev) cudaEventDestroy(e);
     for (auto &e : b->lq_ev)
         if (e) cudaEventDestroy(e);
@@ -1200,12 +1237,12 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
         cudaMemsetAsync(D.cell_cnt, 0, 2 * sizeof(int32_t) * ((size_t)D.hmask + 1), st); // every bucket empty (counts and overflow heads)
         LAUNCH(KC_GRID_BUILD, k_grid_build, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
         LAUNCH(KC_CONTACT, k_contact, cdiv(D.nvox, VX3_CONTACT_WARPS), 32 * VX3_CONTACT_WARPS, D);
-        if (b->any_sticky) LAUNCH(KC_RESOLVE, k_resolve, 1, 1024, D);
     } else if (b->any_detach || b->any_secondary) { // keep the surface flags current (regenerateSurfaceVoxels after a detach / removal)
         LAUNCH(KC_SURFACE, k_surface, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     }
-    if (b->any_detach && D.nlinkslots > 0) LAUNCH(KC_DETACH, k_detach, cdiv(D.nlinkslots, VX3_BLOCK), VX3_BLOCK, D);
-    const bool com = com_step(b, b->hsteps + 1);
+    // attach resolution, then detach, one CTA per simulation (both usually find empty lists and leave at once)
+    if ((b->any_sticky || b->any_detach) && D.nlinkslots > 0) LAUNCH(KC_RESOLVE, k_resolve_detach, b->nsims, 1024, D);
+    const bool com = !b->capturing && com_step(b, b->hsteps + 1);
     if (fused) {
     } else if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
     else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
@@ -1233,6 +1270,60 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     b->hsteps++;
 }
 
+// ---- CUDA-Graph stretches ----
+// The streaming path issues 3-6 kernels per doTimeStep; for small batches the step is launch-bound.  VX3_GRAPH_STEPS plain steps
+// (no centre-of-mass sampling step among them, not the last step of a call) are captured once into a graph and replayed:
+// one driver call per stretch instead of ~100.  Same kernels, same order, same arguments: bit-identical to per-step launches
+// (tests/test_gpu_graph.py).  Off for profiled runs (events around every launch), while the link-pass variant is still being
+// timed, and for slab batches (the halo kernels take the step number as an argument).  VX3_GRAPH=0 disables it.
+#define VX3_GRAPH_STEPS 32
+static void graph_invalidate(vx3_batch *b) {
+    for (int i = 0; i < 2; i++)
+        if (b->graph_exec[i]) {
+            cudaGraphExecDestroy(b->graph_exec[i]);
+            b->graph_exec[i] = nullptr;
+        }
+}
+static bool graph_eligible(const vx3_batch *b) {
+    static const bool enabled = [] {
+        const char *e = getenv("VX3_GRAPH");
+        return !(e && e[0] == '0');
+    }();
+    if (!enabled || b->graph_failed || b->prof.on || b->halo.on) return false;
+    const bool fused = b->use_fused && b->fplan.ok;
+    if (!fused && b->D.nlinkslots > 0 && b->link_queue < 0) return false; // launch_links is still timing its two variants
+    return true;
+}
+static void launch_step(vx3_batch *b, bool check_stop, bool last);
+static bool graph_ensure(vx3_batch *b, bool check_stop) {
+    const int gi = check_stop ? 1 : 0;
+    if (b->graph_exec[gi]) return true;
+    const long long h0 = b->hsteps, l0 = b->launches;
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        b->graph_failed = true;
+        return false;
+    }
+    b->capturing = true;
+    for (int i = 0; i < VX3_GRAPH_STEPS; i++) launch_step(b, check_stop, false);
+    b->capturing = false;
+    const cudaError_t e1 = cudaStreamEndCapture(b->stream, &g);
+    b->graph_launches[gi] = b->launches - l0;
+    b->hsteps = h0;
+    b->launches = l0;
+    cudaError_t e2 = cudaErrorUnknown;
+    if (e1 == cudaSuccess && g) e2 = cudaGraphInstantiate(&b->graph_exec[gi], g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaGetLastError();
+        b->graph_exec[gi] = nullptr;
+        b->graph_failed = true;
+        return false;
+    }
+    return true;
+}
+
 // advance k steps; the on-chip persistent kernel takes the stretches between CoM sampling steps when the batch
 // qualifies (single small collision-free body), the streaming kernels do the rest
 static int advance(vx3_batch *b, long long k, bool check_stop) {
@@ -1247,6 +1338,17 @@ static int advance(vx3_batch *b, long long k, bool check_stop) {
                 if (rc) return fail(VX3_ERR_CUDA, "persistent kernel launch failed");
                 b->hsteps += run;
                 k -= run;
+                continue;
+            }
+        }
+        if (k > VX3_GRAPH_STEPS && graph_eligible(b)) { // a stretch of plain steps, never the last step of the call
+            const long long nxt = next_com_step(b);
+            if ((nxt == 0 || nxt > VX3_GRAPH_STEPS) && graph_ensure(b, check_stop)) {
+                const int gi = check_stop ? 1 : 0;
+                if (cudaGraphLaunch(b->graph_exec[gi], b->stream) != cudaSuccess) return fail(VX3_ERR_CUDA, "cudaGraphLaunch failed");
+                b->hsteps += VX3_GRAPH_STEPS;
+                b->launches += b->graph_launches[gi];
+                k -= VX3_GRAPH_STEPS;
                 continue;
             }
         }
@@ -1475,6 +1577,7 @@ extern "C" int vx3_batch_kernel_stats(vx3_batch *b, int index, char *name, int n
 extern "C" int vx3_batch_set_fused(vx3_batch *b, int on) {
     if (!b) return fail(VX3_ERR_INVALID, "batch is NULL");
     b->use_fused = on != 0;
+    graph_invalidate(b);
     return VX3_OK;
 }
 
@@ -1871,6 +1974,18 @@ extern "C" int vx3_batch_halo_connect_local(vx3_batch *b, int side, vx3_batch *p
 
 // raw centre-of-mass sums of one simulation over its OWNED voxels: sum m*x, m*y, m*z, sum m, sum |pos - initial pos|, count
 // (a decomposed body's ranks add these up before dividing, updateCurrentCenterOfMass VX3_VoxelyzeKernel.cu:477-493)
+extern "C" int vx3_batch_counters(vx3_batch *b, int sim, int64_t *out8) {
+    if (!b || !out8 || sim < 0 || sim >= b->nsims) return fail(VX3_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(b->device));
+    std::vector<SimD> h;
+    int rc = fetch_simd(b, h);
+    if (rc) return rc;
+    const SimD &d = h[sim];
+    const int64_t v[8] = {d.attach_events, d.detach_events, d.link_cnt, d.nsurface, d.cand_peak, d.fail_peak, 0, 0};
+    for (int i = 0; i < 8; i++) out8[i] = v[i];
+    return VX3_OK;
+}
+
 extern "C" int vx3_batch_com_sums(vx3_batch *b, int sim, double *out6) {
     if (!b || sim < 0 || sim >= b->nsims || !out6) return fail(VX3_ERR_INVALID, "bad arguments");
     CK(cudaSetDevice(b->device));

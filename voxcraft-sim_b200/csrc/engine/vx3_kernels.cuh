@@ -1,6 +1,6 @@
 // Streaming step kernels: one launch per phase over the concatenated SoA arrays of the whole batch.
 // Phase order per step = VX3_VoxelyzeKernel::doTimeStep (src/VX3/VX3_VoxelyzeKernel.cu:237-359):
-//   k_links -> [k_grid_build, k_contact, k_resolve] -> [k_detach] -> k_voxels -> [k_signals] -> [k_secondary]
+//   k_links -> [k_grid_build, k_contact] -> [k_resolve_detach] -> k_voxels -> [k_signals] -> [k_secondary]
 //   -> [k_com_partial] -> k_tail
 #pragma once
 #include "vx3_physics.cuh"
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
         LinkRegs L;
         LinkMid mid;
         float dmN = 0, dmP = 0;
-        int state0 = 0;
+        int state0 = 0, hotf = 0;
         mid.small = true;
         if (!live) continue;
         {
@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
             const int status = hot0.z;
             const float dt = __int_as_float(hot1.x);
             const int hot_flags = hot1.y;
+            hotf = hot_flags;
             const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
             // the few end-material values, read up front so that their latencies overlap
             struct { double size, on_after; float cte, dmn; int fixed; } mN, mP;
@@ -274,6 +275,16 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
         *D.lh(3, gc) = make_double2(L.angle2v.x, L.angle2v.y);
         *D.lh(4, gc) = make_double2(L.angle2v.z, L.rest);
         D.lstrain[gc] = make_float4(L.strain, L.maxStrain, L.strainOffset, L.stress);
+        // EnableDetach: a link past its failure strain goes on its simulation's failed-link list; k_resolve_detach takes it off the
+        // voxels after this step's attach phase (gpu_update_detach, VX3_VoxelyzeKernel.cu:946-968, runs after updateAttach)
+        if ((hotf & SHF_DETACH) && mat_failed(lm, L.maxStrain) && !(L.state & LKS_FAILED)) {
+            const SimC &Sd = D.simc[c.w];
+            const int k = atomicAdd(&D.simd[c.w].fail_count, 1);
+            if (k < Sd.fail_cap) {
+                D.fail_list[Sd.fail_off + k] = gc;
+                L.state |= LKS_FAILED;
+            }
+        }
         if (L.state != state0) D.lstate[gc] = L.state; // (regime / velocity-valid / new-link bits rarely change)
         *D.lf(0, gc) = make_double2(o.forceNeg.x, o.forceNeg.y);
         *D.lf(1, gc) = make_double2(o.forceNeg.z, o.momentNeg.x);
@@ -331,7 +342,7 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
         LinkRegs L;
         LinkMid mid;
         float dmN = 0, dmP = 0;
-        int state0 = 0;
+        int state0 = 0, hotf = 0;
         mid.small = true;
         if (live) {
             // ---- every load of this link, all independent ----
@@ -363,6 +374,7 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
             const int status = hot0.z;
             const float dt = __int_as_float(hot1.x);
             const int hot_flags = hot1.y;
+            hotf = hot_flags;
             const int axis = (L.state & LKS_AXIS_MASK) >> LKS_AXIS_SHIFT;
             struct { double size, on_after; float cte, dmn; int fixed; } mN, mP;
             {
@@ -402,6 +414,16 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
         *D.lh(3, gc) = make_double2(L.angle2v.x, L.angle2v.y);
         *D.lh(4, gc) = make_double2(L.angle2v.z, L.rest);
         D.lstrain[gc] = make_float4(L.strain, L.maxStrain, L.strainOffset, L.stress);
+        // EnableDetach: a link past its failure strain goes on its simulation's failed-link list; k_resolve_detach takes it off the
+        // voxels after this step's attach phase (gpu_update_detach, VX3_VoxelyzeKernel.cu:946-968, runs after updateAttach)
+        if ((hotf & SHF_DETACH) && mat_failed(lm, L.maxStrain) && !(L.state & LKS_FAILED)) {
+            const SimC &Sd = D.simc[c.w];
+            const int k = atomicAdd(&D.simd[c.w].fail_count, 1);
+            if (k < Sd.fail_cap) {
+                D.fail_list[Sd.fail_off + k] = gc;
+                L.state |= LKS_FAILED;
+            }
+        }
         if (L.state != state0) D.lstate[gc] = L.state; // (regime / velocity-valid / new-link bits rarely change)
         *D.lf(0, gc) = make_double2(o.forceNeg.x, o.forceNeg.y);
         *D.lf(1, gc) = make_double2(o.forceNeg.z, o.momentNeg.x);
@@ -592,7 +614,6 @@ __device__ __forceinline__ bool sim_collides(const SimC &S) { return S.enable_co
 // before this kernel.  Also writes each voxel's ContactRec and publishes this step's temperature (updateTemperature :219-235).
 __global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v == 0) *D.cand_count = 0;
     if (v >= D.nvox) return;
     const int sim = D.vsim[v];
     const SimC &S = D.simc[sim];
@@ -630,8 +651,13 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
             rec.mat = mat;
             rec.fixed = m.fixed;
             const int slot = atomicAdd(&D.cell_cnt[rec.bucket], 1);
-            if (slot < VX3_CELL_SLOTS) D.cell_items[VX3_CELL_SLOTS * (size_t)rec.bucket + slot] = v;
-            else D.cell_next[v] = atomicExch(&D.cell_ovf[rec.bucket], v + 1) - 1;
+            if (slot < VX3_CELL_SLOTS) {
+                CellItem it;
+                it.x = (float)p.x; it.y = (float)p.y; it.z = (float)p.z;
+                it.v = v;
+                *reinterpret_cast<float4 *>(D.cell_items + VX3_CELL_SLOTS * (size_t)rec.bucket + slot) = make_float4(it.x, it.y, it.z, __int_as_float(it.v));
+            } else
+                D.cell_next[v] = atomicExch(&D.cell_ovf[rec.bucket], v + 1) - 1;
         }
     }
     D.crec[v] = rec;
@@ -670,7 +696,14 @@ __device__ __forceinline__ int uf_find(const Dev &D, int x) {
 __device__ __forceinline__ bool uf_disconnected(const Dev &D, int a, int b) { return D.uf && uf_find(D, a) != uf_find(D, b); }
 
 // is_neighbor (VX3_VoxelyzeKernel.cu:651-680), iterative
+__device__ bool is_neighbor_dfs(const Dev &D, int v1, int v2, int depth);
+// The answer does not depend on the order the paths are tried in; the reference's depth-first order can walk hundreds of
+// 5-link paths before it tries the 2-link one that ends the search, so the short paths are tried first (<= 36 nodes).
 __device__ bool is_neighbor(const Dev &D, int v1, int v2, int depth) {
+    if (depth > 2 && is_neighbor_dfs(D, v1, v2, 2)) return true;
+    return is_neighbor_dfs(D, v1, v2, depth);
+}
+__device__ bool is_neighbor_dfs(const Dev &D, int v1, int v2, int depth) {
     if (v1 == v2) return true;
     if (depth <= 0) return false;
     int sv[6], sl[6], si[6];
@@ -716,6 +749,11 @@ struct ContactSelf {
     ContactRec r;
     bool have_links;
     int vl[6], vo[6]; // own links and their other ends (loaded when the first candidate passes the envelope test)
+    // first cut on the bucket's float positions: nothing farther than the largest possible envelope of this simulation (= the
+    // grid's cell edge) plus the rounding of the two float positions can pass the exact test; voxels of other simulations that
+    // hashed to the bucket fall outside [vlo, vhi)
+    float fx, fy, fz, reach;
+    int vlo, vhi;
 };
 // the 64-byte record in two 256-bit requests (sm_100 LDG.E.ENL2.256) instead of four 128-bit ones: a contact sweep looks at
 // ~90 candidate records per surface voxel, and the phase is bound by the number of memory requests it issues
@@ -735,6 +773,22 @@ __device__ __forceinline__ void contact_self(const Dev &D, int v, ContactSelf &c
     c.v = v;
     c.r = load_crec(D, v);
     c.have_links = false;
+    if (c.r.bucket >= 0) {
+        const SimC &S = D.simc[c.r.sim];
+        c.fx = (float)c.r.px; c.fy = (float)c.r.py; c.fz = (float)c.r.pz;
+        const float edge = (float)(1.0 / S.cell_inv);
+        // float rounding of a coordinate is <= 2^-24 |x|; both positions are within a few cell edges of each other
+        c.reach = edge * 1.001f + 2.4e-7f * (fabsf(c.fx) + fabsf(c.fy) + fabsf(c.fz) + 6.0f * edge);
+        c.vlo = S.voff;
+        c.vhi = S.voff + S.nvox;
+    }
+}
+// conservative: false only when the exact envelope test of contact_candidate must fail as well
+__device__ __forceinline__ bool contact_first_cut(const ContactSelf &c, const float4 it) {
+    const int u = __float_as_int(it.w);
+    if (u < c.vlo || u >= c.vhi || u == c.v) return false;
+    const float dx = it.x - c.fx, dy = it.y - c.fy, dz = it.z - c.fz;
+    return dx * dx + dy * dy + dz * dz <= c.reach * c.reach;
 }
 __device__ __forceinline__ void contact_self_links(const Dev &D, ContactSelf &c) {
     if (c.have_links) return;
@@ -773,22 +827,31 @@ __device__ __forceinline__ bool contact_candidate(const Dev &D, ContactSelf &c, 
         }
     return !(linked && !fresh);
 }
-// All voxels of bucket b, through fn(u): the inline slots (their records are prefetched first: the candidates' loads are
-// independent of each other), then the overflow chain.
 __device__ __forceinline__ void prefetch_crec(const Dev &D, int u) { asm volatile("prefetch.global.L2 [%0];" ::"l"(D.crec + u)); }
-template <class F> __device__ __forceinline__ void bucket_for_each(const Dev &D, int b, F fn) {
+// All voxels of bucket b that survive the first cut, through fn(u): the bucket's inline slots (voxel + float position, two
+// 64-byte halves of one line), then the overflow chain (rare; no float copy, so every chained voxel goes to the exact test).
+#ifndef VX3_CONTACT_FIRSTCUT
+#define VX3_CONTACT_FIRSTCUT 1
+#endif
+template <class F> __device__ __forceinline__ void bucket_for_each(const Dev &D, const ContactSelf &c, int b, F fn) {
     const int n = D.cell_cnt[b];
     if (n == 0) return;
-    unsigned long long i0, i1, i2, i3; // the bucket's 8 inline slots: one 256-bit request (written by atomics in k_grid_build, an earlier kernel)
-    asm("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(i0), "=l"(i1), "=l"(i2), "=l"(i3) : "l"(D.cell_items + VX3_CELL_SLOTS * (size_t)b));
-    const int ids[VX3_CELL_SLOTS] = {(int)(unsigned)i0, (int)(i0 >> 32), (int)(unsigned)i1, (int)(i1 >> 32), (int)(unsigned)i2, (int)(i2 >> 32), (int)(unsigned)i3, (int)(i3 >> 32)};
+    const float4 *items = reinterpret_cast<const float4 *>(D.cell_items + VX3_CELL_SLOTS * (size_t)b);
     const int m = n < VX3_CELL_SLOTS ? n : VX3_CELL_SLOTS;
+    float4 it[VX3_CELL_SLOTS];
 #pragma unroll
     for (int k = 0; k < VX3_CELL_SLOTS; k++)
-        if (k < m) prefetch_crec(D, ids[k]);
+        if (k < m) it[k] = __ldcg(items + k); // written by k_grid_build (an earlier kernel of the step)
+    unsigned pass = 0;
 #pragma unroll
     for (int k = 0; k < VX3_CELL_SLOTS; k++)
-        if (k < m) fn(ids[k]);
+        if (k < m && (!VX3_CONTACT_FIRSTCUT || contact_first_cut(c, it[k]))) pass |= 1u << k;
+#pragma unroll
+    for (int k = 0; k < VX3_CELL_SLOTS; k++) // the survivors' records are independent loads: start them all before the first is used
+        if (pass & (1u << k)) prefetch_crec(D, __float_as_int(it[k].w));
+#pragma unroll
+    for (int k = 0; k < VX3_CELL_SLOTS; k++)
+        if (pass & (1u << k)) fn(__float_as_int(it[k].w));
     if (n > VX3_CELL_SLOTS)
         for (int u = D.cell_ovf[b] - 1; u >= 0; u = D.cell_next[u]) fn(u);
 }
@@ -837,13 +900,13 @@ __device__ __forceinline__ V3 contact_partner(const Dev &D, const SimC &S, int v
     // slots only fill up during the attach phase, so an occupied slot now stays a rejection at this pair's turn
     if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) return f;
     if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) return f; // links are only added during the phase: true now stays true
-    const int slot = atomicAdd(D.cand_count, 1);
-    if (slot < D.cand_cap) {
+    const int slot = atomicAdd(&D.simd[D.vsim[hi]].cand_count, 1);
+    if (slot < S.cand_cap) {
         Cand cd;
         cd.key = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
         cd.info = dir1 | (dir2 << 3) | (axis << 6) | (rev << 8);
         cd._pad = 0;
-        D.cands[slot] = cd;
+        D.cands[S.cand_off + slot] = cd;
     }
     return f;
 }
@@ -875,7 +938,7 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
             for (int dx = -1; dx <= 1; dx++) {
                 const int cx = cs.r.cx + dx, cy = cs.r.cy + dy_, cz = cs.r.cz + dz;
                 const int b = (int)(cell_hash(cs.r.sim, cx, cy, cz) & (unsigned)D.hmask);
-                bucket_for_each(D, b, [&](int u) {
+                bucket_for_each(D, cs, b, [&](int u) {
                     bool fresh;
                     if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) return;
                     if (np < VX3_MAX_PARTNERS) partner[np++] = fresh ? (u | (1 << 30)) : u;
@@ -917,10 +980,25 @@ __device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
 #ifndef VX3_CONTACT_MIN_CTAS
 #define VX3_CONTACT_MIN_CTAS 8 // 64 registers: the phase is a chain of dependent loads per warp, so resident warps are what counts (6 / 8 / 10 / 12 CTAs: 59.9 / 52.4 / 62.2 / 69.6 us on config 4)
 #endif
+#define VX3_MAX_SURVIVORS 192 // voxels that pass the float first cut and are not plain lattice neighbours, per surface voxel
+// the exact envelope test of handle_collision_attachment (VX3_VoxelyzeKernel.cu:682-697) on two ContactRecs, voxel1 = higher index
+__device__ __forceinline__ bool contact_envelope(const ContactRec &rv, int v, const ContactRec &ru, int u) {
+    if (rv.fixed && ru.fixed) return false;
+    const V3 pv(rv.px, rv.py, rv.pz), pu(ru.px, ru.py, ru.pz);
+    const V3 diff = (v > u) ? (pv - pu) : (pu - pv);
+    const double watch = ((v > u) ? (rv.bs + ru.bs) : (ru.bs + rv.bs)) * VX3_COLLISION_ENVELOPE_RADIUS;
+    if (diff.x > watch || diff.x < -watch) return false;
+    if (diff.y > watch || diff.y < -watch) return false;
+    if (diff.z > watch || diff.z < -watch) return false;
+    return !(diff.Length() > watch);
+}
+
 __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) k_contact(Dev D) {
+    __shared__ int sSurv[VX3_CONTACT_WARPS][VX3_MAX_SURVIVORS];
+    __shared__ unsigned char sFrom[VX3_CONTACT_WARPS][VX3_MAX_SURVIVORS]; // which of the 27 cells the survivor was found under
     __shared__ int sList[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS], sSorted[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS];
     __shared__ double sForce[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS][3];
-    __shared__ int sCnt[VX3_CONTACT_WARPS];
+    __shared__ int sCnt[VX3_CONTACT_WARPS][2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int v = blockIdx.x * VX3_CONTACT_WARPS + w;
     if (v >= D.nvox) return; // (whole warps leave together)
@@ -929,24 +1007,87 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
     if (cs.r.bucket < 0) return;
     const SimC &S = D.simc[cs.r.sim];
     SimD &dy = D.simd[cs.r.sim];
-    if (lane == 0) sCnt[w] = 0;
+    if (lane < 2) sCnt[w][lane] = 0;
+    // ---- my own links, one per lane: the far end, and whether the link was made in this step (its contact force is added and
+    // taken back, :827-830) — a plain lattice neighbour is no contact partner (is_neighbor depth 1, :699-703) ----
+    int my_vo = -1, my_fresh = 0;
+    if (lane < 6) {
+        const int li = D.vlinks[6 * (size_t)v + lane];
+        if (li >= 0) {
+            const int2 e = D.lends[li];
+            my_vo = (e.x == v) ? e.y : e.x;
+            my_fresh = (D.lstate[li] & LKS_JUST_CREATED) ? 1 : 0;
+        }
+    }
+    int vo[6];
+    unsigned freshmask = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        vo[i] = __shfl_sync(0xFFFFFFFFu, my_vo, i);
+        freshmask |= (unsigned)__shfl_sync(0xFFFFFFFFu, my_fresh, i) << i;
+    }
     __syncwarp();
+    // ---- stage 1: 27 lanes walk the 27 cells; whoever passes the float first cut and is not a plain neighbour goes on the list ----
+    auto consider = [&](int u) {
+        int tag = u;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if (vo[i] == u) {
+                if (!((freshmask >> i) & 1)) return; // linked, and not in this step: never a partner
+                tag = u | (1 << 30);
+            }
+        const int k = atomicAdd(&sCnt[w][0], 1);
+        if (k < VX3_MAX_SURVIVORS) {
+            sSurv[w][k] = tag;
+            sFrom[w][k] = (unsigned char)lane;
+        }
+    };
     if (lane < 27) {
         const int dx = lane % 3 - 1, dy_ = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
         const int cx = cs.r.cx + dx, cy = cs.r.cy + dy_, cz = cs.r.cz + dz;
         const int b = (int)(cell_hash(cs.r.sim, cx, cy, cz) & (unsigned)D.hmask);
-        bucket_for_each(D, b, [&](int u) {
-            bool fresh;
-            if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) return;
-            const int k = atomicAdd(&sCnt[w], 1);
-            if (k < VX3_MAX_PARTNERS) sList[w][k] = fresh ? (u | (1 << 30)) : u;
-        });
+        const int nb = D.cell_cnt[b];
+        if (nb > 0) {
+            const float4 *items = reinterpret_cast<const float4 *>(D.cell_items + VX3_CELL_SLOTS * (size_t)b);
+            const int m = nb < VX3_CELL_SLOTS ? nb : VX3_CELL_SLOTS;
+            float4 it[VX3_CELL_SLOTS];
+#pragma unroll
+            for (int k = 0; k < VX3_CELL_SLOTS; k++)
+                if (k < m) it[k] = __ldcg(items + k);
+#pragma unroll
+            for (int k = 0; k < VX3_CELL_SLOTS; k++)
+                if (k < m && contact_first_cut(cs, it[k])) consider(__float_as_int(it[k].w));
+            if (nb > VX3_CELL_SLOTS) // overflow chain: no float copy, straight to the exact test
+                for (int u = D.cell_ovf[b] - 1; u >= 0; u = D.cell_next[u])
+                    if (u != v) consider(u);
+        }
     }
     __syncwarp();
-    int n = sCnt[w];
+    int ns = sCnt[w][0];
+    if (ns > VX3_MAX_SURVIVORS) {
+        if (lane == 0) dy.err = VX3_ERR_CAPACITY;
+        ns = VX3_MAX_SURVIVORS;
+    }
+    // ---- stage 2: one lane per survivor: its record, the exact test (same cell-independent arithmetic as the all-pairs sweep) ----
+    for (int i = lane; i < ns; i += 32) {
+        const int tag = sSurv[w][i], u = tag & 0x3FFFFFFF;
+        const ContactRec ur = load_crec(D, u);
+        // two of the 27 cells (or a cell of another simulation) may share a hash bucket: a voxel counts only under its own cell
+        const int from = sFrom[w][i];
+        if (ur.cx != cs.r.cx + from % 3 - 1 || ur.cy != cs.r.cy + (from / 3) % 3 - 1 || ur.cz != cs.r.cz + from / 9 - 1 || ur.sim != cs.r.sim) continue;
+        if (!contact_envelope(cs.r, v, ur, u)) continue;
+        const int k = atomicAdd(&sCnt[w][1], 1);
+        if (k < VX3_MAX_PARTNERS) sList[w][k] = tag;
+    }
+    __syncwarp();
+    int n = sCnt[w][1];
     if (n > VX3_MAX_PARTNERS) {
         if (lane == 0) dy.err = VX3_ERR_CAPACITY;
         n = VX3_MAX_PARTNERS;
+    }
+    if (n == 0) { // nobody near: the pending contact force is zero (the voxel pass cleared it)
+        if (lane == 0 && S.enable_collision) store3(D.contact, v, V3(0, 0, 0));
+        return;
     }
     // rank by partner index (indices are unique)
     for (int i = lane; i < n; i += 32) {
@@ -978,101 +1119,126 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
     }
 }
 
-// Sequential resolution of the attach candidates in canonical (first, second) order: a candidate is accepted
-// only if both facing slots are still empty and the voxels are still not within 5 links at its turn
-// (SURVEY.md A.7).  Creates the link like VX3_Link's device ctor + reset() (VX3_Link.cu:31-70).
-__global__ void __launch_bounds__(1024) k_resolve(Dev D) {
-    __shared__ unsigned long long skey[2048];
-    __shared__ int sinfo[2048];
-    int n = *D.cand_count;
-    if (n == 0) return;
-    if (n > D.cand_cap || n > 2048) {
-        if (threadIdx.x == 0)
-            for (int s = 0; s < D.nsims; s++) D.simd[s].err = VX3_ERR_CAPACITY;
-        n = min(n, min(D.cand_cap, 2048));
+// Attach resolution, then detach, for ONE simulation per CTA.
+//
+// Attach: sequential resolution of the simulation's candidates in canonical (first, second) order: a candidate is accepted
+// only if both facing slots are still empty and the voxels are still not within 5 links at its turn.  Creates
+// the link like VX3_Link's device ctor + reset() (VX3_Link.cu:31-70).  The candidates are sorted by key first: in shared memory
+// up to 2048 of them, in place in the simulation's (power-of-two sized) region of the candidate array beyond that.
+// Detach (gpu_update_detach, VX3_VoxelyzeKernel.cu:946-968): the links the link pass put on the failed list leave their voxels'
+// slots — after the attach phase, as in the reference, so a slot freed now cannot be claimed in the same step.
+#define VX3_RESOLVE_SM 2048
+__device__ void resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, unsigned long long key, int info) {
+    const int hi = (int)(key >> 32), lo = (int)(key & 0xFFFFFFFFu);
+    const int dir1 = info & 7, dir2 = (info >> 3) & 7, axis = (info >> 6) & 3, rev = (info >> 8) & 1;
+    if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) return;
+    if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) return;
+    if (dy.link_cnt >= S.lcap) { dy.err = VX3_ERR_CAPACITY; return; }
+    const VoxMatC &mh = D.vmat_tab[D.vmat[hi]];
+    if (mh.self_lmat < 0) { dy.err = VX3_ERR_INVALID; return; }
+    const int g = S.loff + dy.link_cnt++;
+    const int vneg = rev ? lo : hi, vpos = rev ? hi : lo; // pVNeg/pVPos of VX3_Link(voxelA, dirA, voxelB, dirB)
+    D.vlinks[6 * (size_t)hi + dir1] = g;
+    D.vlinks[6 * (size_t)lo + dir2] = g;
+    D.lends[g] = make_int2(vneg, vpos);
+    D.lmat[g] = mh.self_lmat;
+    D.lc4[g] = make_int4(vneg, vpos, mh.self_lmat, sim);
+    D.lstate[g] = (axis << LKS_AXIS_SHIFT) | LKS_SMALL | LKS_JUST_CREATED | (S.safety_guard << LKS_NEWLINK_SHIFT);
+    const VoxMatC &mn = D.vmat_tab[D.vmat[vneg]], &mp = D.vmat_tab[D.vmat[vpos]];
+    for (int k = 0; k < 4; k++) *D.lh(k, g) = make_double2(0.0, 0.0);
+    *D.lh(4, g) = make_double2(0.0, 0.5 * (base_size_axis(mn, D.tempe[vneg], axis) + base_size_axis(mp, D.tempe[vpos], axis)));
+    for (int k = 0; k < 6; k++) *D.lf(k, g) = make_double2(0.0, 0.0); // the new link's end forces start at zero (VX3_Link::reset)
+    D.lstrain[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float sn = (float)mn.nomSize, sp = (float)mp.nomSize; // transverseArea() with zero strain
+    D.larea[g] = make_float2(0.5f * (sn * sn + sp * sp), 0.0f);
+    dy.attach_events++;
+    if (D.uf) { // the two voxels' trees become one
+        const int ra = uf_find(D, hi), rb = uf_find(D, lo);
+        if (ra != rb) D.uf[ra > rb ? ra : rb] = ra > rb ? rb : ra;
     }
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-        skey[i] = i < n ? D.cands[i].key : ~0ull;
-        sinfo[i] = i < n ? D.cands[i].info : 0;
-    }
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) // bitonic sort
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool up = (i & k) == 0;
-                    if ((skey[i] > skey[ixj]) == up) {
-                        const unsigned long long tk = skey[i]; skey[i] = skey[ixj]; skey[ixj] = tk;
-                        const int ti = sinfo[i]; sinfo[i] = sinfo[ixj]; sinfo[ixj] = ti;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    if (threadIdx.x != 0) return;
-    for (int c = 0; c < n; c++) {
-        const int hi = (int)(skey[c] >> 32), lo = (int)(skey[c] & 0xFFFFFFFFu);
-        const int info = sinfo[c];
-        const int dir1 = info & 7, dir2 = (info >> 3) & 7, axis = (info >> 6) & 3, rev = (info >> 8) & 1;
-        if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) continue;
-        if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) continue;
-        const int sim = D.vsim[hi];
-        const SimC &S = D.simc[sim];
-        SimD &dy = D.simd[sim];
-        if (dy.link_cnt >= S.lcap) { dy.err = VX3_ERR_CAPACITY; continue; }
-        const VoxMatC &mh = D.vmat_tab[D.vmat[hi]];
-        if (mh.self_lmat < 0) { dy.err = VX3_ERR_INVALID; continue; }
-        const int g = S.loff + dy.link_cnt++;
-        const int vneg = rev ? lo : hi, vpos = rev ? hi : lo; // pVNeg/pVPos of VX3_Link(voxelA, dirA, voxelB, dirB)
-        D.vlinks[6 * (size_t)hi + dir1] = g;
-        D.vlinks[6 * (size_t)lo + dir2] = g;
-        D.lends[g] = make_int2(vneg, vpos);
-        D.lmat[g] = mh.self_lmat;
-        D.lc4[g] = make_int4(vneg, vpos, mh.self_lmat, sim);
-        D.lstate[g] = (axis << LKS_AXIS_SHIFT) | LKS_SMALL | LKS_JUST_CREATED | (S.safety_guard << LKS_NEWLINK_SHIFT);
-        const VoxMatC &mn = D.vmat_tab[D.vmat[vneg]], &mp = D.vmat_tab[D.vmat[vpos]];
-        for (int k = 0; k < 4; k++) *D.lh(k, g) = make_double2(0.0, 0.0);
-        *D.lh(4, g) = make_double2(0.0, 0.5 * (base_size_axis(mn, D.tempe[vneg], axis) + base_size_axis(mp, D.tempe[vpos], axis)));
-        for (int k = 0; k < 6; k++) *D.lf(k, g) = make_double2(0.0, 0.0); // the new link's end forces start at zero (VX3_Link::reset)
-        D.lstrain[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float sn = (float)mn.nomSize, sp = (float)mp.nomSize; // transverseArea() with zero strain
-        D.larea[g] = make_float2(0.5f * (sn * sn + sp * sp), 0.0f);
-        dy.attach_events++;
-        if (D.uf) { // the two voxels' trees become one
-            const int ra = uf_find(D, hi), rb = uf_find(D, lo);
-            if (ra != rb) D.uf[ra > rb ? ra : rb] = ra > rb ? rb : ra;
-        }
-        __threadfence_block();
-        if (S.enable_collision) { // take this pair's contact force back in sequence position (:827-830)
-            contact_phase(D, hi, false);
-            contact_phase(D, lo, false);
-        }
+    __threadfence_block();
+    if (S.enable_collision) { // take this pair's contact force back in sequence position (:827-830)
+        contact_phase(D, hi, false);
+        contact_phase(D, lo, false);
     }
 }
 
-// gpu_update_detach (VX3_VoxelyzeKernel.cu:946-968)
-__global__ void __launch_bounds__(VX3_BLOCK) k_detach(Dev D) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= D.nlinkslots) return;
-    const int2 e = D.lends[g];
-    if (e.x < 0) return;
-    const int st = D.lstate[g];
-    if (st & (LKS_DETACHED | LKS_REMOVED)) return;
-    const int sim = D.vsim[e.x];
+__global__ void __launch_bounds__(1024) k_resolve_detach(Dev D) {
+    __shared__ unsigned long long skey[VX3_RESOLVE_SM];
+    __shared__ int sinfo[VX3_RESOLVE_SM];
+    const int sim = blockIdx.x;
     const SimC &S = D.simc[sim];
     SimD &dy = D.simd[sim];
-    if (!S.enable_detach || dy.status != VX3_SIM_RUNNING || dy.diverged || dy.dt == 0) return;
-    const LinkMatC &lm = D.lmat_tab[D.lmat[g]];
-    if (!mat_failed(lm, D.lstrain[g].y)) return;
-    D.lstate[g] = st | LKS_DETACHED;
-    for (int i = 0; i < 6; i++) {
-        if (D.vlinks[6 * (size_t)e.x + i] == g) D.vlinks[6 * (size_t)e.x + i] = -1;
-        if (D.vlinks[6 * (size_t)e.y + i] == g) D.vlinks[6 * (size_t)e.y + i] = -1;
+    int n = S.cand_cap > 0 ? dy.cand_count : 0;
+    const int nfail = S.fail_cap > 0 ? dy.fail_count : 0;
+    if (n == 0 && nfail == 0) return;
+    const bool running = dy.status == VX3_SIM_RUNNING && !dy.diverged && dy.dt != 0;
+    if (threadIdx.x == 0) {
+        if (n > dy.cand_peak) dy.cand_peak = n;
+        if (nfail > dy.fail_peak) dy.fail_peak = nfail;
     }
-    atomicAdd(&dy.detach_events, 1);
+    if (n > S.cand_cap) { // more simultaneous candidates than the region holds: this simulation reports it, the others go on
+        if (threadIdx.x == 0) dy.err = VX3_ERR_CAPACITY;
+        n = S.cand_cap;
+    }
+    if (n > 0 && running) {
+        Cand *cands = D.cands + S.cand_off;
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        const bool in_sm = np2 <= VX3_RESOLVE_SM;
+        if (in_sm) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                skey[i] = i < n ? cands[i].key : ~0ull;
+                sinfo[i] = i < n ? cands[i].info : 0;
+            }
+        } else {
+            for (int i = n + threadIdx.x; i < np2; i += blockDim.x) cands[i].key = ~0ull; // pad in place (np2 <= cand_cap)
+        }
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1) // bitonic sort by (first, second)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                    const int ixj = i ^ j;
+                    if (ixj <= i) continue;
+                    const bool up = (i & k) == 0;
+                    if (in_sm) {
+                        if ((skey[i] > skey[ixj]) == up) {
+                            const unsigned long long tk = skey[i]; skey[i] = skey[ixj]; skey[ixj] = tk;
+                            const int ti = sinfo[i]; sinfo[i] = sinfo[ixj]; sinfo[ixj] = ti;
+                        }
+                    } else if ((cands[i].key > cands[ixj].key) == up) {
+                        const Cand t = cands[i]; cands[i] = cands[ixj]; cands[ixj] = t;
+                    }
+                }
+                __syncthreads();
+            }
+        if (threadIdx.x == 0)
+            for (int c = 0; c < n; c++) {
+                if (in_sm) resolve_accept(D, S, dy, sim, skey[c], sinfo[c]);
+                else resolve_accept(D, S, dy, sim, cands[c].key, cands[c].info);
+            }
+    }
+    __syncthreads(); // detach after attach
+    if (nfail > 0 && running) {
+        const int m = nfail < S.fail_cap ? nfail : S.fail_cap;
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const int g = D.fail_list[S.fail_off + k];
+            const int st = D.lstate[g];
+            if (st & (LKS_DETACHED | LKS_REMOVED)) continue;
+            const int2 e = D.lends[g];
+            D.lstate[g] = (st | LKS_DETACHED) & ~LKS_FAILED;
+            for (int i = 0; i < 6; i++) {
+                if (D.vlinks[6 * (size_t)e.x + i] == g) D.vlinks[6 * (size_t)e.x + i] = -1;
+                if (D.vlinks[6 * (size_t)e.y + i] == g) D.vlinks[6 * (size_t)e.y + i] = -1;
+            }
+            atomicAdd(&dy.detach_events, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        dy.cand_count = 0;
+        dy.fail_count = 0;
+    }
 }
 
 // SecondaryExperiment (VX3_VoxelyzeKernel.cu:336-350): removeVoxels (:365-399) per voxel — a voxel whose material's

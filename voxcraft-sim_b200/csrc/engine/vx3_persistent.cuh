@@ -30,6 +30,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -481,6 +483,42 @@ struct PersistentTables {
     std::vector<int> lk_slot, vx_id, vx_lane, deps, ndeps;
 };
 
+// The block partition and the lane tables are a pure function of the body's lattice and link topology, and a worker
+// that evaluates one batch after another (or re-creates the same body: bench.py's end-to-end loop) sees the same
+// topology again and again: the last few plans are kept, keyed by a 128-bit hash of (coordinates, link ends,
+// voxel link slots, offsets, SM count).  A hit replaces the bisection + table build (~1.5 ms for a 20^3 body).
+struct PersistentPlanCache {
+    struct Entry {
+        unsigned long long h0 = 0, h1 = 0;
+        int grid = 0, block = 0, ro = 0;
+        PersistentTables tb;
+        unsigned long long stamp = 0;
+    };
+    std::mutex mu;
+    std::vector<Entry> entries;
+    unsigned long long clock = 0;
+    static PersistentPlanCache &get() {
+        static PersistentPlanCache c;
+        return c;
+    }
+    static void mix(unsigned long long &h0, unsigned long long &h1, const void *data, size_t bytes) {
+        const unsigned char *p = static_cast<const unsigned char *>(data);
+        size_t i = 0;
+        for (; i + 8 <= bytes; i += 8) {
+            unsigned long long w;
+            memcpy(&w, p + i, 8);
+            h0 = (h0 ^ w) * 0x9E3779B97F4A7C15ull;
+            h0 ^= h0 >> 29;
+            h1 = (h1 + w) * 0xC2B2AE3D27D4EB4Full;
+            h1 ^= h1 >> 31;
+        }
+        for (; i < bytes; i++) {
+            h0 = (h0 ^ p[i]) * 0x100000001B3ull;
+            h1 = (h1 + p[i]) * 0x9E3779B97F4A7C15ull;
+        }
+    }
+};
+
 // recursive coordinate bisection: voxels idx[lo, hi) go to CTAs [c0, c0 + nc).  The selection runs on packed 64-bit keys
 // (coordinate along the cut axis, voxel index) in a scratch array: plain integer compares, no indirection — (coordinate,
 // index) is a strict total order, so the partition is unique whatever nth_element does inside.
@@ -529,6 +567,28 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     if ((long long)V > (long long)G * VX3_PERSIST_MAX_RO || (long long)L > (long long)G * VX3_PERSIST_MAX_BLOCK) return; // cannot fit: skip the partitioning
     if ((V + 15) / 16 < G) G = (V + 15) / 16; // at least ~16 voxels per CTA
     if (G < 1) G = 1;
+    unsigned long long h0 = 0x243F6A8885A308D3ull, h1 = 0x13198A2E03707344ull;
+    const bool use_cache = getenv("VX3_NO_PLAN_CACHE") == nullptr;
+    if (use_cache) {
+        const int hdr[6] = {V, L, voff, loff, G, (int)sizeof(int2)};
+        PersistentPlanCache::mix(h0, h1, hdr, sizeof(hdr));
+        PersistentPlanCache::mix(h0, h1, ixyz + 3 * (size_t)voff, 3 * sizeof(int16_t) * (size_t)V);
+        PersistentPlanCache::mix(h0, h1, lends + loff, sizeof(int2) * (size_t)L);
+        PersistentPlanCache::mix(h0, h1, vlinks + 6 * (size_t)voff, 6 * sizeof(int32_t) * (size_t)V);
+        PersistentPlanCache &pc = PersistentPlanCache::get();
+        std::lock_guard<std::mutex> lk(pc.mu);
+        for (auto &e : pc.entries)
+            if (e.h0 == h0 && e.h1 == h1) {
+                e.stamp = ++pc.clock;
+                tb = e.tb;
+                p.timing = getenv("VX3_PERSIST_TIMING") != nullptr;
+                p.grid = e.grid;
+                p.block = e.block;
+                p.ro = e.ro;
+                p.ok = true;
+                return;
+            }
+    }
     const bool lapt = getenv("VX3_CREATE_TIMING") != nullptr;
     auto lt0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -607,6 +667,19 @@ inline void persistent_plan(PersistentPlan &p, const std::vector<SimC> &simc, bo
     p.block = T;
     p.ro = ro;
     p.ok = true;
+    if (use_cache) {
+        PersistentPlanCache &pc = PersistentPlanCache::get();
+        std::lock_guard<std::mutex> lk(pc.mu);
+        if (pc.entries.size() >= 4) { // evict the least recently used plan
+            size_t old = 0;
+            for (size_t i = 1; i < pc.entries.size(); i++)
+                if (pc.entries[i].stamp < pc.entries[old].stamp) old = i;
+            pc.entries.erase(pc.entries.begin() + old);
+        }
+        PersistentPlanCache::Entry e;
+        e.h0 = h0; e.h1 = h1; e.grid = G; e.block = T; e.ro = ro; e.tb = tb; e.stamp = ++pc.clock;
+        pc.entries.push_back(std::move(e));
+    }
 }
 
 inline int persistent_run(PersistentPlan &p, const Dev &D, cudaStream_t st, long long nsteps, bool check_stop, long long *launches) {

@@ -135,6 +135,11 @@ class Batch:
         self._check(self.lib.vx3_batch_com_sums(self.h, sim, out), "vx3_batch_com_sums")
         return list(out)
 
+    def counters(self, sim=0):
+        out = (C.c_int64 * 8)()
+        self._check(self.lib.vx3_batch_counters(self.h, sim, out), "vx3_batch_counters")
+        return dict(attach=out[0], detach=out[1], links=out[2], cand_peak=out[4], fail_peak=out[5])
+
     def close(self):
         if self.h:
             self.lib.vx3_batch_destroy(self.h)
