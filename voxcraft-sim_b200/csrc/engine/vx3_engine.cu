@@ -1077,6 +1077,12 @@ extern "C" void vx3_batch_destroy(vx3_batch *b) {
     for (int sd = 0; sd < 2; sd++)
         if (b->halo.side[sd].peer_open) cudaIpcCloseMemHandle(b->halo.side[sd].peer_flag);
     graph_invalidate(b);
+    if (b->halo.stream2) {
+        cudaStreamSynchronize(b->halo.stream2);
+        cudaStreamDestroy(b->halo.stream2);
+        cudaEventDestroy(b->halo.ev_step);
+        cudaEventDestroy(b->halo.ev_halo);
+    }
     for (auto &e : b->prof.ev) cudaEventDestroy(e);
     for (auto &e : b->lq_ev)
         if (e) cudaEventDestroy(e);
@@ -1173,9 +1179,12 @@ static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
 // The link pass has two bit-identical variants (k_links: the large-angle branch in place; k_links_deferred: those links
 // deferred to dense per-warp passes); which is faster depends on the batch, so the first streaming steps of a batch time
 // both with CUDA events (one warm-up round, then 3 trials each) and the batch keeps the faster.  VX3_LINK_QUEUE=0/1 pins it.
-static void launch_links(vx3_batch *b) {
+static void launch_links(vx3_batch *b, int tile0 = 0, int tile_end = -1) {
     const Dev &D = b->D;
     cudaStream_t st = b->stream;
+    if (tile_end < 0) tile_end = b->link_tiles;
+    if (tile_end <= tile0) return;
+    const int grid = std::max(1, std::min(tile_end - tile0, b->link_grid));
     int variant = b->link_queue;
     bool trial = false;
     if (variant < 0) {
@@ -1196,11 +1205,11 @@ static void launch_links(vx3_batch *b) {
         }
     }
     if (b->link_smtab) {
-        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<true>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-        else LAUNCH_SM(KC_LINKS, k_links<true>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<true>, grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        else LAUNCH_SM(KC_LINKS, k_links<true>, grid, VX3_LINK_T, 0, D, tile_end, nullptr, nullptr, 0, tile0);
     } else {
-        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<false>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
-        else LAUNCH_SM(KC_LINKS, k_links<false>, b->link_grid, VX3_LINK_T, 0, D, b->link_tiles);
+        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<false>, grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        else LAUNCH_SM(KC_LINKS, k_links<false>, grid, VX3_LINK_T, 0, D, tile_end, nullptr, nullptr, 0, tile0);
     }
     if (trial) {
         cudaEventRecord(b->lq_ev[1], st);
@@ -1211,6 +1220,48 @@ static void launch_links(vx3_batch *b) {
     }
 }
 
+template <class T> static int d2h(vx3_batch *b, std::vector<T> &h, const T *d, size_t off, size_t n);
+// the main stream goes on only when the ghost poses of the previous step are in place
+static void halo_wait(vx3_batch *b) {
+    if (b->halo.on && b->halo.pending) {
+        cudaStreamWaitEvent(b->stream, b->halo.ev_halo, 0);
+        b->halo.pending = false;
+    }
+}
+// first step of a connected slab batch: second stream + events, the spin limit in cycles, and how many leading link tiles are
+// free of ghost ends (the host-side partition stores the face links last)
+static int halo_prepare(vx3_batch *b) {
+    Halo &H = b->halo;
+    if (H.stream2) return VX3_OK;
+    CK(cudaStreamCreateWithFlags(&H.stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&H.ev_step, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&H.ev_halo, cudaEventDisableTiming));
+    double ms = VX3_HALO_TIMEOUT_MS_DEFAULT;
+    if (const char *e = getenv("VX3_HALO_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
+    int khz = 1500000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
+    H.spin_cycles = (long long)(ms * (double)khz);
+    H.face_tile0 = 0;
+    if (b->D.nlinkslots > 0 && !(getenv("VX3_HALO_OVERLAP") && getenv("VX3_HALO_OVERLAP")[0] == '0')) {
+        std::vector<int2> ends;
+        std::vector<int32_t> vflags;
+        int rc;
+        if ((rc = d2h(b, ends, b->D.lends, 0, (size_t)b->D.nlinkslots))) return rc;
+        if ((rc = d2h(b, vflags, b->D.vflags, 0, (size_t)b->D.nvox))) return rc;
+        CK(cudaStreamSynchronize(b->stream));
+        int first_face = b->D.nlinkslots;
+        for (int g = 0; g < b->D.nlinkslots; g++) {
+            if (ends[g].x < 0) continue;
+            if ((vflags[ends[g].x] | vflags[ends[g].y]) & VX3_VOX_GHOST) {
+                first_face = g;
+                break;
+            }
+        }
+        H.face_tile0 = first_face / VX3_LINK_T; // the boundary tile goes with the face range
+    }
+    return VX3_OK;
+}
+
 // last: the final step of a stepping call — the fused kernel then also writes the end forces of interior links to HBM,
 // where a state read-back expects them
 static void launch_step(vx3_batch *b, bool check_stop, bool last) {
@@ -1218,6 +1269,7 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     cudaStream_t st = b->stream;
     const bool fused = b->use_fused && b->fplan.ok;
     if (fused) {
+        halo_wait(b);
         const FusedPlan &f = b->fplan;
         if (f.nface > 0) {
             if (b->link_smtab) LAUNCH_SM(KC_LINKS_FACE, (k_links<true, true>), f.face_grid, VX3_LINK_T, 0, D, f.face_tiles, f.face_slot, f.face_c4, f.nface);
@@ -1231,8 +1283,16 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
             if (last) LAUNCH_SM(KC_FUSED, (k_fused<false, true>), f.grid, VX3_FUSE_T, f.smem, D, a);
             else LAUNCH_SM(KC_FUSED, (k_fused<false, false>), f.grid, VX3_FUSE_T, f.smem, D, a);
         }
-    } else if (D.nlinkslots > 0)
-        launch_links(b);
+    } else if (D.nlinkslots > 0) {
+        if (b->halo.on && b->halo.face_tile0 > 0) { // interior links first: they read no ghost pose, the exchange of the previous step may still be in flight
+            launch_links(b, 0, b->halo.face_tile0);
+            halo_wait(b);
+            launch_links(b, b->halo.face_tile0, b->link_tiles);
+        } else {
+            halo_wait(b);
+            launch_links(b);
+        }
+    }
     if (b->any_collide) {
         cudaMemsetAsync(D.cell_cnt, 0, 2 * sizeof(int32_t) * ((size_t)D.hmask + 1), st); // every bucket empty (counts and overflow heads)
         LAUNCH(KC_GRID_BUILD, k_grid_build, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
@@ -1241,7 +1301,7 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
         LAUNCH(KC_SURFACE, k_surface, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     }
     // attach resolution, then detach, one CTA per simulation (both usually find empty lists and leave at once)
-    if ((b->any_sticky || b->any_detach) && D.nlinkslots > 0) LAUNCH(KC_RESOLVE, k_resolve_detach, b->nsims, 1024, D);
+    if ((b->any_sticky || b->any_detach) && D.nlinkslots > 0) LAUNCH(KC_RESOLVE, k_resolve_detach, b->nsims, VX3_RESOLVE_T, D);
     const bool com = !b->capturing && com_step(b, b->hsteps + 1);
     if (fused) {
     } else if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
@@ -1251,21 +1311,27 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
     else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
-    if (b->halo.on) { // face poses to the neighbour slabs, ghost poses from them (vx3_halo.cuh)
+    if (b->halo.on) { // face poses to the neighbour slabs, ghost poses from them (vx3_halo.cuh), on the second stream
+        Halo &H = b->halo;
         const unsigned int step1 = (unsigned int)(b->hsteps + 1);
         const int parity = (int)(b->hsteps & 1);
+        cudaEventRecord(H.ev_step, b->stream);
+        cudaStreamWaitEvent(H.stream2, H.ev_step, 0);
+        st = H.stream2;
         for (int sd = 0; sd < 2; sd++) {
-            HaloSide &h = b->halo.side[sd];
+            HaloSide &h = H.side[sd];
             if (h.n_send > 0 && (h.peer_open || h.peer_local))
                 LAUNCH(KC_HALO, k_halo_send, std::min(64, cdiv(4 * h.n_send, VX3_HALO_BLOCK)), VX3_HALO_BLOCK, D.pose, h.send_idx, h.n_send, h.peer_buf, h.peer_flag,
                        h.send_count, step1, parity);
         }
         for (int sd = 0; sd < 2; sd++) {
-            HaloSide &h = b->halo.side[sd];
+            HaloSide &h = H.side[sd];
             if (h.n_recv > 0 && (h.peer_open || h.peer_local))
                 LAUNCH(KC_HALO, k_halo_recv, std::min(64, cdiv(4 * h.n_recv, VX3_HALO_BLOCK)), VX3_HALO_BLOCK, D.pose, h.recv_idx, h.n_recv, h.recv_buf, h.recv_flag, step1,
-                       parity, b->halo.err);
+                       parity, H.err, H.spin_cycles, D.simd);
         }
+        cudaEventRecord(H.ev_halo, H.stream2);
+        H.pending = true;
     }
     b->hsteps++;
 }
@@ -1327,6 +1393,12 @@ static bool graph_ensure(vx3_batch *b, bool check_stop) {
 // advance k steps; the on-chip persistent kernel takes the stretches between CoM sampling steps when the batch
 // qualifies (single small collision-free body), the streaming kernels do the rest
 static int advance(vx3_batch *b, long long k, bool check_stop) {
+    if (b->any_ghost && !b->halo.on && k > 0)
+        return fail(VX3_ERR_INVALID, "the batch holds ghost voxels of a decomposed body but its halo exchange is not connected (vx3_batch_halo_connect)");
+    if (b->halo.on) {
+        int rc = halo_prepare(b);
+        if (rc) return rc;
+    }
     while (k > 0) {
         if (b->use_persistent && b->pplan.ok) {
             long long nxt = next_com_step(b); // steps until the next sampling step (it must run on the streaming path)
@@ -1355,6 +1427,7 @@ static int advance(vx3_batch *b, long long k, bool check_stop) {
         launch_step(b, check_stop, k == 1);
         k--;
     }
+    halo_wait(b); // what follows on the main stream (read-backs, the timing event) sees the ghosts of the last step
     return VX3_OK;
 }
 

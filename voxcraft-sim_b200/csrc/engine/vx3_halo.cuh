@@ -12,6 +12,12 @@
 //                received records into my ghost voxels' pose records.
 // Receive buffers are double-buffered by step parity: a neighbour can be at most one step ahead of me (its step s+2 send
 // needs my step s+1 send, which follows my step s receive), so the buffer it overwrites is never the one I still read.
+//
+// OVERLAP.  The exchange of step s runs on a second stream (Halo::stream2) behind an event recorded after the step's voxel
+// pass, while the main stream already evaluates step s+1's INTERIOR links — the links with two owned ends, which read no ghost
+// pose; the host-side partition stores them first (parallel.partition_slabs), so they are one tile range.  The main stream
+// waits for the exchange (Halo::ev_halo) only before the FACE-link range.  Send + wait + scatter are hidden behind the largest
+// kernel of the step.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -20,7 +26,10 @@
 namespace vx3 {
 
 #define VX3_HALO_BLOCK 256
-#define VX3_HALO_SPIN_LIMIT (4000000000ll) // cycles (~2 s): a dead neighbour must not hang the GPU
+// a dead neighbour must not hang the GPU for ever: the wait gives up after this many milliseconds (VX3_HALO_TIMEOUT_MS, default
+// 60 s — a rank can be held up for seconds by paging, JIT or a profiler), marks the batch failed and freezes it (dt = 0: every
+// later step kernel of the stream is a no-op); the host sees VX3_ERR_CUDA at its next step / sync call
+#define VX3_HALO_TIMEOUT_MS_DEFAULT 60000
 
 struct HaloSide {                 // one neighbour
     int n_send = 0, n_recv = 0;
@@ -39,6 +48,11 @@ struct Halo {
     bool on = false;
     HaloSide side[2]; // 0 = lower neighbour, 1 = upper neighbour
     int *err = nullptr; // device flag: spin limit hit
+    cudaStream_t stream2 = nullptr;               // the exchange runs here
+    cudaEvent_t ev_step = nullptr, ev_halo = nullptr; // voxel pass of step s done / ghost poses of step s in place
+    bool pending = false;                         // an exchange is in flight that the main stream has not waited for yet
+    int face_tile0 = -1;                          // link tiles [0, face_tile0) hold no link with a ghost end (-1: not analysed yet)
+    long long spin_cycles = 0;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -69,16 +83,19 @@ __global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(const double *__re
 
 // wait for the neighbour's step number, then ghost poses <- receive buffer
 __global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_recv(double *pose, const int32_t *__restrict__ idx, int n, const double *recv_buf,
-                                                               const unsigned int *recv_flag, unsigned int step1, int parity, int *err) {
+                                                               const unsigned int *recv_flag, unsigned int step1, int parity, int *err, long long spin_cycles,
+                                                               SimD *simd) {
     __shared__ int ok;
     if (threadIdx.x == 0) {
-        ok = 1;
+        ok = *reinterpret_cast<volatile int *>(err) == 0; // sticky: after one failed wait nothing is scattered any more
         const long long t0 = clock64();
-        while (ld_acquire_sys(recv_flag + 32 * parity) < step1) {
-            if (clock64() - t0 > VX3_HALO_SPIN_LIMIT) {
+        while (ok && ld_acquire_sys(recv_flag + 32 * parity) < step1) {
+            if (clock64() - t0 > spin_cycles) {
                 ok = 0;
                 *err = 1;
-                break;
+                simd->err = VX3_ERR_CUDA;
+                simd->dt = 0.0f; // freeze: doTimeStep(0) does nothing (VX3_VoxelyzeKernel.cu:240-241)
+                __threadfence();
             }
         }
     }

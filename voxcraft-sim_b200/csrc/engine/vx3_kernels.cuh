@@ -172,7 +172,7 @@ __device__ __forceinline__ int4 link_c4(const Dev &D, long long g) { return g < 
 // LIST: the pass runs over a list of link slots (list_slot[i], with their index records list_c4[i]) instead of all slots —
 // the pre-pass of the fused step (vx3_fused.cuh), which evaluates only the links across block faces.
 template <bool SMTAB, bool LIST = false>
-__global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles, const int *__restrict__ list_slot = nullptr, const int4 *__restrict__ list_c4 = nullptr, int nlist = 0) {
+__global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles, const int *__restrict__ list_slot = nullptr, const int4 *__restrict__ list_c4 = nullptr, int nlist = 0, int tile0 = 0) {
     __shared__ LinkSmem sm;
     const int tid = threadIdx.x;
     const long long G = gridDim.x;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
         for (int i = tid; i < D.n_lmats * (int)(sizeof(LinkMatC) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.lm)[i] = reinterpret_cast<const int *>(D.lmat_tab)[i];
     }
     __syncthreads();
-    long long tile = blockIdx.x;
+    long long tile = (long long)tile0 + blockIdx.x; // tiles [tile0, ntiles): the whole array, or one of the two ranges of a slab batch (vx3_halo.cuh)
     int gnext;
     int4 c4 = fetch(tile * VX3_LINK_T + tid, gnext);
     for (; tile < ntiles; tile += G) {
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
 // unchanged) and runs the complete update, large-angle branch included, with all lanes busy.  The gathers of a dense pass
 // are uncoalesced, but only the few percent of deferred links pay for that.  Same arithmetic on the same inputs: bit-identical
 // to k_links.  No CTA barrier anywhere.
-template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links_deferred(Dev D, int ntiles) {
+template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links_deferred(Dev D, int ntiles, int tile0 = 0) {
     __shared__ LinkSmem sm;
     __shared__ int sDef[VX3_LINK_T / 32][64];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -315,7 +315,7 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
         for (int i = tid; i < D.n_lmats * (int)(sizeof(LinkMatC) / 4); i += VX3_LINK_T) reinterpret_cast<int *>(sm.lm)[i] = reinterpret_cast<const int *>(D.lmat_tab)[i];
     }
     __syncthreads();
-    long long tile = blockIdx.x;
+    long long tile = (long long)tile0 + blockIdx.x;
     int4 c4 = link_c4(D, tile * VX3_LINK_T + tid);
     int nd = 0; // entries in this warp's queue (warp-uniform)
     for (;;) {
@@ -1128,6 +1128,9 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
 // Detach (gpu_update_detach, VX3_VoxelyzeKernel.cu:946-968): the links the link pass put on the failed list leave their voxels'
 // slots — after the attach phase, as in the reference, so a slot freed now cannot be claimed in the same step.
 #define VX3_RESOLVE_SM 2048
+#ifndef VX3_RESOLVE_T
+#define VX3_RESOLVE_T 256
+#endif
 __device__ void resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, unsigned long long key, int info) {
     const int hi = (int)(key >> 32), lo = (int)(key & 0xFFFFFFFFu);
     const int dir1 = info & 7, dir2 = (info >> 3) & 7, axis = (info >> 6) & 3, rev = (info >> 8) & 1;
@@ -1163,7 +1166,7 @@ __device__ void resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, u
     }
 }
 
-__global__ void __launch_bounds__(1024) k_resolve_detach(Dev D) {
+__global__ void __launch_bounds__(VX3_RESOLVE_T) k_resolve_detach(Dev D) {
     __shared__ unsigned long long skey[VX3_RESOLVE_SM];
     __shared__ int sinfo[VX3_RESOLVE_SM];
     const int sim = blockIdx.x;

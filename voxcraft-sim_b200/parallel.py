@@ -148,6 +148,10 @@ def partition_slabs(desc, world, rank, axis=0):
     if nl and _np.abs(on - op).max() > 1:
         raise ValueError("a link joins two non-adjacent slabs: slabs must be at least one lattice layer thick")
     keep_l = _np.nonzero((on == rank) | (op == rank))[0]
+    # links with two owned ends first, links across a face last: the engine evaluates the first range while the halo exchange of
+    # the previous step is still in flight (csrc/engine/vx3_halo.cuh) — the order of a model's links carries no meaning
+    face_l = on[keep_l] != op[keep_l]
+    keep_l = _np.concatenate([keep_l[~face_l], keep_l[face_l]])
     used = own.copy()
     used[vneg[keep_l]] = True
     used[vpos[keep_l]] = True
