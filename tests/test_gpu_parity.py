@@ -133,8 +133,14 @@ def test_divergence_stops_at_the_reference_step(persistent):
         assert re.steps == ro.steps == done + 1
         assert re.current_time == ro.current_time
         assert np.isnan(re.fitness_score)
+        # doTimeStep returned false BEFORE any voxel moved in that step: the state is the oracle's, on the persistent path too
+        # (its CTAs run up to a step apart; the engine replays a diverged stretch on the streaming path, vx3_engine.cu persist_guard)
+        se, so = eng.state(0), orc.state()
+        compare_states(se, so, KIN, 1e-9, "state of the diverged simulation")
+        np.testing.assert_array_equal(se["link_flags"], so["link_flags"])
         eng.step(10, dt)  # a finished simulation does not move
         assert eng.results()[0].steps == ro.steps
+        util.assert_bit_equal(eng.state(0), se, KIN, "a finished simulation does not move")
     finally:
         lib.vx3_builder_destroy(b)
 

@@ -310,6 +310,12 @@ struct vx3_batch {
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     long long graph_launches[2] = {0, 0};
     bool graph_failed = false, capturing = false;
+    // launch-start snapshot of the arena for the on-chip persistent path (persist_guard): a divergence inside a persistent launch
+    // is re-run on the streaming path, which stops every voxel at the reference's step
+    size_t arena_bytes = 0;
+    unsigned char *snap = nullptr;
+    bool snap_valid = false;
+    long long snap_hsteps = 0;
     // storage order of a fused batch: model (ABI) index -> device index and back, global indices; empty = identity
     std::vector<int> vperm, lperm, vinv, linv;
     int vdev(size_t ext) const { return vperm.empty() ? (int)ext : vperm[ext]; }
@@ -1038,6 +1044,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     int rc;
     if (plan.up_bytes > b->res.hcap) return cleanup(fail(VX3_ERR_INVALID, "internal: staging bound too small"));
     if ((rc = resources_grow_device(b->res, plan.total))) return cleanup(rc);
+    b->arena_bytes = plan.total;
     lap("grow arena");
     for (const ArenaPlan::Item &it : plan.placed) *it.field = b->res.d + it.off;
     for (const ArenaPlan::Item &it : plan.up) {
@@ -1445,15 +1452,67 @@ static int check_device_errors(vx3_batch *b) {
     return VX3_OK;
 }
 
+// ---- divergence inside a persistent launch ----
+// doTimeStep returns false BEFORE any voxel moves in the diverging step (VX3_VoxelyzeKernel.cu:273-281).  The persistent
+// kernel's CTAs run up to one step apart, so when one of them sees a link diverge, others have already integrated that step:
+// step count, time and status are exact, the voxel state is not.  The guard copies the batch's arena aside before a stepping
+// call that will use the persistent path (one device-to-device copy of a few MB per call) and, if the call ends DIVERGED,
+// puts it back and replays the stretch on the streaming path, which shares the physics code bit for bit and stops exactly
+// like the reference.
+static int persist_guard_begin(vx3_batch *b, long long k) {
+    b->snap_valid = false;
+    if (!(b->use_persistent && b->pplan.ok) || k <= 0 || b->arena_bytes == 0) return VX3_OK;
+    if (!b->snap) {
+        if (cudaMalloc((void **)&b->snap, b->arena_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            b->snap = nullptr;
+            return VX3_OK; // no room for the copy: status / step count / time stay exact, the voxel state of a diverged run does not
+        }
+        b->allocs.push_back(b->snap);
+    }
+    CK(cudaMemcpyAsync(b->snap, b->res.d, b->arena_bytes, cudaMemcpyDeviceToDevice, b->stream));
+    b->snap_valid = true;
+    b->snap_hsteps = b->hsteps;
+    return VX3_OK;
+}
+static int fetch_simd(vx3_batch *b, std::vector<SimD> &h);
+static int persist_guard_end(vx3_batch *b, bool check_stop) {
+    if (!b->snap_valid) return VX3_OK;
+    b->snap_valid = false;
+    std::vector<SimD> h;
+    int rc = fetch_simd(b, h);
+    if (rc) return rc;
+    if (h[0].status != VX3_SIM_DIVERGED) return VX3_OK;
+    const long long steps_div = h[0].steps;
+    const long long hsteps_end = b->hsteps;
+    CK(cudaMemcpyAsync(b->res.d, b->snap, b->arena_bytes, cudaMemcpyDeviceToDevice, b->stream));
+    rc = fetch_simd(b, h);
+    if (rc) return rc;
+    const long long replay = steps_div - h[0].steps; // doTimeStep calls up to and including the one that returned false
+    b->hsteps = b->snap_hsteps;
+    const bool up = b->use_persistent;
+    b->use_persistent = false;
+    rc = replay > 0 ? advance(b, replay, check_stop) : VX3_OK;
+    b->use_persistent = up;
+    b->hsteps = hsteps_end; // the host-side call counter keeps counting calls (finished simulations ignore them)
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    return VX3_OK;
+}
+
 extern "C" int vx3_batch_step_dt(vx3_batch *b, int64_t k, float dt) {
     if (!b || k < 0) return fail(VX3_ERR_INVALID, "bad arguments");
     CK(cudaSetDevice(b->device));
     const long long l0 = b->launches;
     set_dt(b, dt);
     CK(cudaEventRecord(b->ev0, b->stream));
-    int rc = advance(b, k, false);
+    int rc = persist_guard_begin(b, k);
+    if (rc) return rc;
+    rc = advance(b, k, false);
     if (rc) return rc;
     CK(cudaEventRecord(b->ev1, b->stream));
+    rc = persist_guard_end(b, false); // (after the timing event: the check reads the simulation's scalars back)
+    if (rc) return rc;
     CK(cudaEventSynchronize(b->ev1));
     CK(cudaGetLastError());
     float ms = 0;
@@ -1510,7 +1569,12 @@ extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history
     // CurStepCount at the start of this run: the loop index j of CUDA_Simulation restarts at 0 with every run, the device
     // counter does not (earlier vx3_batch_step / _run calls)
     std::vector<long long> steps0(b->nsims);
-    for (int s = 0; s < b->nsims; s++) steps0[s] = h[s].steps;
+    for (int s = 0; s < b->nsims; s++) {
+        steps0[s] = h[s].steps;
+        // the CoM sampling cadence is scheduled from the host's call counter and executed on the device's CurStepCount
+        if (h[s].status == VX3_SIM_RUNNING && h[s].steps != b->hsteps)
+            return fail(VX3_ERR_INVALID, "internal: host and device step counters of simulation " + std::to_string(s) + " disagree");
+    }
     std::vector<char> announced_end(b->nsims, 0);
     char line[768];
     if (history) {
@@ -1554,7 +1618,11 @@ extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history
                     todo = std::min(todo, nf);
                 }
         }
+        rc = persist_guard_begin(b, todo);
+        if (rc) return rc;
         rc = advance(b, todo, true);
+        if (rc) return rc;
+        rc = persist_guard_end(b, true);
         if (rc) return rc;
         j += todo;
         rc = fetch_simd(b, h);
