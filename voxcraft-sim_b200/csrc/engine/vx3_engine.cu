@@ -1084,12 +1084,6 @@ extern "C" void vx3_batch_destroy(vx3_batch *b) {
     for (int sd = 0; sd < 2; sd++)
         if (b->halo.side[sd].peer_open) cudaIpcCloseMemHandle(b->halo.side[sd].peer_flag);
     graph_invalidate(b);
-    if (b->halo.stream2) {
-        cudaStreamSynchronize(b->halo.stream2);
-        cudaStreamDestroy(b->halo.stream2);
-        cudaEventDestroy(b->halo.ev_step);
-        cudaEventDestroy(b->halo.ev_halo);
-    }
     for (auto &e : b->prof.ev) cudaEventDestroy(e);
     for (auto &e : b->lq_ev)
         if (e) cudaEventDestroy(e);
@@ -1228,28 +1222,45 @@ static void launch_links(vx3_batch *b, int tile0 = 0, int tile_end = -1) {
 }
 
 template <class T> static int d2h(vx3_batch *b, std::vector<T> &h, const T *d, size_t off, size_t n);
-// the main stream goes on only when the ghost poses of the previous step are in place
+// ghost poses of the previous step: wait for the neighbours' step numbers, scatter their records (k_halo_recv) — on the main
+// stream, placed right before the first kernel that reads a ghost pose
 static void halo_wait(vx3_batch *b) {
-    if (b->halo.on && b->halo.pending) {
-        cudaStreamWaitEvent(b->stream, b->halo.ev_halo, 0);
-        b->halo.pending = false;
+    Halo &H = b->halo;
+    if (!H.on || !H.pending) return;
+    H.pending = false;
+    cudaStream_t st = b->stream;
+    const Dev &D = b->D;
+    const unsigned int step1 = (unsigned int)H.sent_step1;
+    const int parity = H.sent_parity;
+    HaloRecvArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int sd = 0; sd < 2; sd++) {
+        HaloSide &h = H.side[sd];
+        if (h.n_recv > 0 && (h.peer_open || h.peer_local)) {
+            a.idx[sd] = h.recv_idx; a.recv_buf[sd] = h.recv_buf; a.recv_flag[sd] = h.recv_flag;
+            a.n[sd] = h.n_recv;
+            a.nb[sd] = std::min(1024, cdiv(4 * h.n_recv, VX3_HALO_BLOCK));
+        }
+    }
+    if (a.nb[0] + a.nb[1] > 0) {
+        LAUNCH(KC_HALO, k_halo_wait, 1, 32, a, step1, parity, H.err, H.spin_cycles, D.simd);
+        LAUNCH(KC_HALO, k_halo_recv, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, parity, H.err);
     }
 }
-// first step of a connected slab batch: second stream + events, the spin limit in cycles, and how many leading link tiles are
-// free of ghost ends (the host-side partition stores the face links last)
+// first step of a connected slab batch: the spin limit in cycles, and how many leading link tiles are free of ghost ends (the
+// host-side partition stores the face links last)
 static int halo_prepare(vx3_batch *b) {
     Halo &H = b->halo;
-    if (H.stream2) return VX3_OK;
-    CK(cudaStreamCreateWithFlags(&H.stream2, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&H.ev_step, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&H.ev_halo, cudaEventDisableTiming));
+    if (H.face_tile0 >= 0) return VX3_OK;
     double ms = VX3_HALO_TIMEOUT_MS_DEFAULT;
     if (const char *e = getenv("VX3_HALO_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
     int khz = 1500000;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
     H.spin_cycles = (long long)(ms * (double)khz);
     H.face_tile0 = 0;
-    if (b->D.nlinkslots > 0 && !(getenv("VX3_HALO_OVERLAP") && getenv("VX3_HALO_OVERLAP")[0] == '0')) {
+    // two-range link pass (interior links before the receive): opt-in — measured no faster than send-early / receive-late alone
+    // (4 GPUs 359 vs 353, 8 GPUs 216 vs 211 us per step): the second link launch costs what the hidden wait saves
+    if (b->D.nlinkslots > 0 && getenv("VX3_HALO_OVERLAP") && getenv("VX3_HALO_OVERLAP")[0] == '1') {
         std::vector<int2> ends;
         std::vector<int32_t> vflags;
         int rc;
@@ -1318,26 +1329,23 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
     else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
-    if (b->halo.on) { // face poses to the neighbour slabs, ghost poses from them (vx3_halo.cuh), on the second stream
+    if (b->halo.on) { // my face poses to the neighbour slabs (vx3_halo.cuh); their poses are collected before the next face-link pass
         Halo &H = b->halo;
         const unsigned int step1 = (unsigned int)(b->hsteps + 1);
         const int parity = (int)(b->hsteps & 1);
-        cudaEventRecord(H.ev_step, b->stream);
-        cudaStreamWaitEvent(H.stream2, H.ev_step, 0);
-        st = H.stream2;
+        HaloSendArgs a;
+        memset(&a, 0, sizeof(a));
         for (int sd = 0; sd < 2; sd++) {
             HaloSide &h = H.side[sd];
-            if (h.n_send > 0 && (h.peer_open || h.peer_local))
-                LAUNCH(KC_HALO, k_halo_send, std::min(64, cdiv(4 * h.n_send, VX3_HALO_BLOCK)), VX3_HALO_BLOCK, D.pose, h.send_idx, h.n_send, h.peer_buf, h.peer_flag,
-                       h.send_count, step1, parity);
+            if (h.n_send > 0 && (h.peer_open || h.peer_local)) {
+                a.idx[sd] = h.send_idx; a.peer_buf[sd] = h.peer_buf; a.peer_flag[sd] = h.peer_flag; a.count[sd] = h.send_count;
+                a.n[sd] = h.n_send;
+                a.nb[sd] = std::min(1024, cdiv(4 * h.n_send, VX3_HALO_BLOCK));
+            }
         }
-        for (int sd = 0; sd < 2; sd++) {
-            HaloSide &h = H.side[sd];
-            if (h.n_recv > 0 && (h.peer_open || h.peer_local))
-                LAUNCH(KC_HALO, k_halo_recv, std::min(64, cdiv(4 * h.n_recv, VX3_HALO_BLOCK)), VX3_HALO_BLOCK, D.pose, h.recv_idx, h.n_recv, h.recv_buf, h.recv_flag, step1,
-                       parity, H.err, H.spin_cycles, D.simd);
-        }
-        cudaEventRecord(H.ev_halo, H.stream2);
+        if (a.nb[0] + a.nb[1] > 0) LAUNCH(KC_HALO, k_halo_send, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, step1, parity);
+        H.sent_step1 = step1;
+        H.sent_parity = parity;
         H.pending = true;
     }
     b->hsteps++;
@@ -1434,7 +1442,7 @@ static int advance(vx3_batch *b, long long k, bool check_stop) {
         launch_step(b, check_stop, k == 1);
         k--;
     }
-    halo_wait(b); // what follows on the main stream (read-backs, the timing event) sees the ghosts of the last step
+    halo_wait(b); // the ghosts of the last step are in place when the call returns (read-backs, centre of mass)
     return VX3_OK;
 }
 

@@ -8,16 +8,22 @@
 // host involvement and no NCCL call:
 //   k_halo_send  writes my face poses straight into the neighbour's receive buffer (peer memory opened through CUDA IPC,
 //                i.e. plain stores over NVLink), then publishes the step number with a system-scope release;
-//   k_halo_recv  spins (acquire, system scope) on the step number the neighbours published into MY flags, then moves the
-//                received records into my ghost voxels' pose records.
+//   k_halo_wait  spins (acquire, system scope, one thread per side) on the step number the neighbours published into MY flags;
+//   k_halo_recv  then moves the received records into my ghost voxels' pose records.
 // Receive buffers are double-buffered by step parity: a neighbour can be at most one step ahead of me (its step s+2 send
 // needs my step s+1 send, which follows my step s receive), so the buffer it overwrites is never the one I still read.
 //
-// OVERLAP.  The exchange of step s runs on a second stream (Halo::stream2) behind an event recorded after the step's voxel
-// pass, while the main stream already evaluates step s+1's INTERIOR links — the links with two owned ends, which read no ghost
-// pose; the host-side partition stores them first (parallel.partition_slabs), so they are one tile range.  The main stream
-// waits for the exchange (Halo::ev_halo) only before the FACE-link range.  Send + wait + scatter are hidden behind the largest
-// kernel of the step.
+// ORDER.  Everything stays in ONE stream: ... voxel pass(s), k_tail(s), k_halo_send(s) | k_halo_wait(s), k_halo_recv(s), link
+// pass(s+1) ...: a rank's records are on their way as soon as its voxel pass is done, and are collected right before the next
+// link pass.  Two refinements were built and measured on the 4M-voxel body (us per step, 4 / 8 GPUs):
+//   * the exchange on a second stream under the next step's link pass: 462 / -  (worse than 382 / 213 before: the link pass is a
+//     persistent tile loop that fills every CTA slot until it ends, the other stream's kernels do not get on the SMs);
+//   * VX3_HALO_OVERLAP=1: the link pass in two tile ranges — INTERIOR links (two owned ends; stored first by
+//     parallel.partition_slabs) before the receive, FACE links after it, so the transfer hides behind the interior range:
+//     359 / 216 against 353 / 211 without it — the second link launch costs what the hidden wait saves.  Left opt-in.
+// What did pay: exchange kernels as wide as the face (one 16-byte quarter per thread, both sides in one launch; the first
+// version moved a face with 64 CTAs in five dependent rounds) and ONE polling thread per side (hundreds of CTAs polling a
+// system-scope flag slow the whole step down 5x): k_halo 92 -> 54 us of kernel time per step at 8 GPUs, 32 us of it exposed.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -48,9 +54,9 @@ struct Halo {
     bool on = false;
     HaloSide side[2]; // 0 = lower neighbour, 1 = upper neighbour
     int *err = nullptr; // device flag: spin limit hit
-    cudaStream_t stream2 = nullptr;               // the exchange runs here
-    cudaEvent_t ev_step = nullptr, ev_halo = nullptr; // voxel pass of step s done / ghost poses of step s in place
-    bool pending = false;                         // an exchange is in flight that the main stream has not waited for yet
+    bool pending = false;                         // my poses of step sent_step1 are out, the neighbours' are not collected yet
+    unsigned int sent_step1 = 0;
+    int sent_parity = 0;
     int face_tile0 = -1;                          // link tiles [0, face_tile0) hold no link with a ghost end (-1: not analysed yet)
     long long spin_cycles = 0;
 };
@@ -62,48 +68,69 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
     return v;
 }
 
-// my face poses -> the neighbour's receive buffer (peer stores), then the step number
-__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(const double *__restrict__ pose, const int32_t *__restrict__ idx, int n, double *peer_buf,
-                                                               unsigned int *peer_flag, unsigned int *count, unsigned int step1, int parity) {
-    double2 *dst = reinterpret_cast<double2 *>(peer_buf + (size_t)parity * n * 8);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n; i += gridDim.x * blockDim.x) { // one 16-byte quarter per thread: coalesced peer stores
-        const int v = idx[i >> 2];
+// Both neighbours in one launch: the CTAs [0, nb[0]) serve side 0, the rest side 1; one 16-byte quarter of a pose record per
+// thread and ONE quarter per thread (the grid covers the face), so a kernel is a single round of independent accesses.
+struct HaloSendArgs {
+    const int32_t *idx[2];
+    double *peer_buf[2];
+    unsigned int *peer_flag[2], *count[2];
+    int n[2], nb[2];
+};
+struct HaloRecvArgs {
+    const int32_t *idx[2];
+    const double *recv_buf[2];
+    const unsigned int *recv_flag[2];
+    int n[2], nb[2];
+};
+
+// my face poses -> the neighbours' receive buffers (peer stores), then the step number
+__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(const double *__restrict__ pose, HaloSendArgs a, unsigned int step1, int parity) {
+    const int sd = (int)blockIdx.x < a.nb[0] ? 0 : 1;
+    const int blk = sd ? (int)blockIdx.x - a.nb[0] : (int)blockIdx.x;
+    const int n = a.n[sd];
+    double2 *dst = reinterpret_cast<double2 *>(a.peer_buf[sd] + (size_t)parity * n * 8);
+    for (int i = blk * blockDim.x + threadIdx.x; i < 4 * n; i += a.nb[sd] * blockDim.x) { // coalesced peer stores
+        const int v = a.idx[sd][i >> 2];
         dst[i] = reinterpret_cast<const double2 *>(pose + 8 * (size_t)v)[i & 3];
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int arrived = atomicAdd(count, 1u);
-        if (arrived == gridDim.x - 1) { // last CTA: every CTA's stores are fenced
-            *count = 0u;
-            st_release_sys(peer_flag + 32 * parity, step1);
+        const unsigned int arrived = atomicAdd(a.count[sd], 1u);
+        if (arrived == (unsigned int)a.nb[sd] - 1) { // last CTA of this side: every CTA's stores are fenced
+            *a.count[sd] = 0u;
+            st_release_sys(a.peer_flag[sd] + 32 * parity, step1);
         }
     }
 }
 
-// wait for the neighbour's step number, then ghost poses <- receive buffer
-__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_recv(double *pose, const int32_t *__restrict__ idx, int n, const double *recv_buf,
-                                                               const unsigned int *recv_flag, unsigned int step1, int parity, int *err, long long spin_cycles,
-                                                               SimD *simd) {
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        ok = *reinterpret_cast<volatile int *>(err) == 0; // sticky: after one failed wait nothing is scattered any more
-        const long long t0 = clock64();
-        while (ok && ld_acquire_sys(recv_flag + 32 * parity) < step1) {
-            if (clock64() - t0 > spin_cycles) {
-                ok = 0;
-                *err = 1;
-                simd->err = VX3_ERR_CUDA;
-                simd->dt = 0.0f; // freeze: doTimeStep(0) does nothing (VX3_VoxelyzeKernel.cu:240-241)
-                __threadfence();
-            }
+// wait for the neighbours' step numbers: ONE thread per side polls the system-scope flag (hundreds of CTAs polling it, as a first
+// version of the wide receive kernel did, slow the step down 5x: 1.9 ms instead of 0.36 ms on 4 GPUs)
+__global__ void k_halo_wait(HaloRecvArgs a, unsigned int step1, int parity, int *err, long long spin_cycles, SimD *simd) {
+    const int sd = threadIdx.x;
+    if (sd > 1 || a.nb[sd] == 0) return;
+    if (*reinterpret_cast<volatile int *>(err) != 0) return; // sticky: after one failed wait nothing is scattered any more
+    const long long t0 = clock64();
+    while (ld_acquire_sys(a.recv_flag[sd] + 32 * parity) < step1) {
+        if (clock64() - t0 > spin_cycles) {
+            *err = 1;
+            simd->err = VX3_ERR_CUDA;
+            simd->dt = 0.0f; // freeze: doTimeStep(0) does nothing (VX3_VoxelyzeKernel.cu:240-241)
+            __threadfence();
+            return;
         }
     }
-    __syncthreads();
-    if (!ok) return;
-    const double2 *src = reinterpret_cast<const double2 *>(recv_buf + (size_t)parity * n * 8);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n; i += gridDim.x * blockDim.x) {
-        const int v = idx[i >> 2];
+}
+
+// ghost poses <- receive buffers (after k_halo_wait in the same stream)
+__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_recv(double *pose, HaloRecvArgs a, int parity, const int *err) {
+    if (*err) return;
+    const int sd = (int)blockIdx.x < a.nb[0] ? 0 : 1;
+    const int blk = sd ? (int)blockIdx.x - a.nb[0] : (int)blockIdx.x;
+    const int n = a.n[sd];
+    const double2 *src = reinterpret_cast<const double2 *>(a.recv_buf[sd] + (size_t)parity * n * 8);
+    for (int i = blk * blockDim.x + threadIdx.x; i < 4 * n; i += a.nb[sd] * blockDim.x) {
+        const int v = a.idx[sd][i >> 2];
         reinterpret_cast<double2 *>(pose + 8 * (size_t)v)[i & 3] = __ldcv(src + i); // written by another device: never from a stale L1 line
     }
 }
