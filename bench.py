@@ -10,7 +10,9 @@ path shards by independent simulation: every rank steps its o
 no data-path collective, scaling = weak; the only cross-rank traffic is the end-of-run gather of fitness results.
 
 The same run also measures, in the same process group and with the same timing rules, the two multi-GPU workloads
-north_star names, and reports them as sub-objects of the one JSON line (`--skip-extra` leaves them out):
+north_star names, and reports them as sub-objects of the one JSON line (`--skip-extra` leaves them out; each timed region is
+about a second long, so that the one nvidia-smi sample that may fall into it — every query stalls kernel launches for tens of
+milliseconds — does not decide the number):
   "config3"  the vx3_node_worker batch: 512 random 10^3 robots PER GPU (4096 over 8), weak scaling, streaming kernels
   "config5"  ONE 200x200x100 body: undivided at N=1, cut into N x-slabs with halo exchange over peer memory at N>1
              (strong scaling), with a bit-exact self-check of the slab run against the undivided body on rank 0
@@ -549,15 +551,15 @@ def main():
         from voxcraft_sim_b200 import workloads as W
         c3_specs = [W.c3_spec(k) for k in range(args.sims_per_gpu)]
         extras["config3"] = extra_resident("c3", c3_specs, "config3: batch of %d random 10x10x10 robots per GPU (vx3_node_worker fitness eval), %d in all"
-                                           % (args.sims_per_gpu, args.sims_per_gpu * world), "weak", lib, rank, local_rank, world, barrier, 200, 10, 3)
+                                           % (args.sims_per_gpu, args.sims_per_gpu * world), "weak", lib, rank, local_rank, world, barrier, 400, 20, 3)
         c5_specs, c5_label = build_workload("c5", None, 0)
         if world > 1:
             c5_built = [sp.build(lib) for sp in c5_specs]
-            extras["config5"] = run_decomposed(args, lib, c5_built, c5_label, rank, local_rank, world, 4, 2, 50)
+            extras["config5"] = run_decomposed(args, lib, c5_built, c5_label, rank, local_rank, world, 20, 3, 100)
             for b5, _ in c5_built:
                 lib.vx3_builder_destroy(b5)
         else:
-            extras["config5"] = extra_resident("c5", c5_specs, c5_label, "strong", lib, rank, local_rank, world, barrier, 50, 4, 3)
+            extras["config5"] = extra_resident("c5", c5_specs, c5_label, "strong", lib, rank, local_rank, world, barrier, 100, 6, 3)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu:

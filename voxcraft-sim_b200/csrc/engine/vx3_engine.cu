@@ -2121,8 +2121,6 @@ extern "C" int vx3_batch_halo_connect_local(vx3_batch *b, int side, vx3_batch *p
     return VX3_OK;
 }
 
-// raw centre-of-mass sums of one simulation over its OWNED voxels: sum m*x, m*y, m*z, sum m, sum |pos - initial pos|, count
-// (a decomposed body's ranks add these up before dividing, updateCurrentCenterOfMass VX3_VoxelyzeKernel.cu:477-493)
 extern "C" int vx3_batch_counters(vx3_batch *b, int sim, int64_t *out8) {
     if (!b || !out8 || sim < 0 || sim >= b->nsims) return fail(VX3_ERR_INVALID, "bad arguments");
     CK(cudaSetDevice(b->device));
@@ -2135,6 +2133,8 @@ extern "C" int vx3_batch_counters(vx3_batch *b, int sim, int64_t *out8) {
     return VX3_OK;
 }
 
+// raw centre-of-mass sums of one simulation over its OWNED voxels: sum m*x, m*y, m*z, sum m, sum |pos - initial pos|, count
+// (a decomposed body's ranks add these up before dividing, updateCurrentCenterOfMass VX3_VoxelyzeKernel.cu:477-493)
 extern "C" int vx3_batch_com_sums(vx3_batch *b, int sim, double *out6) {
     if (!b || sim < 0 || sim >= b->nsims || !out6) return fail(VX3_ERR_INVALID, "bad arguments");
     CK(cudaSetDevice(b->device));
