@@ -119,3 +119,32 @@ def test_fitness_program_with_all_24_operators():
         eng.close()
     finally:
         lib.vx3_builder_destroy(b)
+
+
+def test_force_field_program_longer_than_128_tokens():
+    """Per-voxel programs may be as long as the reference's 1024-token buffers (VX3_VoxelyzeKernel.cuh:113-119): a 500-token
+    force field (a sum of 80 sinusoids) against the oracle."""
+    from scenarios import forcefield_spec
+    from voxcraft_sim_b200.model import expr_to_tokens
+    spec = forcefield_spec()
+    expr = ("CONST", 0.0)
+    for i in range(80):
+        expr = ("ADD", expr, ("MUL", ("CONST", 2e-5 * (1 + i % 7)), ("SIN", ("MUL", ("VAR", "t"), ("CONST", 40.0 + 13.0 * i)))))
+    assert 128 < len(expr_to_tokens(expr)) <= 1024
+    spec.set_program(abi.PROG_FORCE_Y, expr)
+    lib = util.load_engine()
+    b, d = spec.build(lib)
+    try:
+        orc0 = OracleSim(d)
+        dt = float(np.float32(0.9 * orc0.recommended_dt()))
+        exact, envs = libm_envelope(d, 400, dt, [400], keys=FLOAT_KEYS)
+        for persistent in (True, False):
+            eng = EngineBatch([d])
+            eng.set_profiling(False, use_persistent=persistent)
+            eng.step(400, dt)
+            se = eng.state(0)
+            gate_within_envelope(se, exact[0], envs[0], FLOAT_KEYS, "long force field, persistent=%s" % persistent)
+            np.testing.assert_array_equal(se["vox_flags"], exact[0]["vox_flags"])
+            eng.close()
+    finally:
+        lib.vx3_builder_destroy(b)

@@ -29,7 +29,7 @@ namespace vx3 {
 #define LKS_NEWLINK_SHIFT VX3_LINKSTATE_NEWLINK_SHIFT
 #define LKS_PUBLIC_MASK (~(LKS_AXIS_MASK | LKS_JUST_CREATED | LKS_FAILED))
 
-#define VX3_DEV_MAX_TOKENS 128 // per-voxel programs (force field, attach conditions) on the device evaluator
+#define VX3_DEV_MAX_TOKENS 128 // per-voxel programs (force field, attach conditions): up to this many tokens run in the small evaluator frame
 #define VX3_MAX_PARTNERS 96    // contact partners of one voxel inside the collision envelope
 #define VX3_CELL_SLOTS 8       // voxels a grid bucket holds inline (one 32-byte sector)
 

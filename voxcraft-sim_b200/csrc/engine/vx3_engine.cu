@@ -396,7 +396,6 @@ static int validate_model(const vx3_model_desc &m, int idx) {
     for (int s = 0; s < VX3_PROG_COUNT; s++) {
         if (m.prog[s].n < 0 || m.prog[s].n > VX3_MAX_TOKENS) return bad("token program too long");
         if (m.prog[s].n > 0 && !m.prog[s].tok) return bad("token program pointer missing");
-        if (s >= VX3_PROG_FORCE_X && m.prog[s].n > VX3_DEV_MAX_TOKENS) return bad("per-voxel token programs are limited to 128 tokens");
     }
     return VX3_OK;
 }
@@ -1043,8 +1042,12 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     lap("arena layout");
     int rc;
     if (plan.up_bytes > b->res.hcap) return cleanup(fail(VX3_ERR_INVALID, "internal: staging bound too small"));
-    if ((rc = resources_grow_device(b->res, plan.total))) return cleanup(rc);
+    // a batch on the persistent path keeps a launch-start copy of its arena (persist_guard) in the upper half of the same
+    // allocation: it comes out of the per-process cache like the arena itself (no cudaMalloc / cudaFree per batch)
+    const size_t arena_al = (plan.total + 255) / 256 * 256;
+    if ((rc = resources_grow_device(b->res, b->pplan.ok ? 2 * arena_al : plan.total))) return cleanup(rc);
     b->arena_bytes = plan.total;
+    b->snap = b->pplan.ok ? reinterpret_cast<unsigned char *>(b->res.d) + arena_al : nullptr;
     lap("grow arena");
     for (const ArenaPlan::Item &it : plan.placed) *it.field = b->res.d + it.off;
     for (const ArenaPlan::Item &it : plan.up) {
@@ -1247,6 +1250,27 @@ static void halo_wait(vx3_batch *b) {
         LAUNCH(KC_HALO, k_halo_recv, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, parity, H.err);
     }
 }
+// CUDA loads a kernel's code at its first launch (lazy module loading), and that load can wait for the kernels already running
+// on the device.  A slab's k_halo_wait spins until its neighbour has sent — if the neighbour is driven by this process and its
+// first launch of some kernel has to load it, the two wait for each other until the spin limit (seen as a failed
+// vx3_batch_sync in tests/test_decomposition.py with two slabs on one device).  So every kernel of the step path is loaded before
+// the first exchange.
+static void preload_step_kernels() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const void *ks[] = {(const void *)k_links<true>, (const void *)k_links<false>, (const void *)k_links_deferred<true>, (const void *)k_links_deferred<false>,
+                            (const void *)k_links<true, true>, (const void *)k_links<false, true>, (const void *)k_voxels<true>, (const void *)k_voxels<false>,
+                            (const void *)k_fused<true, false>, (const void *)k_fused<true, true>, (const void *)k_fused<false, false>, (const void *)k_fused<false, true>,
+                            (const void *)k_tail_light, (const void *)k_tail, (const void *)k_com_partial, (const void *)k_sim_update, (const void *)k_set_dt,
+                            (const void *)k_halo_send, (const void *)k_halo_wait, (const void *)k_halo_recv, (const void *)k_surface, (const void *)k_secondary,
+                            (const void *)k_signals, (const void *)k_step_cap};
+        for (const void *k : ks) {
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, k) != cudaSuccess) cudaGetLastError();
+        }
+    });
+}
+
 // first step of a connected slab batch: the spin limit in cycles, and how many leading link tiles are free of ghost ends (the
 // host-side partition stores the face links last)
 static int halo_prepare(vx3_batch *b) {
@@ -1469,15 +1493,7 @@ static int check_device_errors(vx3_batch *b) {
 // like the reference.
 static int persist_guard_begin(vx3_batch *b, long long k) {
     b->snap_valid = false;
-    if (!(b->use_persistent && b->pplan.ok) || k <= 0 || b->arena_bytes == 0) return VX3_OK;
-    if (!b->snap) {
-        if (cudaMalloc((void **)&b->snap, b->arena_bytes) != cudaSuccess) {
-            cudaGetLastError();
-            b->snap = nullptr;
-            return VX3_OK; // no room for the copy: status / step count / time stay exact, the voxel state of a diverged run does not
-        }
-        b->allocs.push_back(b->snap);
-    }
+    if (!(b->use_persistent && b->pplan.ok) || k <= 0 || b->arena_bytes == 0 || !b->snap) return VX3_OK;
     CK(cudaMemcpyAsync(b->snap, b->res.d, b->arena_bytes, cudaMemcpyDeviceToDevice, b->stream));
     b->snap_valid = true;
     b->snap_hsteps = b->hsteps;
@@ -2042,6 +2058,7 @@ static const size_t kHaloFlagBytes = 256;
 
 extern "C" int vx3_batch_halo_setup(vx3_batch *b, int side, int n_send, const int32_t *send_vox, int n_recv, const int32_t *recv_vox) {
     if (!b || side < 0 || side > 1 || n_send < 0 || n_recv < 0) return fail(VX3_ERR_INVALID, "bad arguments");
+    preload_step_kernels();
     if (b->nsims != 1) return fail(VX3_ERR_INVALID, "halo exchange applies to a batch of ONE decomposed body");
     if (b->any_collide) return fail(VX3_ERR_INVALID, "halo exchange: collisions / attach are not supported across slabs");
     CK(cudaSetDevice(b->device));

@@ -444,7 +444,10 @@ __device__ __forceinline__ void prog_vars(const SimC &S, const SimD &dy, double 
 __device__ __forceinline__ double eval_slot(const Dev &D, const SimC &S, int slot, const double *vars, double dflt) {
     if (S.prog_n[slot] <= 0) return dflt; // "tag absent": defined result (vx3_abi.h, vx3_program)
     bool ok;
-    return mt_eval<VX3_DEV_MAX_TOKENS>(D.tokens + S.prog_off[slot], S.prog_n[slot], vars, &ok);
+    // the evaluator keeps one value per token (VX3_MathTree.h:52): programs of up to 128 tokens — all the reference's demos — run in
+    // a 1 KB frame, longer ones (the reference allows 1024, VX3_VoxelyzeKernel.cuh:113-119) in the 8 KB one
+    if (S.prog_n[slot] <= VX3_DEV_MAX_TOKENS) return mt_eval<VX3_DEV_MAX_TOKENS>(D.tokens + S.prog_off[slot], S.prog_n[slot], vars, &ok);
+    return mt_eval<VX3_MAX_TOKENS>(D.tokens + S.prog_off[slot], S.prog_n[slot], vars, &ok);
 }
 
 // gpu_update_voxels (VX3_VoxelyzeKernel.cu:582-623) -> VX3_Voxel::timeStep
