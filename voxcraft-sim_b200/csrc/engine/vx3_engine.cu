@@ -768,11 +768,27 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.nchunks = (int)chunks.size() - S.chunk_off;
         dy.status = VX3_SIM_RUNNING;
         dy.link_cnt = m.n_links;
-        // collision grid cell: at least the largest possible collision envelope (2 * 0.625 * baseSizeAverage)
-        double maxT = fabs(m.opt.temp_amplitude);
+        // collision grid cell: at least the largest collision envelope that can occur, 2 * 0.625 * baseSizeAverage at the
+        // temperature that makes a voxel largest.  Temperatures stay in [-|A|, 0], or [-|A|, |A|] with EnableExpansion
+        // (gpu_update_temperature, VX3_VoxelyzeKernel.cu:640-645), widened by whatever the model starts with; a material grows
+        // with cte * T, so a positive CTE without EnableExpansion never exceeds the nominal size — the cell is then 1.25 voxels
+        // instead of 1.5 and the 27-cell sweep sees 42 % less volume
+        double t_lo = 0, t_hi = 0;
+        if (m.opt.vary_temp_enabled && m.opt.temp_period > 0) {
+            t_lo = -fabs(m.opt.temp_amplitude);
+            t_hi = m.opt.enable_expansion ? fabs(m.opt.temp_amplitude) : 0.0;
+        }
         if (m.temp && (m.opt.enable_collision || m.opt.enable_attach))
-            for (int i = 0; i < m.n_voxels; i++) maxT = std::max(maxT, (double)fabsf(m.temp[i]));
-        const double cell = 2 * VX3_COLLISION_ENVELOPE_RADIUS * sb[s].maxSize * (1 + maxT * sb[s].maxCte) * (1 + 1e-6);
+            for (int i = 0; i < m.n_voxels; i++) {
+                t_lo = std::min(t_lo, (double)m.temp[i]);
+                t_hi = std::max(t_hi, (double)m.temp[i]);
+            }
+        double grow = 1.0;
+        for (int i = 0; i < m.n_voxel_mats; i++) {
+            const double cte = m.voxel_mats[i].alphaCTE;
+            grow = std::max(grow, std::max(1 + t_lo * cte, 1 + t_hi * cte));
+        }
+        const double cell = 2 * VX3_COLLISION_ENVELOPE_RADIUS * sb[s].maxSize * grow * (1 + 1e-5);
         S.cell_inv = cell > 0 ? 1.0 / cell : 1.0;
     }
 
