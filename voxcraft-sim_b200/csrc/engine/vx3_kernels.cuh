@@ -84,7 +84,11 @@ __device__ __forceinline__ V3 load_linmom(const Dev &D, int v) {
 // Tried and dropped, each measured slower: cp.async staging of the next links' records (the LSU write wavefronts of the
 // gathers throttle the MIO queue), L1/L2 software prefetch, a class-sorted processing order that makes warps uniform in
 // small/large-angle mode (−34 % instructions, but the indirection costs more in sector efficiency than it saves), and
-// storing end forces by receiving voxel (streams for the voxel pass, but leaves partially written sectors -> ECC RMW).
+// storing end forces by receiving voxel (streams for the voxel pass, but leaves partially written sectors -> ECC RMW), and
+// (round 2) software pipelining in registers — every load of link i+1 issued at the top of iteration i, the index record two
+// links ahead: 168 registers, 3 CTAs per SM instead of 4, and 20-26 % slower (config 3 110 vs 92 us per step, config 5 link pass
+// 942 vs 746 us): the pass is bound by dependent fp64 issue at register-limited occupancy, and warps, not hidden loads, are
+// what it is short of.
 #define VX3_SM_VMATS 32
 #define VX3_SM_LMATS 64
 struct LinkSmem {
