@@ -516,9 +516,7 @@ def main():
             m = d.contents
             h2d += m.n_voxels * (3 * 2 + 4 + 24 + 32 + 24 + 24 + 4 + 4 + 8 + 24 + 4) + m.n_links * (4 * 4 + 72 + 4 * 4 + 4 + 4 + 8 + 12)
         d2h = sum(C.sizeof(type(res[0])) for _ in res) + sum(d.contents.n_voxels * (48 + 4) for d in descs)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        def e2e_cycle():
             bt = Batch(descs, fma=fma, device=local_rank)
             if args.no_persistent:
                 bt.set_profiling(False, use_persistent=False)
@@ -526,6 +524,12 @@ def main():
             bt.results()
             bt.positions(None)  # every simulation's init_pos / pos / matid (SavePositionOfAllVoxels), one D2H
             bt.close()
+        for _ in range(min(Wm, 3)):  # warm-up: the second arena + pinned staging buffer of the resource cache are allocated once
+            e2e_cycle()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_cycle()
         barrier()
         e2e_t = time.perf_counter() - t0
         e2e = {"t": e2e_t, "steps": e2e_steps, "h2d": h2d, "d2h": d2h}

@@ -69,8 +69,8 @@ if __name__ == "__main__":
     lib.vx3_builder_destroy(b)
     run("ragged", 100, persistent=False, fused=True)
     run("act333", 100, persistent=False)
-    run("pile_sticky", 400, persistent=False)
-    run("detach", 200, persistent=False)
+    run("pile_sticky", 2500, persistent=False)
+    run("detach", 1500, persistent=False)
     run("sig_body", 100, persistent=False)
     run("secondary", 200, persistent=False)
     # the halo exchange is NOT run here: compute-sanitizer serialises kernels, and a receive kernel that spins for a send
