@@ -278,8 +278,12 @@ typedef struct vx3_run_opts {
     int32_t emit_history;   /* honour RecordStepSize and stream frames to the callback  */
 } vx3_run_opts;
 
-/* History sink: receives the bytes the reference writes with device printf
- * (src/VX3/VX3_SimulationManager.cu:40-50,70-114).  Called on the caller's thread. */
+/* History sink: receives, byte for byte, what the reference's CUDA_Simulation kernel writes with device printf
+ * (src/VX3/VX3_SimulationManager.cu:11-121): the "Simulation %d runs" line (:25), the {{{setting}}} header when
+ * RecordStepSize > 0 (:40-50), "real_stepsize: ..." (:56-58; preceded / followed by recommendedTimeStep's "WARNING: No links."
+ * for a model without links), the voxel / link frames (:70-114), "Diverged" (:65-69) and the "ends" line (:118-119).  The
+ * device index in those lines is the batch's device, the simulation index the model's position in the batch.  Called on the
+ * caller's thread. */
 typedef void (*vx3_history_cb)(void *user, int sim, const char *bytes, size_t n);
 
 typedef struct vx3_batch vx3_batch; /* opaque: one batch = one device = one stream */
