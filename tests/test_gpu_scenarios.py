@@ -148,3 +148,42 @@ def test_force_field_program_longer_than_128_tokens():
             eng.close()
     finally:
         lib.vx3_builder_destroy(b)
+
+
+def test_mixed_batch_of_colliding_simulations():
+    """Several collision / attach / detach simulations in ONE batch (the worker's normal job): every simulation has its own
+    candidate and failed-link lists and its own resolve CTA, so each must equal its oracle — topology bit-exact — exactly as when
+    it runs alone."""
+    names = ["pile_sticky", "detach", "c4small", "touch", "pile", "secondary"]
+    lib = util.load_engine()
+    built = []
+    try:
+        for n in names:
+            sc = scenario(n)
+            spec = sc["spec"]()
+            b, d = spec.build(lib)
+            if sc["link_capacity"]:
+                d.contents.link_capacity = sc["link_capacity"]
+            built.append((b, d, sc))
+        eng = EngineBatch([d for _, d, _ in built])
+        orcs = [OracleSim(d) for _, d, _ in built]
+        for chunk in range(4):
+            eng.step(400)
+            for i, (o, (_, d, sc)) in enumerate(zip(orcs, built)):
+                assert o.step(400, -1.0) == 400
+                se, so = eng.state(i, link_cap=sc["link_capacity"] or None), o.state()
+                what = "%s in a mixed batch after %d steps" % (names[i], 400 * (chunk + 1))
+                assert se["link_vneg"].shape == so["link_vneg"].shape, what
+                for k in INT_KEYS:
+                    np.testing.assert_array_equal(se[k], so[k], err_msg="%s: %s" % (what, k))
+                gate_within_envelope(se, so, None, ["pos", "orient"], what, rel_floor=1e-8)
+                re, ro = eng.results()[i], o.result()
+                assert (re.num_links, re.collision_count, re.steps) == (ro.num_links, ro.collision_count, ro.steps), what
+                c = eng.counters(i)
+                oc = o.counts()
+                assert (c["attach"], c["detach"]) == (oc["attach"], oc["detach"]), what
+        assert sum(o.counts()["attach"] for o in orcs) > 0 and sum(o.counts()["detach"] for o in orcs) > 0
+        eng.close()
+    finally:
+        for b, _, _ in built:
+            lib.vx3_builder_destroy(b)

@@ -1245,12 +1245,11 @@ template <class T> static int d2h(vx3_batch *b, std::vector<T> &h, const T *d, s
 // stream, placed right before the first kernel that reads a ghost pose
 static void halo_wait(vx3_batch *b) {
     Halo &H = b->halo;
-    if (!H.on || !H.pending) return;
+    if (!H.on) return;
+    if (!H.pending && !b->capturing) return; // (inside a captured stretch every step collects: the kernels themselves know whether there is anything new)
     H.pending = false;
     cudaStream_t st = b->stream;
     const Dev &D = b->D;
-    const unsigned int step1 = (unsigned int)H.sent_step1;
-    const int parity = H.sent_parity;
     HaloRecvArgs a;
     memset(&a, 0, sizeof(a));
     for (int sd = 0; sd < 2; sd++) {
@@ -1262,8 +1261,8 @@ static void halo_wait(vx3_batch *b) {
         }
     }
     if (a.nb[0] + a.nb[1] > 0) {
-        LAUNCH(KC_HALO, k_halo_wait, 1, 32, a, step1, parity, H.err, H.spin_cycles, D.simd);
-        LAUNCH(KC_HALO, k_halo_recv, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, parity, H.err);
+        LAUNCH(KC_HALO, k_halo_wait, 1, 32, a, H.seq, H.err, H.spin_cycles, D.simd);
+        LAUNCH(KC_HALO, k_halo_recv, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, H.seq, H.err);
     }
 }
 // CUDA loads a kernel's code at its first launch (lazy module loading), and that load can wait for the kernels already running
@@ -1371,8 +1370,6 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
     if (b->halo.on) { // my face poses to the neighbour slabs (vx3_halo.cuh); their poses are collected before the next face-link pass
         Halo &H = b->halo;
-        const unsigned int step1 = (unsigned int)(b->hsteps + 1);
-        const int parity = (int)(b->hsteps & 1);
         HaloSendArgs a;
         memset(&a, 0, sizeof(a));
         for (int sd = 0; sd < 2; sd++) {
@@ -1383,9 +1380,7 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
                 a.nb[sd] = std::min(1024, cdiv(4 * h.n_send, VX3_HALO_BLOCK));
             }
         }
-        if (a.nb[0] + a.nb[1] > 0) LAUNCH(KC_HALO, k_halo_send, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, step1, parity);
-        H.sent_step1 = step1;
-        H.sent_parity = parity;
+        if (a.nb[0] + a.nb[1] > 0) LAUNCH(KC_HALO, k_halo_send, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, H.seq);
         H.pending = true;
     }
     b->hsteps++;
@@ -1396,7 +1391,7 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
 // (no centre-of-mass sampling step among them, not the last step of a call) are captured once into a graph and replayed:
 // one driver call per stretch instead of ~100.  Same kernels, same order, same arguments: bit-identical to per-step launches
 // (tests/test_gpu_graph.py).  Off for profiled runs (events around every launch), while the link-pass variant is still being
-// timed, and for slab batches (the halo kernels take the step number as an argument).  VX3_GRAPH=0 disables it.
+// timed.  Slab batches qualify too: their exchange kernels take the step number from device memory.  VX3_GRAPH=0 disables it.
 #define VX3_GRAPH_STEPS 32
 static void graph_invalidate(vx3_batch *b) {
     for (int i = 0; i < 2; i++)
@@ -1410,7 +1405,10 @@ static bool graph_eligible(const vx3_batch *b) {
         const char *e = getenv("VX3_GRAPH");
         return !(e && e[0] == '0');
     }();
-    if (!enabled || b->graph_failed || b->prof.on || b->halo.on) return false;
+    if (!enabled || b->graph_failed || b->prof.on) return false;
+    // two slabs driven by ONE host thread (the same-process test set-up) cannot run ahead of each other by a whole stretch: the
+    // first one's receive would spin while the second one's graph is still being instantiated
+    if (b->halo.on && (b->halo.side[0].peer_local || b->halo.side[1].peer_local)) return false;
     const bool fused = b->use_fused && b->fplan.ok;
     if (!fused && b->D.nlinkslots > 0 && b->link_queue < 0) return false; // launch_links is still timing its two variants
     return true;
@@ -1475,6 +1473,7 @@ static int advance(vx3_batch *b, long long k, bool check_stop) {
                 if (cudaGraphLaunch(b->graph_exec[gi], b->stream) != cudaSuccess) return fail(VX3_ERR_CUDA, "cudaGraphLaunch failed");
                 b->hsteps += VX3_GRAPH_STEPS;
                 b->launches += b->graph_launches[gi];
+                b->halo.pending = b->halo.on; // the stretch ends with a send
                 k -= VX3_GRAPH_STEPS;
                 continue;
             }
@@ -2097,6 +2096,7 @@ extern "C" int vx3_batch_halo_setup(vx3_batch *b, int side, int n_send, const in
     h.n_send = n_send;
     h.n_recv = n_recv;
     if (!b->halo.err && (rc = b->alloc(&b->halo.err, 1))) return rc;
+    if (!b->halo.seq && (rc = b->alloc(&b->halo.seq, 4))) return rc;
     CK(cudaStreamSynchronize(b->stream));
     return VX3_OK;
 }
@@ -2129,6 +2129,7 @@ extern "C" int vx3_batch_halo_connect(vx3_batch *b, int side, const void *peer_h
     h.peer_open = true;
     b->halo.on = true;
     b->use_persistent = false;
+    graph_invalidate(b);
     return VX3_OK;
 }
 
@@ -2151,6 +2152,7 @@ extern "C" int vx3_batch_halo_connect_local(vx3_batch *b, int side, vx3_batch *p
     h.peer_local = true;
     b->halo.on = true;
     b->use_persistent = false;
+    graph_invalidate(b);
     return VX3_OK;
 }
 

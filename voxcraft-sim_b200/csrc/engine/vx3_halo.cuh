@@ -54,9 +54,10 @@ struct Halo {
     bool on = false;
     HaloSide side[2]; // 0 = lower neighbour, 1 = upper neighbour
     int *err = nullptr; // device flag: spin limit hit
-    bool pending = false;                         // my poses of step sent_step1 are out, the neighbours' are not collected yet
-    unsigned int sent_step1 = 0;
-    int sent_parity = 0;
+    bool pending = false;                         // my poses are out, the neighbours' are not collected yet (host-side hint only)
+    // device-side sequence numbers {sent, collected, send arrivals, receive arrivals}: the exchange kernels take the step number from here, not from
+    // a kernel argument, so that a stretch of steps can be captured once in a CUDA Graph and replayed
+    unsigned int *seq = nullptr;
     int face_tile0 = -1;                          // link tiles [0, face_tile0) hold no link with a ghost end (-1: not analysed yet)
     long long spin_cycles = 0;
 };
@@ -84,7 +85,11 @@ struct HaloRecvArgs {
 };
 
 // my face poses -> the neighbours' receive buffers (peer stores), then the step number
-__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(const double *__restrict__ pose, HaloSendArgs a, unsigned int step1, int parity) {
+__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(const double *__restrict__ pose, HaloSendArgs a, unsigned int *seq) {
+    // this is send number seq[0] + 1 (every CTA reads it before the last one to arrive bumps it); neighbours run in lock step, so
+    // both sides of a face count the same sends
+    const unsigned int step1 = *reinterpret_cast<volatile unsigned int *>(seq) + 1u;
+    const int parity = (int)((step1 - 1u) & 1u);
     const int sd = (int)blockIdx.x < a.nb[0] ? 0 : 1;
     const int blk = sd ? (int)blockIdx.x - a.nb[0] : (int)blockIdx.x;
     const int n = a.n[sd];
@@ -101,14 +106,23 @@ __global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(const double *__re
             *a.count[sd] = 0u;
             st_release_sys(a.peer_flag[sd] + 32 * parity, step1);
         }
+        const unsigned int all = atomicAdd(seq + 2, 1u);
+        if (all == (unsigned int)(a.nb[0] + a.nb[1]) - 1) { // last CTA of the launch: every CTA has read seq[0]
+            seq[2] = 0u;
+            __threadfence();
+            seq[0] = step1;
+        }
     }
 }
 
 // wait for the neighbours' step numbers: ONE thread per side polls the system-scope flag (hundreds of CTAs polling it, as a first
 // version of the wide receive kernel did, slow the step down 5x: 1.9 ms instead of 0.36 ms on 4 GPUs)
-__global__ void k_halo_wait(HaloRecvArgs a, unsigned int step1, int parity, int *err, long long spin_cycles, SimD *simd) {
+__global__ void k_halo_wait(HaloRecvArgs a, const unsigned int *seq, int *err, long long spin_cycles, SimD *simd) {
     const int sd = threadIdx.x;
     if (sd > 1 || a.nb[sd] == 0) return;
+    const unsigned int step1 = seq[0]; // my sends so far = the neighbours' send I need
+    if (step1 == 0 || seq[1] == step1) return; // nothing sent yet / already collected
+    const int parity = (int)((step1 - 1u) & 1u);
     if (*reinterpret_cast<volatile int *>(err) != 0) return; // sticky: after one failed wait nothing is scattered any more
     const long long t0 = clock64();
     while (ld_acquire_sys(a.recv_flag[sd] + 32 * parity) < step1) {
@@ -123,8 +137,11 @@ __global__ void k_halo_wait(HaloRecvArgs a, unsigned int step1, int parity, int 
 }
 
 // ghost poses <- receive buffers (after k_halo_wait in the same stream)
-__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_recv(double *pose, HaloRecvArgs a, int parity, const int *err) {
+__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_recv(double *pose, HaloRecvArgs a, unsigned int *seq, const int *err) {
     if (*err) return;
+    const unsigned int step1 = seq[0];
+    if (step1 == 0 || *reinterpret_cast<volatile unsigned int *>(seq + 1) == step1) return; // (the same answer in every CTA: seq[1] moves when all have read it)
+    const int parity = (int)((step1 - 1u) & 1u);
     const int sd = (int)blockIdx.x < a.nb[0] ? 0 : 1;
     const int blk = sd ? (int)blockIdx.x - a.nb[0] : (int)blockIdx.x;
     const int n = a.n[sd];
@@ -132,6 +149,14 @@ __global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_recv(double *pose, Halo
     for (int i = blk * blockDim.x + threadIdx.x; i < 4 * n; i += a.nb[sd] * blockDim.x) {
         const int v = a.idx[sd][i >> 2];
         reinterpret_cast<double2 *>(pose + 8 * (size_t)v)[i & 3] = __ldcv(src + i); // written by another device: never from a stale L1 line
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int all = atomicAdd(seq + 3, 1u);
+        if (all == (unsigned int)(a.nb[0] + a.nb[1]) - 1) { // last CTA: every CTA of the launch has read seq[1]
+            seq[3] = 0u;
+            seq[1] = step1;
+        }
     }
 }
 

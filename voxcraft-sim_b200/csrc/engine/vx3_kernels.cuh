@@ -633,10 +633,10 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
     rec.mat = 0;
     rec.fixed = 0;
     rec._pad = 0;
-    if (dy.status == VX3_SIM_RUNNING && !dy.diverged && dy.dt != 0 && sim_collides(S)) {
+    // (the surface flags follow the links in EVERY running simulation of the batch, also one that has collisions off but loses
+    // links to detach / removal while its batch mates collide; only the grid is for colliding simulations)
+    if (dy.status == VX3_SIM_RUNNING && !dy.diverged && dy.dt != 0) {
         int flags = D.vflags[v];
-        const float tempe = unpack_t(D.pose[8 * (size_t)v + 7]);
-        D.tempe[v] = tempe; // this step's temperature, for the contact phase
         bool interior = true; // VX3_Voxel::updateSurface (VX3_Voxel.cu:515-524): the bit named SURFACE means interior
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -645,7 +645,9 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_grid_build(Dev D) {
         }
         const int nf = interior ? (flags | VX3_VOX_SURFACE) : (flags & ~VX3_VOX_SURFACE);
         if (nf != flags) D.vflags[v] = nf;
-        if (!interior && !(flags & VXF_REMOVED)) {
+        const float tempe = sim_collides(S) ? unpack_t(D.pose[8 * (size_t)v + 7]) : 0.0f;
+        if (sim_collides(S)) D.tempe[v] = tempe; // this step's temperature, for the contact phase
+        if (sim_collides(S) && !interior && !(flags & VXF_REMOVED)) {
             const V3 p = load_pos(D.pose, v);
             const int mat = D.vmat[v];
             const VoxMatC &m = D.vmat_tab[mat];
