@@ -380,6 +380,12 @@ int vx3_batch_com_sums(vx3_batch *b, int sim, double *out6);
  * slots in use, 0 (reserved), largest number of attach candidates one step produced, largest number of links one step put on the
  * failed list, 0, 0}. */
 int vx3_batch_counters(vx3_batch *b, int sim, int64_t *out8);
+/* Self-check of the depth-5 neighbour search (test hook; is_neighbor, VX3_VoxelyzeKernel.cu:651-680): n_pairs pseudo-random voxel
+ * pairs of simulation `sim` — a voxel and one picked within its index neighbourhood, so that most pairs are a few links apart — are
+ * put to the bounded two-sided search the contact phase uses and to the reference's path walk; *mismatches = pairs on which the
+ * two disagree, *positives = pairs found within five links.  VX3_ERR_INVALID when the batch holds no adjacency table (nothing in it
+ * attaches). */
+int vx3_batch_check_neighbor_search(vx3_batch *b, int sim, int n_pairs, unsigned seed, int *mismatches, int *positives);
 /* Queue k steps (explicit dt, or dt < 0 like vx3_batch_step) without waiting; vx3_batch_sync waits.  For one host thread
  * that drives several batches whose step streams wait for each other (slabs of a decomposed body): queue the slabs in
  * rounds of a few dozen steps — a round that overflows the driver's launch queue (~1000 launches) blocks the host on one

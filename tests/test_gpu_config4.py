@@ -64,6 +64,9 @@ def run_impact(grid, steps, chunk, min_cand_peak):
         assert oc["attach"] > 100, "the scenario must create links"
         assert ec["cand_peak"] >= min_cand_peak, "candidates in one step: %d" % ec["cand_peak"]
         print(grid, "attach", oc["attach"], "detach", oc["detach"], "peak candidates in one step", ec["cand_peak"])
+        # the contact phase's two-sided depth-5 neighbour search against the reference's path walk, on the glued-together pile
+        mism, positives = eng.check_neighbor_search(0, n_pairs=40000, seed=7)
+        assert mism == 0 and 100 < positives < 40000, (mism, positives)
         eng.close()
     finally:
         lib.vx3_builder_destroy(b)

@@ -193,6 +193,7 @@ def declare_engine_api(lib):
     lib.vx3_batch_halo_connect.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.vx3_batch_com_sums.argtypes = [vp, C.c_int, P(f64)]
     lib.vx3_batch_counters.argtypes = [vp, C.c_int, P(C.c_int64)]
+    lib.vx3_batch_check_neighbor_search.argtypes = [vp, C.c_int, C.c_int, C.c_uint, P(C.c_int), P(C.c_int)]
     lib.vx3_batch_halo_connect_local.argtypes = [vp, C.c_int, vp]
     lib.vx3_batch_step_async.argtypes = [vp, i64, f32]
     lib.vx3_abi_sizeof.argtypes = [C.c_char_p]
@@ -213,7 +214,7 @@ ENGINE_SYMBOLS = ["vx3_batch_create", "vx3_batch_run", "vx3_batch_step", "vx3_ba
                   "vx3_batch_last_timing", "vx3_batch_set_profiling", "vx3_batch_kernel_stats", "vx3_batch_set_fused",
                   "vx3_batch_fused_info", "vx3_fused_plan_check", "vx3_batch_halo_setup",
                   "vx3_batch_halo_export", "vx3_batch_halo_connect", "vx3_batch_halo_connect_local", "vx3_batch_com_sums",
-                  "vx3_batch_counters", "vx3_batch_step_async", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_engine_trim", "vx3_last_error",
+                  "vx3_batch_counters", "vx3_batch_check_neighbor_search", "vx3_batch_step_async", "vx3_abi_sizeof", "vx3_sort_results", "vx3_batch_destroy", "vx3_engine_trim", "vx3_last_error",
                   "vx3_abi_version"]
 WORKER_SYMBOLS = ["vx3_worker_run_vxt", "vx3_worker_run_files", "vx3_write_report", "vx3_write_report_positions"]
 MODEL_SYMBOLS = ["vx3_material_params_default", "vx3_env_params_default", "vx3_sim_options_default", "vx3_builder_create",

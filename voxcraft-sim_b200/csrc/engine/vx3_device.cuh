@@ -107,6 +107,8 @@ struct SimC {
 #define SHF_ATTACH_COND (1 << 4)
 #define SHF_SIGNALS (1 << 5)
 #define SHF_DETACH (1 << 6)      // EnableDetach: the link pass lists the links whose failure strain is passed
+#define SHF_SECONDARY (1 << 7)   // SecondaryExperiment
+#define SHF_STOP_PROG (1 << 8)   // a stop-condition program is present
 
 // per-simulation dynamic scalars (VX3_VoxelyzeKernel members that change during the run).  The first 48 bytes are the
 // "hot" block every link / voxel of the simulation needs each step; the streaming kernels prefetch it with three
@@ -228,6 +230,8 @@ struct Dev {
     CellItem *cell_items;
     struct ContactRec *crec; // [nvox] what the contact phase needs of a voxel, in one 64-byte record (written by k_grid_build)
     int32_t *uf;      // [nvox] union-find parents over the voxels (NULL unless a simulation can attach), see uf_find
+    int32_t *vnb;     // [nvox][8] the voxel at the far end of each of the six link slots (-1: none; two pad entries) — the link graph as
+                      // an adjacency table for within_five_links (allocated with uf; kept current by attach / detach / removal)
     Cand *cands;        // per-simulation regions (SimC::cand_off / cand_cap), counts in SimD::cand_count
     int32_t *fail_list; // per-simulation regions (SimC::fail_off / fail_cap) of link slots, counts in SimD::fail_count
     // CoM partials [nchunks][6]: sum m*x, m*y, m*z, m, sum dist, n_measured

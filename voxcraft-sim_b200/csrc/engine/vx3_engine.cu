@@ -736,7 +736,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.optimal_dt = vx3_model_recommended_dt(&m);
         dy.hot_flags = ((S.vary_temp && S.temp_period > 0) ? SHF_THERMAL : 0) | (S.enable_expansion ? SHF_EXPANSION : 0) | (S.enable_cilia ? SHF_CILIA : 0) |
                        (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0) |
-                       (S.enable_detach ? SHF_DETACH : 0);
+                       (S.enable_detach ? SHF_DETACH : 0) | (S.secondary_experiment ? SHF_SECONDARY : 0) | (S.prog_n[VX3_PROG_STOP] > 0 ? SHF_STOP_PROG : 0);
         dy.temp_amp = S.temp_amp;
         dy.temp_period = S.temp_period;
         b->vmat_local[s].assign(m.vox_mat, m.vox_mat + m.n_voxels);
@@ -928,7 +928,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     D.vstride = (int)VS;
     D.lstride = (int)LS;
     // ---- plan the rest of the arena: the small tables follow the in-place arrays, zero-initialised slices come last ----
-    std::vector<int32_t> uf_host;
+    std::vector<int32_t> uf_host, vnb_host;
 #define UP(field, vec) plan.upload(const_cast<std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type **>(&D.field), vec)
     UP(simc, b->simc);
     UP(simd, simd);
@@ -991,6 +991,13 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             }
             for (size_t v = 0; v < nvox; v++) uf_host[v] = find((int)v);
             plan.upload(&D.uf, uf_host);
+            vnb_host.assign(nvox * 8, -1);
+            for (size_t v = 0; v < nvox; v++)
+                for (int k = 0; k < 6; k++) {
+                    const int li = vlinks[6 * v + k];
+                    if (li >= 0) vnb_host[8 * v + k] = lends[li].x == (int)v ? lends[li].y : lends[li].x;
+                }
+            plan.upload(&D.vnb, vnb_host);
         }
     }
     {
@@ -1092,6 +1099,23 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     if (ce != cudaSuccess) return cleanup(fail(VX3_ERR_CUDA, std::string("batch init: ") + cudaGetErrorString(ce)));
     lap("upload + device init");
     *out = b;
+    return VX3_OK;
+}
+
+extern "C" int vx3_batch_check_neighbor_search(vx3_batch *b, int sim, int n_pairs, unsigned seed, int *mismatches, int *positives) {
+    if (!b || sim < 0 || sim >= b->nsims || n_pairs <= 0 || !mismatches || !positives) return fail(VX3_ERR_INVALID, "bad arguments");
+    if (!b->D.vnb) return fail(VX3_ERR_INVALID, "the batch holds no adjacency table (no simulation in it attaches)");
+    CK(cudaSetDevice(b->device));
+    int *out = nullptr;
+    int rc = b->alloc(&out, 2);
+    if (rc) return rc;
+    k_check_neighbor_search<<<cdiv(n_pairs, 128), 128, 0, b->stream>>>(b->D, b->simc[sim].voff, b->simc[sim].nvox, n_pairs, seed, out);
+    int h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaGetLastError());
+    *mismatches = h[0];
+    *positives = h[1];
     return VX3_OK;
 }
 
@@ -1290,6 +1314,11 @@ static void preload_step_kernels() {
 // host-side partition stores the face links last)
 static int halo_prepare(vx3_batch *b) {
     Halo &H = b->halo;
+    H.send_blocks = 0;
+    for (int sd = 0; sd < 2; sd++) {
+        const HaloSide &h = H.side[sd];
+        if (h.n_send > 0 && (h.peer_open || h.peer_local)) H.send_blocks += std::min(1024, cdiv(4 * h.n_send, VX3_HALO_BLOCK));
+    }
     if (H.face_tile0 >= 0) return VX3_OK;
     double ms = VX3_HALO_TIMEOUT_MS_DEFAULT;
     if (const char *e = getenv("VX3_HALO_TIMEOUT_MS")) ms = std::max(1.0, atof(e));
@@ -1366,7 +1395,10 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     if (b->any_signals) LAUNCH(KC_SIGNALS, k_signals, b->nsims, 256, D); // end of timeStep (VX3_Voxel.cu:270-275), before removeVoxels
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
+    // (a slab batch is one simulation, and on a plain step its end-of-step bookkeeping rides in the send kernel)
+    int tail_in_send = -1;
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
+    else if (b->halo.on && b->halo.send_blocks > 0) tail_in_send = check_stop ? 1 : 0;
     else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
     if (b->halo.on) { // my face poses to the neighbour slabs (vx3_halo.cuh); their poses are collected before the next face-link pass
         Halo &H = b->halo;
@@ -1380,7 +1412,7 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
                 a.nb[sd] = std::min(1024, cdiv(4 * h.n_send, VX3_HALO_BLOCK));
             }
         }
-        if (a.nb[0] + a.nb[1] > 0) LAUNCH(KC_HALO, k_halo_send, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D.pose, a, H.seq);
+        if (a.nb[0] + a.nb[1] > 0) LAUNCH(KC_HALO, k_halo_send, a.nb[0] + a.nb[1], VX3_HALO_BLOCK, D, a, H.seq, tail_in_send);
         H.pending = true;
     }
     b->hsteps++;

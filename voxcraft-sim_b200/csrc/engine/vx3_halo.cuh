@@ -58,6 +58,7 @@ struct Halo {
     // device-side sequence numbers {sent, collected, send arrivals, receive arrivals}: the exchange kernels take the step number from here, not from
     // a kernel argument, so that a stretch of steps can be captured once in a CUDA Graph and replayed
     unsigned int *seq = nullptr;
+    int send_blocks = 0;                          // CTAs of k_halo_send (0: this slab sends nothing)
     int face_tile0 = -1;                          // link tiles [0, face_tile0) hold no link with a ghost end (-1: not analysed yet)
     long long spin_cycles = 0;
 };
@@ -84,8 +85,11 @@ struct HaloRecvArgs {
     int n[2], nb[2];
 };
 
-// my face poses -> the neighbours' receive buffers (peer stores), then the step number
-__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(const double *__restrict__ pose, HaloSendArgs a, unsigned int *seq) {
+// my face poses -> the neighbours' receive buffers (peer stores), then the step number.  tail >= 0: the last CTA also does the
+// end-of-step bookkeeping of the (single) simulation, k_tail_light's work with check_stop = tail — one launch less per step
+__global__ void __launch_bounds__(VX3_HALO_BLOCK) k_halo_send(Dev D, HaloSendArgs a, unsigned int *seq, int tail) {
+    const double *__restrict__ pose = D.pose;
+    if (tail >= 0 && blockIdx.x == gridDim.x - 1 && threadIdx.x == VX3_HALO_BLOCK - 1) tail_light(D, 0, tail);
     // this is send number seq[0] + 1 (every CTA reads it before the last one to arrive bumps it); neighbours run in lock step, so
     // both sides of a face count the same sends
     const unsigned int step1 = *reinterpret_cast<volatile unsigned int *>(seq) + 1u;

@@ -706,9 +706,96 @@ __device__ __forceinline__ bool uf_disconnected(const Dev &D, int a, int b) { re
 
 // is_neighbor (VX3_VoxelyzeKernel.cu:651-680), iterative
 __device__ bool is_neighbor_dfs(const Dev &D, int v1, int v2, int depth);
+// The reference walks every non-reversing path of up to 5 links from voxel1 depth-first: true iff the two voxels are at most
+// 5 links apart in the link graph (a shortest path never reverses).  For a pair that is NOT — two bodies of a pile glued
+// together somewhere else, touching here: the common case once a pile has settled — that walk is ~4700 path steps of two
+// dependent loads each, in one lane, every step (config 4 after 5000 steps: k_contact 503 us instead of 37).  Same answer from
+// both ends: the ball of radius 2 around v2 (<= 37 voxels) against the ball of radius 3 around v1, on the adjacency table
+// D.vnb (one 32-byte row per voxel; the voxels' link slots are kept symmetric by attach, detach and removal): 45 rows in
+// 9 rounds of independent loads.  Without the table (no simulation of the batch attaches) the path walk stays.
+__device__ __forceinline__ void load_nb_row(const Dev &D, int x, int r[6]) {
+    const int4 a = *reinterpret_cast<const int4 *>(D.vnb + 8 * (size_t)x);
+    const int2 c = *reinterpret_cast<const int2 *>(D.vnb + 8 * (size_t)x + 4);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = c.x; r[5] = c.y;
+}
+__device__ __forceinline__ unsigned long long nb_bloom(int x) { return 1ull << (((unsigned)x * 0x9E3779B1u) >> 26); }
+__device__ __noinline__ bool within_five_links(const Dev &D, int v1, int v2) {
+    if (v1 == v2) return true;
+    int B[44], nB = 0; // v2's ball of radius 2 (with repeats; <= 37 while the slots are symmetric)
+    int lvl[6], nl = 0;
+    int r[6][6];
+    load_nb_row(D, v2, r[0]);
+    B[nB++] = v2;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (r[0][i] >= 0) {
+            if (r[0][i] == v1) return true;
+            lvl[nl++] = r[0][i];
+            B[nB++] = r[0][i];
+        }
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (k < nl) load_nb_row(D, lvl[k], r[k]);
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (k < nl)
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const int x = r[k][i];
+                if (x >= 0 && x != v2) {
+                    if (x == v1) return true;
+                    B[nB++] = x;
+                }
+            }
+    unsigned long long bloom = 0;
+    for (int j = 0; j < nB; j++) bloom |= nb_bloom(B[j]);
+    auto in_ball = [&](int x) {
+        if (!(bloom & nb_bloom(x))) return false;
+        for (int j = 0; j < nB; j++)
+            if (B[j] == x) return true;
+        return false;
+    };
+    // v1's side, level by level: distance 3, 4, 5 in total
+    load_nb_row(D, v1, r[0]);
+    nl = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (r[0][i] >= 0) {
+            if (in_ball(r[0][i])) return true;
+            lvl[nl++] = r[0][i];
+        }
+    int A2[36], n2 = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (k < nl) load_nb_row(D, lvl[k], r[k]);
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+        if (k < nl)
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const int x = r[k][i];
+                if (x >= 0 && x != v1) {
+                    if (in_ball(x)) return true;
+                    A2[n2++] = x;
+                }
+            }
+    for (int k0 = 0; k0 < n2; k0 += 6) {
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (k0 + k < n2) load_nb_row(D, A2[k0 + k], r[k]);
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            if (k0 + k < n2)
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    if (r[k][i] >= 0 && in_ball(r[k][i])) return true;
+    }
+    return false;
+}
 // The answer does not depend on the order the paths are tried in; the reference's depth-first order can walk hundreds of
 // 5-link paths before it tries the 2-link one that ends the search, so the short paths are tried first (<= 36 nodes).
 __device__ bool is_neighbor(const Dev &D, int v1, int v2, int depth) {
+    if (depth == 5 && D.vnb) return within_five_links(D, v1, v2);
     if (depth > 2 && is_neighbor_dfs(D, v1, v2, 2)) return true;
     return is_neighbor_dfs(D, v1, v2, depth);
 }
@@ -731,6 +818,25 @@ __device__ bool is_neighbor_dfs(const Dev &D, int v1, int v2, int depth) {
         sv[d] = other; sl[d] = li; si[d] = 0;
     }
     return false;
+}
+
+// test hook (vx3_batch_check_neighbor_search): both searches on pseudo-random pairs of one simulation's voxels
+__global__ void k_check_neighbor_search(Dev D, int v0, int nv, int n_pairs, unsigned seed, int *out2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    unsigned h = seed * 0x9E3779B1u + (unsigned)i * 0x85EBCA6Bu;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    const int a = (int)(h % (unsigned)nv);
+    unsigned g = h * 0xC2B2AE35u + 0x27D4EB2Fu;
+    g ^= g >> 16;
+    // every other pair from the same few dozen indices (a body of the pile), the rest from a wider window
+    const int span = (i & 1) ? 64 : 600;
+    int bq = a + (int)(g % (unsigned)(2 * span + 1)) - span;
+    bq = bq < 0 ? 0 : (bq >= nv ? nv - 1 : bq);
+    const bool fast = within_five_links(D, v0 + a, v0 + bq);
+    const bool walk = is_neighbor_dfs(D, v0 + a, v0 + bq, 5);
+    if (fast != walk) atomicAdd(out2, 1);
+    if (walk) atomicAdd(out2 + 1, 1);
 }
 
 // VX3_Collision (VX3_Collision.cu:3-31): force stored on voxel1 (= the higher index of the pair)
@@ -1152,6 +1258,10 @@ __device__ void resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, u
     const int vneg = rev ? lo : hi, vpos = rev ? hi : lo; // pVNeg/pVPos of VX3_Link(voxelA, dirA, voxelB, dirB)
     D.vlinks[6 * (size_t)hi + dir1] = g;
     D.vlinks[6 * (size_t)lo + dir2] = g;
+    if (D.vnb) {
+        D.vnb[8 * (size_t)hi + dir1] = lo;
+        D.vnb[8 * (size_t)lo + dir2] = hi;
+    }
     D.lends[g] = make_int2(vneg, vpos);
     D.lmat[g] = mh.self_lmat;
     D.lc4[g] = make_int4(vneg, vpos, mh.self_lmat, sim);
@@ -1240,8 +1350,14 @@ __global__ void __launch_bounds__(VX3_RESOLVE_T) k_resolve_detach(Dev D) {
             const int2 e = D.lends[g];
             D.lstate[g] = (st | LKS_DETACHED) & ~LKS_FAILED;
             for (int i = 0; i < 6; i++) {
-                if (D.vlinks[6 * (size_t)e.x + i] == g) D.vlinks[6 * (size_t)e.x + i] = -1;
-                if (D.vlinks[6 * (size_t)e.y + i] == g) D.vlinks[6 * (size_t)e.y + i] = -1;
+                if (D.vlinks[6 * (size_t)e.x + i] == g) {
+                    D.vlinks[6 * (size_t)e.x + i] = -1;
+                    if (D.vnb) D.vnb[8 * (size_t)e.x + i] = -1;
+                }
+                if (D.vlinks[6 * (size_t)e.y + i] == g) {
+                    D.vlinks[6 * (size_t)e.y + i] = -1;
+                    if (D.vnb) D.vnb[8 * (size_t)e.y + i] = -1;
+                }
             }
             atomicAdd(&dy.detach_events, 1);
         }
@@ -1282,9 +1398,11 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_secondary(Dev D) {
             for (int q = 0; q < 6; q++)
                 if (D.vlinks[6 * (size_t)nb + q] == li) {
                     D.vlinks[6 * (size_t)nb + q] = -1;
+                    if (D.vnb) D.vnb[8 * (size_t)nb + q] = -1;
                     break;
                 }
             D.vlinks[6 * (size_t)v + k] = -1;
+            if (D.vnb) D.vnb[8 * (size_t)v + k] = -1;
         }
     }
     if (!dy.initpos_reinitialized && S.reinit_after < t) store3(D.initpos, v, load_pos(D.pose, v)); // saveInitialPosition()
@@ -1577,25 +1695,32 @@ __global__ void __launch_bounds__(128) k_tail(Dev D, int com_ready, int check_st
 
 // k_tail for a step on which NO simulation of the batch samples its centre of mass (the host knows the cadence): one
 // thread per simulation.  A simulation that nevertheless reaches a sampling step here reports VX3_ERR_INVALID.
+// Everything the decision needs sits in the first 64 bytes of SimD and is loaded up front, in one round trip (as a chain of
+// early-outs the same code was five dependent loads, 6.5 us per step for a kernel that does nothing most of the time).
 __device__ void tail_light(const Dev &D, int sim, int check_stop) {
-    const SimC &S = D.simc[sim];
     SimD &dy = D.simd[sim];
-    if (dy.status != VX3_SIM_RUNNING) return;
+    const int status = dy.status, diverged = dy.diverged, hot = dy.hot_flags;
     const float dtF = dy.dt;
-    dy.steps += 1;
+    const double t = dy.t, period = dy.temp_period;
+    const long long steps = dy.steps + 1;
+    if (status != VX3_SIM_RUNNING) return;
+    dy.steps = steps;
     if (dtF == 0) return;
-    if (dy.diverged) {
+    if (diverged) {
         dy.status = VX3_SIM_DIVERGED;
         return;
     }
-    const int CycleStep = (int)(S.temp_period / dtF);
-    if (CycleStep > 0 && dy.steps % CycleStep == 0) dy.err = VX3_ERR_INVALID;
-    if (S.secondary_experiment && !dy.initpos_reinitialized && S.reinit_after < dy.t) { // :344-348
-        dy.initpos_reinitialized = 1;
-        for (int k = 0; k < 3; k++) dy.com0[k] = dy.com[k]; // InitializeCenterOfMass()
+    const int CycleStep = (int)(period / dtF);
+    if (CycleStep > 0 && steps % CycleStep == 0) dy.err = VX3_ERR_INVALID;
+    if (hot & SHF_SECONDARY) {
+        const SimC &S = D.simc[sim];
+        if (!dy.initpos_reinitialized && S.reinit_after < t) { // :344-348
+            dy.initpos_reinitialized = 1;
+            for (int k = 0; k < 3; k++) dy.com0[k] = dy.com[k]; // InitializeCenterOfMass()
+        }
     }
-    dy.t += dtF;
-    if (check_stop && stop_condition_met(D, S, dy)) dy.status = VX3_SIM_STOPPED;
+    dy.t = t + dtF;
+    if (check_stop && (hot & SHF_STOP_PROG) && stop_condition_met(D, D.simc[sim], dy)) dy.status = VX3_SIM_STOPPED;
 }
 __global__ void __launch_bounds__(128) k_tail_light(Dev D, int check_stop) {
     const int sim = blockIdx.x * blockDim.x + threadIdx.x;

@@ -140,6 +140,12 @@ class Batch:
         self._check(self.lib.vx3_batch_counters(self.h, sim, out), "vx3_batch_counters")
         return dict(attach=out[0], detach=out[1], links=out[2], cand_peak=out[4], fail_peak=out[5])
 
+    def check_neighbor_search(self, sim=0, n_pairs=4096, seed=1):
+        """(mismatches, positives) of the two-sided depth-5 neighbour search against the reference's path walk on random pairs."""
+        mm, pos = C.c_int(0), C.c_int(0)
+        self._check(self.lib.vx3_batch_check_neighbor_search(self.h, sim, n_pairs, seed, C.byref(mm), C.byref(pos)), "vx3_batch_check_neighbor_search")
+        return mm.value, pos.value
+
     def close(self):
         if self.h:
             self.lib.vx3_batch_destroy(self.h)
