@@ -338,6 +338,7 @@ def extra_resident(tag, specs, label, scaling, lib, rank, local_rank, world, bar
     dev_ms, launches, wall, stats, prof_steps = measure_resident(batch, S, K, Wm, barrier)
     res = batch.results()
     diverged = sum(1 for r in res if r.status == 2)
+    counters = batch.counters(0) if tag == "c4" else None
     batch.close()
     for b, _ in built:
         lib.vx3_builder_destroy(b)
@@ -353,7 +354,10 @@ def extra_resident(tag, specs, label, scaling, lib, rank, local_rank, world, bar
     dev_ms_max = float(tt[0])
     value = float(work[0]) / (dev_ms_max * 1e-3)
     total = sum(v[0] for v in stats.values()) or 1.0
-    return {"workload": label, "value": value, "unit": UNIT, "n_gpus": world, "scaling": scaling, "steps": K, "warmup": Wm, "sim_steps_per_step": S,
+    more = {}
+    if counters is not None:  # which stretch of the pile's life was timed, and how much contact / attach / detach work it held
+        more = {"timed_sim_steps": [Wm * S, (Wm + K) * S], "collision_counters_sim0": counters}
+    return {**more, "workload": label, "value": value, "unit": UNIT, "n_gpus": world, "scaling": scaling, "steps": K, "warmup": Wm, "sim_steps_per_step": S,
             "ms_per_step": dev_ms_max / K, "us_per_sim_step": 1e3 * dev_ms_max / (K * S), "sims_per_gpu": len(descs), "voxels_per_gpu": nvox,
             "links_per_gpu": nlinks, "alg_bytes_per_voxel_step": b_alg, "hbm_roofline_equiv_frac": value * b_alg / (peak * 1e9 * world),
             "kernel_us_per_sim_step": {k: round(1e3 * v[0] / prof_steps, 3) for k, v in stats.items()},
@@ -376,7 +380,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--skip-extra", action="store_true", help="config 2 headline only: leave out the config 3 / config 5 sub-measurements")
+    ap.add_argument("--skip-extra", action="store_true", help="config 2 headline only: leave out the config 3 / 4 / 5 sub-measurements")
     args = ap.parse_args()
     claim_stdout()
     rank, local_rank, world = env_rank()
@@ -556,6 +560,10 @@ def main():
         c3_specs = [W.c3_spec(k) for k in range(args.sims_per_gpu)]
         extras["config3"] = extra_resident("c3", c3_specs, "config3: batch of %d random 10x10x10 robots per GPU (vx3_node_worker fitness eval), %d in all"
                                            % (args.sims_per_gpu, args.sims_per_gpu * world), "weak", lib, rank, local_rank, world, barrier, 400, 20, 3)
+        # config 4 from the start of the fall until the pile has settled and glued itself together (the contact phase costs most
+        # once hundreds of bodies touch and every touching pair of one glued blob needs the depth-5 neighbour test)
+        c4_specs, c4_label = build_workload("c4", None, 0)
+        extras["config4"] = extra_resident("c4", c4_specs, c4_label + " (one pile per GPU)", "weak", lib, rank, local_rank, world, barrier, 1000, 7, 1)
         c5_specs, c5_label = build_workload("c5", None, 0)
         if world > 1:
             c5_built = [sp.build(lib) for sp in c5_specs]
@@ -583,7 +591,7 @@ def main():
                            "l2": "state is mutated by every step (each step reads what the previous one wrote); working set "
                                  "%.1f MB %s the 126 MB L2" % ((nvox * 228 + nlinks * 184) / 1e6, "fits in" if nvox * 228 + nlinks * 184 < 100e6 else "exceeds"),
                            "alg_bytes_per_voxel_step": b_alg, "wall_ms_per_step": 1e3 * wall_max / K, "diverged_sims": int(total_div),
-                           "collision_counters_sim0": counters},
+                           "collision_counters_sim0": counters, "timed_sim_steps": [Wm * S, (Wm + K) * S]},
                 "roofline": roofline,
                 "hbm_roofline_equiv_frac": value * b_alg / (peak * 1e9 * world),
                 "cpu_baseline": cpu_baseline, "clocks": clocks, "gpu_launches": int(total_launches)}

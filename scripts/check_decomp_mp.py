@@ -33,7 +33,8 @@ def main():
     body = parallel.DecomposedBody(slab, dt, device=local)
     body.connect()
     steps = 600
-    body.step(steps)
+    for chunk in (1, 2, 37, 160, 400):  # several stepping calls: every call ends with a collect of its own, the next one starts in the link pass
+        body.step(chunk)
     st = body.batch.state(0)
     own = np.nonzero(slab.owned)[0]
     mine = (slab.voxels[own].tolist(), np.asarray(st["pos"]).reshape(-1, 3)[own].tolist(), np.asarray(st["orient"]).reshape(-1, 4)[own].tolist())

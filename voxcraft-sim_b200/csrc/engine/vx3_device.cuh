@@ -174,8 +174,36 @@ VXHD size_t idx_mo(int p, size_t v) { return ((v >> 5) * 3 + p) * 32 + (v & 31);
 VXHD size_t idx_lf(int k, size_t g) { return ((g >> 5) * 6 + k) * 32 + (g & 31); }
 
 // All device arrays of a batch (plain pointers; owned by the host Batch object).
+// Receive side of a slab's halo exchange as the link pass sees it (vx3_halo.cuh; device-resident, Dev::hin): the link kernel of a slab
+// batch reads its ghost voxels' poses straight from the receive buffers.
+struct HaloIn {
+    int face_tile0;              // link tiles [0, face_tile0) hold no link with a ghost end
+    int n[2];                    // records expected from the lower / upper neighbour
+    const int32_t *idx[2];       // my ghost voxels, in the neighbour's send order
+    const double *buf[2];        // [2 parities][n][8] doubles, written by the neighbour
+    const unsigned int *flag[2]; // [2 parities] send numbers published by the neighbour (32 words apart)
+    unsigned int *seq;           // {my sends so far, the send I have collected, ...} (Halo::seq)
+    unsigned int *state;         // [0] the send number some warp has undertaken to wait for, [32] the send number known to be in (halo_arrival_wait)
+    const int32_t *ghost_row;    // [nvox] -1: an owned voxel; else side << 30 | position in that side's receive buffer
+    int *err;
+    long long spin_cycles;
+};
+
+// Send side, as the voxel pass sees it (Dev::hout): a face voxel's new pose record goes into its own row AND straight into the
+// neighbour's receive buffer (peer memory); the last CTA of the pass to finish publishes the send number.  The voxel's position
+// in the neighbour's buffer is vc4[v].w - 1 = side << 30 | position (0: not a face voxel).
+struct HaloOut {
+    double *buf[2];          // the neighbours' receive buffers for my side: [2 parities][n][8] doubles (peer memory)
+    unsigned int *flag[2];   // the neighbours' [2 parities] send-number words
+    int n[2];
+    unsigned int *seq;       // {my sends so far, ...} (Halo::seq)
+    unsigned int *count;     // arrival counter of the pass's CTAs
+};
+
 struct Dev {
     int32_t nsims, nvox, nlinkslots, nchunks;
+    const HaloIn *hin;   // slab batches whose link pass reads the receive buffers itself, else NULL
+    const HaloOut *hout; // slab batches whose voxel pass sends, else NULL
     const SimC *simc;
     SimD *simd;
     const VoxMatC *vmat_tab;
@@ -194,7 +222,7 @@ struct Dev {
     int32_t *vflags;  // boolStates | VXF_*
     const int32_t *vmat; // global voxel-material index
     const int32_t *vsim;
-    const int4 *vc4;     // {vmat, vsim, vext, 0}: the voxel's constant indices in one 16-byte record (streaming voxel pass)
+    const int4 *vc4;     // {vmat, vsim, vext, halo send position + 1 or 0}: the voxel's constant indices in one 16-byte record (streaming voxel pass)
     const double *phase;
     float *tempe;     // temperature the last executed step used (VX3_Voxel::temp)
     int32_t *vlinks;  // [nvox][6] global link slot or -1

@@ -297,6 +297,7 @@ struct vx3_batch {
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
     bool any_ghost = false;
+    size_t vox_active = 0; // voxels [vox_active, nvox) are all ghosts (a slab model lists them last): the voxel pass leaves their tiles out
     int link_queue = -1; // link pass variant: -1 = still being timed (launch_links), 0 = in place, 1 = deferred dense passes
     int lq_trials = 0;
     double lq_ms[2] = {0, 0};
@@ -918,6 +919,9 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         }
         if (fill_err) return cleanup(fail(VX3_ERR_INVALID, "external index out of range"));
         b->any_ghost |= ghost_seen != 0;
+        b->vox_active = nvox;
+        if (b->any_ghost)
+            while (b->vox_active > 0 && (vflags[b->vox_active - 1] & VX3_VOX_GHOST)) b->vox_active--;
     }
 
     lap("host model -> SoA arrays (in staging)");
@@ -1199,7 +1203,7 @@ static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nv, kv, VX3_VOX_T, 0));
     if (nl < 1 || nv < 1) return fail(VX3_ERR_CUDA, "streaming kernels do not fit on this device");
     b->link_tiles = cdiv(b->D.nlinkslots, VX3_LINK_T);
-    b->vox_tiles = cdiv(b->D.nvox, VX3_VOX_T);
+    b->vox_tiles = std::max(1, cdiv((int)b->vox_active, VX3_VOX_T));
     b->link_grid = std::max(1, std::min(b->link_tiles, nl * prop.multiProcessorCount));
     b->vox_grid = std::max(1, std::min(b->vox_tiles, nv * prop.multiProcessorCount));
     FusedPlan &f = b->fplan;
@@ -1223,7 +1227,7 @@ static int setup_stream_kernels(vx3_batch *b, const cudaDeviceProp &prop) {
 // The link pass has two bit-identical variants (k_links: the large-angle branch in place; k_links_deferred: those links
 // deferred to dense per-warp passes); which is faster depends on the batch, so the first streaming steps of a batch time
 // both with CUDA events (one warm-up round, then 3 trials each) and the batch keeps the faster.  VX3_LINK_QUEUE=0/1 pins it.
-static void launch_links(vx3_batch *b, int tile0 = 0, int tile_end = -1) {
+static void launch_links(vx3_batch *b, int tile0 = 0, int tile_end = -1, bool collect = false) {
     const Dev &D = b->D;
     cudaStream_t st = b->stream;
     if (tile_end < 0) tile_end = b->link_tiles;
@@ -1247,6 +1251,11 @@ static void launch_links(vx3_batch *b, int tile0 = 0, int tile_end = -1) {
             variant = b->lq_trials & 1;
             cudaEventRecord(b->lq_ev[0], st);
         }
+    }
+    if (collect) { // slab batch: the face links read their ghost ends from the receive buffers (vx3_kernels.cuh, halo_arrival_wait)
+        if (b->link_smtab) LAUNCH_SM(KC_LINKS, (k_links_deferred<true, true>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        else LAUNCH_SM(KC_LINKS, (k_links_deferred<false, true>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        return;
     }
     if (b->link_smtab) {
         if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<true>, grid, VX3_LINK_T, 0, D, tile_end, tile0);
@@ -1297,8 +1306,8 @@ static void halo_wait(vx3_batch *b) {
 static void preload_step_kernels() {
     static std::once_flag once;
     std::call_once(once, [] {
-        const void *ks[] = {(const void *)k_links<true>, (const void *)k_links<false>, (const void *)k_links_deferred<true>, (const void *)k_links_deferred<false>,
-                            (const void *)k_links<true, true>, (const void *)k_links<false, true>, (const void *)k_voxels<true>, (const void *)k_voxels<false>,
+        const void *ks[] = {(const void *)k_links<true>, (const void *)k_links<false>, (const void *)k_links_deferred<true>, (const void *)k_links_deferred<false>, (const void *)k_links_deferred<true, true>, (const void *)k_links_deferred<false, true>,
+                            (const void *)k_links<true, true>, (const void *)k_links<false, true>, (const void *)k_voxels<true>, (const void *)k_voxels<false>, (const void *)k_voxels<true, true>, (const void *)k_voxels<false, true>,
                             (const void *)k_fused<true, false>, (const void *)k_fused<true, true>, (const void *)k_fused<false, false>, (const void *)k_fused<false, true>,
                             (const void *)k_tail_light, (const void *)k_tail, (const void *)k_com_partial, (const void *)k_sim_update, (const void *)k_set_dt,
                             (const void *)k_halo_send, (const void *)k_halo_wait, (const void *)k_halo_recv, (const void *)k_surface, (const void *)k_secondary,
@@ -1326,9 +1335,12 @@ static int halo_prepare(vx3_batch *b) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, b->device);
     H.spin_cycles = (long long)(ms * (double)khz);
     H.face_tile0 = 0;
-    // two-range link pass (interior links before the receive): opt-in — measured no faster than send-early / receive-late alone
-    // (4 GPUs 359 vs 353, 8 GPUs 216 vs 211 us per step): the second link launch costs what the hidden wait saves
-    if (b->D.nlinkslots > 0 && getenv("VX3_HALO_OVERLAP") && getenv("VX3_HALO_OVERLAP")[0] == '1') {
+    const char *ik = getenv("VX3_HALO_INKERNEL");
+    H.inkernel = !(ik && ik[0] == '0') && !H.side[0].peer_local && !H.side[1].peer_local && !(b->use_fused && b->fplan.ok) && b->D.nlinkslots > 0;
+    // two-range link pass (interior links before the receive) as two launches: opt-in — measured no faster than send-early /
+    // receive-late alone (4 GPUs 359 vs 353, 8 GPUs 216 vs 211 us per step): the second link launch costs what the hidden wait saves
+    const bool two_launch = !H.inkernel && b->D.nlinkslots > 0 && getenv("VX3_HALO_OVERLAP") && getenv("VX3_HALO_OVERLAP")[0] == '1';
+    if (H.inkernel || two_launch) {
         std::vector<int2> ends;
         std::vector<int32_t> vflags;
         int rc;
@@ -1344,6 +1356,74 @@ static int halo_prepare(vx3_batch *b) {
             }
         }
         H.face_tile0 = first_face / VX3_LINK_T; // the boundary tile goes with the face range
+    }
+    if (H.inkernel) {
+        int rc;
+        if (!H.state && (rc = b->alloc(&H.state, 128))) return rc;
+        if (!H.hin && (rc = b->alloc(&H.hin, 1))) return rc;
+        HaloIn hi;
+        memset(&hi, 0, sizeof(hi));
+        hi.face_tile0 = H.face_tile0;
+        std::vector<int32_t> grow((size_t)b->D.nvox, -1);
+        for (int sd = 0; sd < 2; sd++) {
+            const HaloSide &h = H.side[sd];
+            if (h.n_recv > 0 && (h.peer_open || h.peer_local)) {
+                hi.n[sd] = h.n_recv; hi.idx[sd] = h.recv_idx; hi.buf[sd] = h.recv_buf; hi.flag[sd] = h.recv_flag;
+                std::vector<int32_t> ri;
+                if ((rc = d2h(b, ri, h.recv_idx, 0, (size_t)h.n_recv))) return rc;
+                CK(cudaStreamSynchronize(b->stream));
+                for (int k = 0; k < h.n_recv; k++) grow[ri[k]] = (sd << 30) | k;
+            }
+        }
+        if (!H.ghost_row && (rc = b->upload(&H.ghost_row, grow))) return rc;
+        hi.ghost_row = H.ghost_row;
+        hi.seq = H.seq; hi.state = H.state; hi.err = H.err; hi.spin_cycles = H.spin_cycles;
+        CK(cudaMemcpyAsync(H.hin, &hi, sizeof(hi), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        b->D.hin = H.hin;
+        b->link_queue = 1; // the deferred variant carries the collect
+        graph_invalidate(b);
+        // ---- the send side in the voxel pass ----
+        const char *sf = getenv("VX3_HALO_SENDFUSED");
+        bool fuse_send = !(sf && sf[0] == '0') && !b->any_secondary && !b->any_signals && H.send_blocks > 0;
+        std::vector<int4> vc4;
+        if (fuse_send) {
+            if ((rc = d2h(b, vc4, b->D.vc4, 0, (size_t)b->D.nvox))) return rc;
+            CK(cudaStreamSynchronize(b->stream));
+            for (auto &c : vc4) c.w = 0;
+            for (int sd = 0; sd < 2 && fuse_send; sd++) {
+                const HaloSide &h = H.side[sd];
+                if (!(h.n_send > 0 && (h.peer_open || h.peer_local))) continue;
+                std::vector<int32_t> si;
+                if ((rc = d2h(b, si, h.send_idx, 0, (size_t)h.n_send))) return rc;
+                CK(cudaStreamSynchronize(b->stream));
+                for (int k = 0; k < h.n_send; k++) {
+                    if (vc4[si[k]].w) { // a voxel on both faces (a slab one voxel thick): the stand-alone send kernel handles that
+                        fuse_send = false;
+                        break;
+                    }
+                    vc4[si[k]].w = ((sd << 30) | k) + 1;
+                }
+            }
+        }
+        if (fuse_send) {
+            if (!H.out_count && (rc = b->alloc(&H.out_count, 1))) return rc;
+            if (!H.hout && (rc = b->alloc(&H.hout, 1))) return rc;
+            HaloOut ho;
+            memset(&ho, 0, sizeof(ho));
+            for (int sd = 0; sd < 2; sd++) {
+                const HaloSide &h = H.side[sd];
+                if (h.n_send > 0 && (h.peer_open || h.peer_local)) {
+                    ho.buf[sd] = h.peer_buf; ho.flag[sd] = h.peer_flag; ho.n[sd] = h.n_send;
+                }
+            }
+            ho.seq = H.seq; ho.count = H.out_count;
+            CK(cudaMemcpyAsync(H.hout, &ho, sizeof(ho), cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(const_cast<int4 *>(b->D.vc4), vc4.data(), sizeof(int4) * vc4.size(), cudaMemcpyHostToDevice, b->stream));
+            CK(cudaStreamSynchronize(b->stream));
+            b->D.hout = H.hout;
+            H.send_fused = true;
+        }
     }
     return VX3_OK;
 }
@@ -1370,7 +1450,8 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
             else LAUNCH_SM(KC_FUSED, (k_fused<false, false>), f.grid, VX3_FUSE_T, f.smem, D, a);
         }
     } else if (D.nlinkslots > 0) {
-        if (b->halo.on && b->halo.face_tile0 > 0) { // interior links first: they read no ghost pose, the exchange of the previous step may still be in flight
+        if (b->halo.on && b->halo.inkernel) launch_links(b, 0, -1, true);
+        else if (b->halo.on && b->halo.face_tile0 > 0) { // interior links first: they read no ghost pose, the exchange of the previous step may still be in flight
             launch_links(b, 0, b->halo.face_tile0);
             halo_wait(b);
             launch_links(b, b->halo.face_tile0, b->link_tiles);
@@ -1390,17 +1471,24 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     if ((b->any_sticky || b->any_detach) && D.nlinkslots > 0) LAUNCH(KC_RESOLVE, k_resolve_detach, b->nsims, VX3_RESOLVE_T, D);
     const bool com = !b->capturing && com_step(b, b->hsteps + 1);
     if (fused) {
-    } else if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
-    else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles);
+    } else if (b->halo.on && b->halo.send_fused) { // the voxel pass sends the face poses and, on a plain step, does the end-of-step bookkeeping
+        const int tail = com ? -1 : (check_stop ? 1 : 0);
+        if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, (k_voxels<true, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
+        else LAUNCH_SM(KC_VOXELS, (k_voxels<false, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
+    } else if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, -1);
+    else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, -1);
     if (b->any_signals) LAUNCH(KC_SIGNALS, k_signals, b->nsims, 256, D); // end of timeStep (VX3_Voxel.cu:270-275), before removeVoxels
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
     // (a slab batch is one simulation, and on a plain step its end-of-step bookkeeping rides in the send kernel)
     int tail_in_send = -1;
+    const bool sent_by_voxel_pass = !fused && b->halo.on && b->halo.send_fused;
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
-    else if (b->halo.on && b->halo.send_blocks > 0) tail_in_send = check_stop ? 1 : 0;
+    else if (sent_by_voxel_pass) {
+    } else if (b->halo.on && b->halo.send_blocks > 0) tail_in_send = check_stop ? 1 : 0;
     else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
-    if (b->halo.on) { // my face poses to the neighbour slabs (vx3_halo.cuh); their poses are collected before the next face-link pass
+    if (sent_by_voxel_pass) b->halo.pending = true;
+    else if (b->halo.on) { // my face poses to the neighbour slabs (vx3_halo.cuh); their poses are collected before the next face-link pass
         Halo &H = b->halo;
         HaloSendArgs a;
         memset(&a, 0, sizeof(a));

@@ -4,26 +4,33 @@
 // Every rank holds the voxels of its slab plus GHOST copies (VX3_VOX_GHOST) of the neighbour slabs' face voxels, and every
 // link with at least one owned end; a link that crosses a face is evaluated on both sides from identical inputs, so it
 // needs no message of its own.  The only per-step traffic is the 64-byte pose record (position,
-// orientation, next-step temperature, previousDt) of each face voxel, and it moves inside the step kernels' stream with no
-// host involvement and no NCCL call:
-//   k_halo_send  writes my face poses straight into the neighbour's receive buffer (peer memory opened through CUDA IPC,
-//                i.e. plain stores over NVLink), then publishes the step number with a system-scope release;
-//   k_halo_wait  spins (acquire, system scope, one thread per side) on the step number the neighbours published into MY flags;
-//   k_halo_recv  then moves the received records into my ghost voxels' pose records.
+// orientation, next-step temperature, previousDt) of each face voxel, and it moves inside the step kernels themselves, with no
+// host involvement, no NCCL call and (on the default path) no kernel of its own:
+//   SEND     k_voxels<.., HALO> stores a face voxel's new record into its own pose row AND into the neighbour's receive buffer
+//            (peer memory opened through CUDA IPC: plain stores over NVLink).  Sending threads fence at system scope before
+//            their CTA counts itself in; the last CTA of the pass to finish publishes the send number to both neighbours
+//            and does the step's bookkeeping (tail_light) in a second warp.  (HaloOut, vx3_device.cuh.)
+//   RECEIVE  k_links_deferred<.., HALO> runs the interior link tiles first (parallel.partition_slabs stores the links with two
+//            owned ends first).  Before its first face tile a warp makes sure the neighbours' send number is in — one warp of
+//            the grid polls the system-scope flags, the others a flag in local memory — and the face links then read their
+//            ghost ends straight from the receive buffers (HaloIn::ghost_row): no copy into the ghost voxels' pose rows, and
+//            the transfer has the whole interior range (97 % of the pass) to arrive.
+//   The ghost rows of the pose array are brought up to date only when a stepping call returns (read-backs): k_halo_wait +
+//   k_halo_recv below, once per call.
 // Receive buffers are double-buffered by step parity: a neighbour can be at most one step ahead of me (its step s+2 send
-// needs my step s+1 send, which follows my step s receive), so the buffer it overwrites is never the one I still read.
+// needs my step s+1 send, which follows my step-s+1 link pass, the last reader of its step-s records), so the buffer it overwrites
+// is never the one I still read.  The send number lives in device memory (Halo::seq), not in a kernel argument, so a stretch of
+// steps replays as a CUDA Graph like any other batch.
 //
-// ORDER.  Everything stays in ONE stream: ... voxel pass(s), k_tail(s), k_halo_send(s) | k_halo_wait(s), k_halo_recv(s), link
-// pass(s+1) ...: a rank's records are on their way as soon as its voxel pass is done, and are collected right before the next
-// link pass.  Two refinements were built and measured on the 4M-voxel body (us per step, 4 / 8 GPUs):
-//   * the exchange on a second stream under the next step's link pass: 462 / -  (worse than 382 / 213 before: the link pass is a
-//     persistent tile loop that fills every CTA slot until it ends, the other stream's kernels do not get on the SMs);
-//   * VX3_HALO_OVERLAP=1: the link pass in two tile ranges — INTERIOR links (two owned ends; stored first by
-//     parallel.partition_slabs) before the receive, FACE links after it, so the transfer hides behind the interior range:
-//     359 / 216 against 353 / 211 without it — the second link launch costs what the hidden wait saves.  Left opt-in.
-// What did pay: exchange kernels as wide as the face (one 16-byte quarter per thread, both sides in one launch; the first
-// version moved a face with 64 CTAs in five dependent rounds) and ONE polling thread per side (hundreds of CTAs polling a
-// system-scope flag slow the whole step down 5x): k_halo 92 -> 54 us of kernel time per step at 8 GPUs, 32 us of it exposed.
+// MEASURED on the 4M-voxel body, 8 GPUs, same box back to back (us per step): stand-alone k_halo_send / k_halo_wait / k_halo_recv
+// kernels in the step stream 215.3; receive inside the link pass 205.3; plus send inside the voxel pass 196.1 (2.04e10 voxel-steps/s,
+// 6.6x one GPU).  At 2 GPUs the three differ by < 1 % (600 us steps hide a 20 us exchange either way).  The stand-alone kernels
+// remain as the fallback: two slabs driven by one process (they could hold each other's CTA slots while they wait), slabs one
+// voxel thick, batches with voxel removal, VX3_HALO_INKERNEL=0 / VX3_HALO_SENDFUSED=0.
+// Earlier experiments, all slower (4 / 8 GPUs): the exchange on a second stream under the next link pass 462 / - against 382 / 213
+// (the link pass is a persistent tile loop that fills every CTA slot, the other stream's kernels do not get on the SMs); the link pass
+// as two launches around the receive 359 / 216 against 353 / 211; hundreds of CTAs polling a system-scope flag: 5x slower steps; a
+// collect step inside the link pass (every warp copies a slice, face tiles wait for all): no gain, it is a grid-wide barrier.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -58,17 +65,20 @@ struct Halo {
     // device-side sequence numbers {sent, collected, send arrivals, receive arrivals}: the exchange kernels take the step number from here, not from
     // a kernel argument, so that a stretch of steps can be captured once in a CUDA Graph and replayed
     unsigned int *seq = nullptr;
+    // the link pass reads the neighbours' poses from the receive buffers itself (HaloIn, vx3_device.cuh) unless a neighbour is a batch of this process
+    // (two slabs sharing one device could hold each other's CTA slots while they wait) or VX3_HALO_INKERNEL=0
+    bool inkernel = false;
+    HaloIn *hin = nullptr;
+    unsigned int *state = nullptr;
+    int32_t *ghost_row = nullptr;
+    // ... and the voxel pass sends: a face voxel's record goes to the neighbour as it is computed (HaloOut); needs disjoint face lists
+    bool send_fused = false;
+    HaloOut *hout = nullptr;
+    unsigned int *out_count = nullptr;
     int send_blocks = 0;                          // CTAs of k_halo_send (0: this slab sends nothing)
     int face_tile0 = -1;                          // link tiles [0, face_tile0) hold no link with a ghost end (-1: not analysed yet)
     long long spin_cycles = 0;
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // Both neighbours in one launch: the CTAs [0, nb[0]) serve side 0, the rest side 1; one 16-byte quarter of a pose record per
 // thread and ONE quarter per thread (the grid covers the face), so a kernel is a single round of independent accesses.

@@ -301,6 +301,65 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
     }
 }
 
+
+// ---- halo exchange of a slab batch inside the link pass (vx3_halo.cuh has the protocol) ----
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_sys(unsigned int *p, unsigned int v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_vol_u32(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+__device__ __forceinline__ void halo_fail(SimD *simd, const HaloIn &h) { // a neighbour did not send in time: mark the batch failed and freeze it
+    *h.err = 1;
+    simd->err = VX3_ERR_CUDA;
+    simd->dt = 0.0f; // doTimeStep(0) does nothing (VX3_VoxelyzeKernel.cu:240-241)
+    __threadfence();
+}
+// A slab's link pass reads the poses of its ghost voxels straight from the receive buffers the neighbours wrote (no copy into the
+// ghost voxels' pose rows, no kernel of its own): link tiles [0, face_tile0) touch no ghost; before its first later tile a warp
+// makes sure the neighbours' send number is in.  ONE warp of the grid — the first to get there — waits on the neighbours' flags
+// (system scope) and tells the others through a flag in local memory.  Returns the send number whose buffers are to be read
+// (0: nothing has been sent yet, the ghost rows still hold the model's initial poses).
+__device__ __noinline__ unsigned int halo_arrival_wait(const HaloIn *hin, SimD *simd, int lane) {
+    const HaloIn &h = *hin;
+    const unsigned int step1 = ld_vol_u32(h.seq), collected = ld_vol_u32(h.seq + 1);
+    if (step1 == 0 || collected == step1) return step1; // (collected by k_halo_recv already: the buffers are complete)
+    const int parity = (int)((step1 - 1u) & 1u);
+    unsigned int *claim = h.state, *arrived = h.state + 32; // both hold send numbers and only grow
+    if (lane == 0) {
+        const long long t0 = clock64();
+        if (ld_vol_u32(arrived) < step1) {
+            if (atomicMax(claim, step1) < step1) { // mine to wait for
+                for (int sd = 0; sd < 2; sd++) {
+                    if (h.n[sd] == 0) continue;
+                    while (ld_acquire_sys(h.flag[sd] + 32 * parity) < step1)
+                        if (clock64() - t0 > h.spin_cycles) {
+                            halo_fail(simd, h);
+                            break;
+                        }
+                }
+                __threadfence();
+                *reinterpret_cast<volatile unsigned int *>(arrived) = step1;
+            } else {
+                while (ld_vol_u32(arrived) < step1)
+                    if (clock64() - t0 > 2 * h.spin_cycles) break;
+            }
+        }
+        __threadfence();
+    }
+    __syncwarp();
+    return step1;
+}
+// where a face link's end pose is read: the voxel's own row, or its record in the receive buffer of send number step1
+__device__ __forceinline__ const double2 *halo_pose_row(const HaloIn *hin, const double *pose, int v, unsigned int step1) {
+    const int r = step1 ? __ldg(hin->ghost_row + v) : -1;
+    if (r < 0) return reinterpret_cast<const double2 *>(pose + 8 * (size_t)v);
+    const int sd = r >> 30, slot = r & 0x3FFFFFFF;
+    return reinterpret_cast<const double2 *>(hin->buf[sd] + ((size_t)((step1 - 1u) & 1u) * hin->n[sd] + slot) * 8);
+}
+
 // Second variant of the link pass: a lane whose link turns out to need the large-angle branch
 // does NOT process it — it pushes the link's slot number onto its warp's private queue (shared memory, warp-aggregated
 // push) and idles for the rest of the iteration, so the warp runs the small-angle path only (~780 instructions instead
@@ -309,7 +368,8 @@ __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D,
 // unchanged) and runs the complete update, large-angle branch included, with all lanes busy.  The gathers of a dense pass
 // are uncoalesced, but only the few percent of deferred links pay for that.  Same arithmetic on the same inputs: bit-identical
 // to k_links.  No CTA barrier anywhere.
-template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links_deferred(Dev D, int ntiles, int tile0 = 0) {
+// HALO (slab batches): links of tiles >= HaloIn::face_tile0 may have a ghost end, whose pose comes from the receive buffers.
+template <bool SMTAB, bool HALO = false> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links_deferred(Dev D, int ntiles, int tile0 = 0) {
     __shared__ LinkSmem sm;
     __shared__ int sDef[VX3_LINK_T / 32][64];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -320,6 +380,9 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
     }
     __syncthreads();
     long long tile = (long long)tile0 + blockIdx.x;
+    const long long F = HALO ? D.hin->face_tile0 : 0;
+    bool ghosts_in = false;
+    unsigned int halo_step1 = 0; // the send number whose receive buffers hold the ghost poses (0: none yet)
     int4 c4 = link_c4(D, tile * VX3_LINK_T + tid);
     int nd = 0; // entries in this warp's queue (warp-uniform)
     for (;;) {
@@ -336,6 +399,10 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
         } else if (tiles_left) { // ---- the next tile; the item after it is prefetched into registers ----
             dense = false;
             const int4 c4n = link_c4(D, (tile + G) * VX3_LINK_T + tid);
+            if (HALO && tile >= F && !ghosts_in) {
+                halo_step1 = halo_arrival_wait(D.hin, D.simd, lane);
+                ghosts_in = true;
+            }
             gc = (int)(tile * VX3_LINK_T + tid);
             c = c4;
             c4 = c4n;
@@ -355,6 +422,10 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MI
             const float2 ar = ldv(D.larea + gc);
             L.state = state0 = ldv(D.lstate + gc);
             const double2 *pa = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.x), *pb = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)c.y);
+            if (HALO && ghosts_in) { // a ghost end's pose is in the neighbour's receive buffer
+                pa = halo_pose_row(D.hin, D.pose, c.x, halo_step1);
+                pb = halo_pose_row(D.hin, D.pose, c.y, halo_step1);
+            }
 #if VX3_POSE256
             const double4v A0 = ldgat4(reinterpret_cast<const double *>(pa)), A1 = ldgat4(reinterpret_cast<const double *>(pa) + 4);
             const double4v B0 = ldgat4(reinterpret_cast<const double *>(pb)), B1 = ldgat4(reinterpret_cast<const double *>(pb) + 4);
@@ -487,10 +558,28 @@ __device__ __forceinline__ VoxIdx vox_idx(const Dev &D, long long v) {
         M += V3(fb##dir.y, fc##dir.x, fc##dir.y);                                                                       \
     }
 
-template <bool SMTAB> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MIN_CTAS) k_voxels(Dev D, int ntiles) {
+__device__ void tail_light(const Dev &D, int sim, int check_stop);
+// HALO (slab batches, vx3_halo.cuh): a face voxel's record also goes into the neighbour's receive buffer, and the last CTA to finish
+// publishes the send number to both neighbours and, with tail >= 0, does the end-of-step bookkeeping (tail_light, check_stop = tail).
+template <bool SMTAB, bool HALO = false> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MIN_CTAS) k_voxels(Dev D, int ntiles, int tail = -1) {
     __shared__ VoxSmem sm;
     const int tid = threadIdx.x;
     const long long G = gridDim.x;
+    // this pass is send number seq[0] + 1; every CTA reads the count before the last one to finish moves it
+    const unsigned int send_parity = HALO ? (ld_vol_u32(D.hout->seq) & 1u) : 0u;
+    auto peer_row = [&](int code) -> double * { // code = vc4.w - 1
+        const HaloOut &o = *D.hout;
+        const int sd = code >> 30, slot = code & 0x3FFFFFFF;
+        return o.buf[sd] + ((size_t)send_parity * o.n[sd] + slot) * 8;
+    };
+    bool sent = false; // this thread has stored into a neighbour's buffer
+    auto send_row_as_is = [&](int v, int code) { // a face voxel this pass does not move (fixed, removed, frozen simulation): its row as it stands
+        sent = true;
+        const double2 *src = reinterpret_cast<const double2 *>(D.pose + 8 * (size_t)v);
+        double2 *dst = reinterpret_cast<double2 *>(peer_row(code));
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = ldgat(src + k);
+    };
     if (SMTAB) { // material table -> shared memory
         for (int i = tid; i < D.n_vmats * (int)(sizeof(VoxMatC) / 4); i += VX3_VOX_T) reinterpret_cast<int *>(sm.vm)[i] = reinterpret_cast<const int *>(D.vmat_tab)[i];
         __syncthreads();
@@ -544,8 +633,10 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MI
         const int hot_flags = hot1.y;
         const double temp_amp = __hiloint2double(hot1.w, hot1.z), temp_period = __hiloint2double(hot2.y, hot2.x);
         const VoxMatC &m = SMTAB ? sm.vm[vmi] : D.vmat_tab[vmi];
-        if (status != VX3_SIM_RUNNING || sdiverged) continue;
-        if (dtF == 0) continue;
+        if (status != VX3_SIM_RUNNING || sdiverged || dtF == 0) {
+            if (HALO && id.c4.w) send_row_as_is(v, id.c4.w - 1);
+            continue;
+        }
         const double dt = dtF;
         D.tempe[v] = tempe;
         // temperature the next step will start with (time t + dt), see pack_tp
@@ -556,6 +647,7 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MI
         if (r.flags & VX3_VOX_GHOST) continue; // a neighbour slab owns this voxel: its pose record arrives with the halo exchange
         if ((r.flags & VXF_REMOVED) || m.fixed) {
             if (tempe_next != tempe) D.pose[8 * (size_t)v + 7] = pack_tp(tempe_next, pd_old);
+            if (HALO && id.c4.w) send_row_as_is(v, id.c4.w - 1);
             continue;
         }
         V3 contact(0, 0, 0);
@@ -599,10 +691,37 @@ template <bool SMTAB> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MI
             else r.flags &= ~VXF_ENABLE_ATTACH;
         }
         store_pose(D.pose, v, r.pos, r.orient, tempe_next, dtF);
+        if (HALO && id.c4.w) {
+            sent = true;
+            store_pose(peer_row(id.c4.w - 1), 0, r.pos, r.orient, tempe_next, dtF);
+        }
         *D.mo(0, v) = make_double2(r.linMom.x, r.linMom.y);
         *D.mo(1, v) = make_double2(r.linMom.z, r.angMom.x);
         *D.mo(2, v) = make_double2(r.angMom.y, r.angMom.z);
         if (r.flags != flags0) D.vflags[v] = r.flags; // (the friction / attach bits rarely change)
+    }
+    if (HALO) {
+        // Every sending thread fences its peer stores (system scope) before its CTA counts itself in, so when the last CTA sees the full
+        // count every record is visible to the neighbour: it needs one more fence (cumulativity; nothing of its own is outstanding,
+        // so no NVLink round trip) and two plain system-scope stores — not two store-releases, each of which waits a round trip.
+        // The bookkeeping of the step runs beside it in another warp.
+        __shared__ int sLast;
+        const HaloOut &o = *D.hout;
+        if (sent) __threadfence_system();
+        __syncthreads();
+        if (tid == 0) sLast = atomicAdd(o.count, 1u) == (unsigned int)G - 1;
+        __syncthreads();
+        if (sLast) { // every CTA's records are out, every CTA has read seq and simd
+            if (tid == 0) {
+                *o.count = 0u;
+                const unsigned int step1 = ld_vol_u32(o.seq) + 1u;
+                __threadfence_system();
+                for (int sd = 0; sd < 2; sd++)
+                    if (o.n[sd] > 0) st_relaxed_sys(o.flag[sd] + 32 * (int)send_parity, step1);
+                *reinterpret_cast<volatile unsigned int *>(o.seq) = step1;
+            } else if (tid == 32 && tail >= 0)
+                tail_light(D, 0, tail);
+        }
     }
 }
 

@@ -156,6 +156,9 @@ def partition_slabs(desc, world, rank, axis=0):
     used[vneg[keep_l]] = True
     used[vpos[keep_l]] = True
     keep_v = _np.nonzero(used)[0]
+    # owned voxels first, ghosts last: the engine's voxel pass runs over the owned prefix only (a ghost's record arrives with the halo
+    # exchange; the order of a model's voxels carries no meaning where slabs are allowed: no collisions, no signals)
+    keep_v = _np.concatenate([keep_v[own[keep_v]], keep_v[~own[keep_v]]])
     newv = -_np.ones(nv, _np.int32)
     newv[keep_v] = _np.arange(len(keep_v), dtype=_np.int32)
     newl = -_np.ones(max(nl, 1), _np.int32)
