@@ -121,7 +121,8 @@ struct alignas(16) SimD {
     int32_t hot_flags; // SHF_* (constant)
     double temp_amp;   // TempAmplitude (constant)
     double temp_period; // TempPeriod (constant)
-    int32_t _hot_pad[2];
+    int32_t topo_epoch; // bumped whenever a link of the simulation is created, detached or removed (validates Dev::nbcache entries); starts at 1
+    int32_t _hot_pad;
     long long steps;   // CurStepCount
     int32_t link_cnt;  // d_v_links.size()
     int32_t collision_count;
@@ -258,6 +259,8 @@ struct Dev {
     CellItem *cell_items;
     struct ContactRec *crec; // [nvox] what the contact phase needs of a voxel, in one 64-byte record (written by k_grid_build)
     int32_t *uf;      // [nvox] union-find parents over the voxels (NULL unless a simulation can attach), see uf_find
+    int2 *nbcache;    // [nvox][8] {partner, topo_epoch << 1 | answer}: what within_five_links said about (voxel, partner) while the link graph
+                      // was at that epoch — a settled pile asks the same questions every step (allocated with vnb)
     int32_t *vnb;     // [nvox][8] the voxel at the far end of each of the six link slots (-1: none; two pad entries) — the link graph as
                       // an adjacency table for within_five_links (allocated with uf; kept current by attach / detach / removal)
     Cand *cands;        // per-simulation regions (SimC::cand_off / cand_cap), counts in SimD::cand_count

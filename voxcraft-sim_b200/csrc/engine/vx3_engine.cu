@@ -740,6 +740,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                        (S.enable_detach ? SHF_DETACH : 0) | (S.secondary_experiment ? SHF_SECONDARY : 0) | (S.prog_n[VX3_PROG_STOP] > 0 ? SHF_STOP_PROG : 0);
         dy.temp_amp = S.temp_amp;
         dy.temp_period = S.temp_period;
+        dy.topo_epoch = 1;
         b->vmat_local[s].assign(m.vox_mat, m.vox_mat + m.n_voxels);
         sb[s].ext_base = (int)exts.size();
         for (int i = 0; i < m.n_externals; i++) {
@@ -1002,6 +1003,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                     if (li >= 0) vnb_host[8 * v + k] = lends[li].x == (int)v ? lends[li].y : lends[li].x;
                 }
             plan.upload(&D.vnb, vnb_host);
+            plan.zeroed(&D.nbcache, nvox * 8);
         }
     }
     {

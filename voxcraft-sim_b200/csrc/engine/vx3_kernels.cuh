@@ -939,6 +939,35 @@ __device__ bool is_neighbor_dfs(const Dev &D, int v1, int v2, int depth) {
     return false;
 }
 
+// The contact phase's question "are hi and lo within five links?", with memory: the answer depends on the link graph only, the
+// graph changes on a handful of steps (SimD::topo_epoch counts the changes), and a settled pile asks about the same touching
+// pairs every step.  Eight entries per voxel (its row is written by the lanes of the one warp that leads the voxel's pairs; an entry
+// is one 8-byte word, so a reader sees an old or a new entry, never a torn one, and either is valid for the epoch it names).
+// Only k_contact uses it: the resolve phase changes the graph between its own queries.
+__device__ __forceinline__ bool within_five_links_cached(const Dev &D, int sim, int hi, int lo) {
+    if (!D.nbcache) return is_neighbor(D, hi, lo, 5);
+    const int epoch = D.simd[sim].topo_epoch;
+    int2 *row = D.nbcache + 8 * (size_t)hi;
+    const int4 *r4 = reinterpret_cast<const int4 *>(row);
+    const int4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3];
+    const int px[8] = {q0.x, q0.z, q1.x, q1.z, q2.x, q2.z, q3.x, q3.z}, ev[8] = {q0.y, q0.w, q1.y, q1.w, q2.y, q2.w, q3.y, q3.w};
+    int victim = -1;
+    const int h0 = (int)(((unsigned)lo * 0x9E3779B1u) >> 29);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (px[k] == lo && (ev[k] >> 1) == epoch) return ev[k] & 1;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { // a stale entry to replace, looked for from a partner-dependent start so that lanes spread out
+        const int j = (h0 + k) & 7;
+        if (victim < 0 && (ev[j] >> 1) != epoch) victim = j;
+    }
+    if (victim < 0) victim = h0;
+    const bool nb = is_neighbor(D, hi, lo, 5);
+    row[victim] = make_int2(lo, (epoch << 1) | (nb ? 1 : 0));
+    return nb;
+}
+
 // test hook (vx3_batch_check_neighbor_search): both searches on pseudo-random pairs of one simulation's voxels
 __global__ void k_check_neighbor_search(Dev D, int v0, int nv, int n_pairs, unsigned seed, int *out2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1133,7 +1162,7 @@ __device__ __forceinline__ V3 contact_partner(const Dev &D, const SimC &S, int v
     }
     // slots only fill up during the attach phase, so an occupied slot now stays a rejection at this pair's turn
     if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) return f;
-    if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) return f; // links are only added during the phase: true now stays true
+    if (!uf_disconnected(D, hi, lo) && within_five_links_cached(D, D.vsim[hi], hi, lo)) return f; // links are only added during the phase: true now stays true
     const int slot = atomicAdd(&D.simd[D.vsim[hi]].cand_count, 1);
     if (slot < S.cand_cap) {
         Cand cd;
@@ -1393,6 +1422,7 @@ __device__ void resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, u
     const float sn = (float)mn.nomSize, sp = (float)mp.nomSize; // transverseArea() with zero strain
     D.larea[g] = make_float2(0.5f * (sn * sn + sp * sp), 0.0f);
     dy.attach_events++;
+    dy.topo_epoch++;
     if (D.uf) { // the two voxels' trees become one
         const int ra = uf_find(D, hi), rb = uf_find(D, lo);
         if (ra != rb) D.uf[ra > rb ? ra : rb] = ra > rb ? rb : ra;
@@ -1479,6 +1509,7 @@ __global__ void __launch_bounds__(VX3_RESOLVE_T) k_resolve_detach(Dev D) {
                 }
             }
             atomicAdd(&dy.detach_events, 1);
+            atomicAdd(&dy.topo_epoch, 1);
         }
     }
     __syncthreads();
@@ -1512,6 +1543,7 @@ __global__ void __launch_bounds__(VX3_BLOCK) k_secondary(Dev D) {
             const int li = D.vlinks[6 * (size_t)v + k];
             if (li < 0) continue;
             D.lstate[li] |= LKS_REMOVED; // (a neighbour removed in the same step sets the same bit: benign)
+            atomicAdd(&D.simd[sim].topo_epoch, 1);
             const int2 e = D.lends[li];
             const int nb = (e.x == v) ? e.y : e.x;
             for (int q = 0; q < 6; q++)
