@@ -1010,8 +1010,6 @@ __device__ __forceinline__ V3 pair_contact_force(const Dev &D, int hi, int lo, c
 struct ContactSelf {
     int v;
     ContactRec r;
-    bool have_links;
-    int vl[6], vo[6]; // own links and their other ends (loaded when the first candidate passes the envelope test)
     // first cut on the bucket's float positions: nothing farther than the largest possible envelope of this simulation (= the
     // grid's cell edge) plus the rounding of the two float positions can pass the exact test; voxels of other simulations that
     // hashed to the bucket fall outside [vlo, vhi)
@@ -1035,7 +1033,6 @@ __device__ __forceinline__ ContactRec load_crec(const Dev &D, int v) {
 __device__ __forceinline__ void contact_self(const Dev &D, int v, ContactSelf &c) {
     c.v = v;
     c.r = load_crec(D, v);
-    c.have_links = false;
     if (c.r.bucket >= 0) {
         const SimC &S = D.simc[c.r.sim];
         c.fx = (float)c.r.px; c.fy = (float)c.r.py; c.fz = (float)c.r.pz;
@@ -1046,79 +1043,13 @@ __device__ __forceinline__ void contact_self(const Dev &D, int v, ContactSelf &c
         c.vhi = S.voff + S.nvox;
     }
 }
-// conservative: false only when the exact envelope test of contact_candidate must fail as well
+// conservative: false only when the exact envelope test (contact_envelope) must fail as well
 __device__ __forceinline__ bool contact_first_cut(const ContactSelf &c, const float4 it) {
     const int u = __float_as_int(it.w);
     if (u < c.vlo || u >= c.vhi || u == c.v) return false;
     const float dx = it.x - c.fx, dy = it.y - c.fy, dz = it.z - c.fz;
     return dx * dx + dy * dy + dz * dz <= c.reach * c.reach;
 }
-__device__ __forceinline__ void contact_self_links(const Dev &D, ContactSelf &c) {
-    if (c.have_links) return;
-    c.have_links = true;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        c.vl[i] = D.vlinks[6 * (size_t)c.v + i];
-        c.vo[i] = -1;
-        if (c.vl[i] >= 0) {
-            const int2 e = D.lends[c.vl[i]];
-            c.vo[i] = (e.x == c.v) ? e.y : e.x;
-        }
-    }
-}
-__device__ __forceinline__ bool contact_candidate(const Dev &D, ContactSelf &c, int u, int cx, int cy, int cz, bool &fresh) {
-    const int v = c.v;
-    fresh = false;
-    if (u == v) return false;
-    const ContactRec ur = load_crec(D, u);
-    if (ur.cx != cx || ur.cy != cy || ur.cz != cz || ur.sim != c.r.sim) return false; // other cell hashed to this bucket
-    if (c.r.fixed && ur.fixed) return false;
-    const V3 pv(c.r.px, c.r.py, c.r.pz), pu(ur.px, ur.py, ur.pz);
-    const V3 diff = (v > u) ? (pv - pu) : (pu - pv); // voxel1 - voxel2, voxel1 = higher index
-    const double watch = ((v > u) ? (c.r.bs + ur.bs) : (ur.bs + c.r.bs)) * VX3_COLLISION_ENVELOPE_RADIUS;
-    if (diff.x > watch || diff.x < -watch) return false;
-    if (diff.y > watch || diff.y < -watch) return false;
-    if (diff.z > watch || diff.z < -watch) return false;
-    if (diff.Length() > watch) return false;
-    contact_self_links(D, c);
-    bool linked = false;
-#pragma unroll
-    for (int i = 0; i < 6; i++)
-        if (c.vo[i] == u) {
-            linked = true;
-            if (D.lstate[c.vl[i]] & LKS_JUST_CREATED) fresh = true;
-        }
-    return !(linked && !fresh);
-}
-__device__ __forceinline__ void prefetch_crec(const Dev &D, int u) { asm volatile("prefetch.global.L2 [%0];" ::"l"(D.crec + u)); }
-// All voxels of bucket b that survive the first cut, through fn(u): the bucket's inline slots (voxel + float position, two
-// 64-byte halves of one line), then the overflow chain (rare; no float copy, so every chained voxel goes to the exact test).
-#ifndef VX3_CONTACT_FIRSTCUT
-#define VX3_CONTACT_FIRSTCUT 1
-#endif
-template <class F> __device__ __forceinline__ void bucket_for_each(const Dev &D, const ContactSelf &c, int b, F fn) {
-    const int n = D.cell_cnt[b];
-    if (n == 0) return;
-    const float4 *items = reinterpret_cast<const float4 *>(D.cell_items + VX3_CELL_SLOTS * (size_t)b);
-    const int m = n < VX3_CELL_SLOTS ? n : VX3_CELL_SLOTS;
-    float4 it[VX3_CELL_SLOTS];
-#pragma unroll
-    for (int k = 0; k < VX3_CELL_SLOTS; k++)
-        if (k < m) it[k] = __ldcg(items + k); // written by k_grid_build (an earlier kernel of the step)
-    unsigned pass = 0;
-#pragma unroll
-    for (int k = 0; k < VX3_CELL_SLOTS; k++)
-        if (k < m && (!VX3_CONTACT_FIRSTCUT || contact_first_cut(c, it[k]))) pass |= 1u << k;
-#pragma unroll
-    for (int k = 0; k < VX3_CELL_SLOTS; k++) // the survivors' records are independent loads: start them all before the first is used
-        if (pass & (1u << k)) prefetch_crec(D, __float_as_int(it[k].w));
-#pragma unroll
-    for (int k = 0; k < VX3_CELL_SLOTS; k++)
-        if (pass & (1u << k)) fn(__float_as_int(it[k].w));
-    if (n > VX3_CELL_SLOTS)
-        for (int u = D.cell_ovf[b] - 1; u >= 0; u = D.cell_next[u]) fn(u);
-}
-
 // One partner of v (sorted position irrelevant here): contact force on v from this pair, target hit, signal trigger and,
 // for the pairs v leads (v is the higher index) when emit is set, the attach-candidate test (:729-812) on the step-start
 // link graph with an atomic append of the candidate.
@@ -1186,59 +1117,10 @@ __device__ __forceinline__ void contact_fire_signal(const Dev &D, const SimD &dy
     sg[5] = t;
 }
 
-// Contact phase of one surface voxel, one thread (used by k_resolve to re-evaluate the two voxels of an accepted attach in
-// sequence position): all partners inside the collision envelope, accumulated in ascending partner index = the canonical
-// sequential pair order.
-__device__ __noinline__ void contact_phase(const Dev &D, int v, bool emit) {
-    ContactSelf cs;
-    contact_self(D, v, cs);
-    const SimC &S = D.simc[cs.r.sim];
-    SimD &dy = D.simd[cs.r.sim];
-    int partner[VX3_MAX_PARTNERS];
-    int np = 0;
-    for (int dz = -1; dz <= 1; dz++)
-        for (int dy_ = -1; dy_ <= 1; dy_++)
-            for (int dx = -1; dx <= 1; dx++) {
-                const int cx = cs.r.cx + dx, cy = cs.r.cy + dy_, cz = cs.r.cz + dz;
-                const int b = (int)(cell_hash(cs.r.sim, cx, cy, cz) & (unsigned)D.hmask);
-                bucket_for_each(D, cs, b, [&](int u) {
-                    bool fresh;
-                    if (!contact_candidate(D, cs, u, cx, cy, cz, fresh)) return;
-                    if (np < VX3_MAX_PARTNERS) partner[np++] = fresh ? (u | (1 << 30)) : u;
-                    else dy.err = VX3_ERR_CAPACITY;
-                });
-            }
-    // ascending partner index (insertion sort; np is small)
-    for (int i = 1; i < np; i++) {
-        const int key = partner[i];
-        int j = i - 1;
-        while (j >= 0 && (partner[j] & 0x3FFFFFFF) > (key & 0x3FFFFFFF)) {
-            partner[j + 1] = partner[j];
-            j--;
-        }
-        partner[j + 1] = key;
-    }
-    V3 c(0, 0, 0);
-    int hits = 0;
-    bool fire = false; // EnableSignals: a non-target voxel touching a target voxel fires (:719-725)
-    for (int i = 0; i < np; i++) {
-        const V3 f = contact_partner(D, S, v, partner[i], emit, hits, fire);
-        if (S.enable_collision) {
-            c += f;
-            if ((partner[i] >> 30) & 1) c -= f; // a link was created for this pair: its contact force is taken back (:827-830)
-        }
-    }
-    if (S.enable_collision) {
-        store3(D.contact, v, c);
-        if (emit && hits) atomicAdd(&dy.collision_count, hits);
-        if (emit && fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.r.mat);
-    }
-}
-
 // The contact phase of the step, one WARP per surface voxel: 27 lanes walk the 27 cells around the voxel's cell at once,
 // the partners found are ranked by index, every lane evaluates one partner (contact force, target hit, attach-candidate
 // test incl. the depth-5 neighbour search), and lane 0 adds the forces up in ascending partner index — the same sums in the
-// same order as the one-thread version above.
+// canonical sequential pair order.
 #define VX3_CONTACT_WARPS 4
 #ifndef VX3_CONTACT_MIN_CTAS
 #define VX3_CONTACT_MIN_CTAS 8 // 64 registers: the phase is a chain of dependent loads per warp, so resident warps are what counts (6 / 8 / 10 / 12 CTAs: 59.9 / 52.4 / 62.2 / 69.6 us on config 4)
@@ -1256,21 +1138,24 @@ __device__ __forceinline__ bool contact_envelope(const ContactRec &rv, int v, co
     return !(diff.Length() > watch);
 }
 
-__global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) k_contact(Dev D) {
-    __shared__ int sSurv[VX3_CONTACT_WARPS][VX3_MAX_SURVIVORS];
-    __shared__ unsigned char sFrom[VX3_CONTACT_WARPS][VX3_MAX_SURVIVORS]; // which of the 27 cells the survivor was found under
-    __shared__ int sList[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS], sSorted[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS];
-    __shared__ double sForce[VX3_CONTACT_WARPS][VX3_MAX_PARTNERS][3];
-    __shared__ int sCnt[VX3_CONTACT_WARPS][2];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int v = blockIdx.x * VX3_CONTACT_WARPS + w;
-    if (v >= D.nvox) return; // (whole warps leave together)
+// one warp's scratch for contact_warp
+struct ContactWarpSmem {
+    int surv[VX3_MAX_SURVIVORS];
+    unsigned char from[VX3_MAX_SURVIVORS]; // which of the 27 cells the survivor was found under
+    int list[VX3_MAX_PARTNERS], sorted[VX3_MAX_PARTNERS];
+    double force[VX3_MAX_PARTNERS][3];
+    int cnt[2];
+};
+// emit: the step's contact phase (k_contact).  !emit: the re-evaluation of the two voxels of an attach the resolve phase has just
+// accepted (the pair's contact force is added and taken back in its place in the sum, :827-830) — forces only: no attach
+// candidates, no collision count, no signal.
+__device__ __forceinline__ void contact_warp(const Dev &D, int v, bool emit, int lane, ContactWarpSmem &W) {
     ContactSelf cs;
     contact_self(D, v, cs);
     if (cs.r.bucket < 0) return;
     const SimC &S = D.simc[cs.r.sim];
     SimD &dy = D.simd[cs.r.sim];
-    if (lane < 2) sCnt[w][lane] = 0;
+    if (lane < 2) W.cnt[lane] = 0;
     // ---- my own links, one per lane: the far end, and whether the link was made in this step (its contact force is added and
     // taken back, :827-830) — a plain lattice neighbour is no contact partner (is_neighbor depth 1, :699-703) ----
     int my_vo = -1, my_fresh = 0;
@@ -1299,10 +1184,10 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
                 if (!((freshmask >> i) & 1)) return; // linked, and not in this step: never a partner
                 tag = u | (1 << 30);
             }
-        const int k = atomicAdd(&sCnt[w][0], 1);
+        const int k = atomicAdd(&W.cnt[0], 1);
         if (k < VX3_MAX_SURVIVORS) {
-            sSurv[w][k] = tag;
-            sFrom[w][k] = (unsigned char)lane;
+            W.surv[k] = tag;
+            W.from[k] = (unsigned char)lane;
         }
     };
     if (lane < 27) {
@@ -1326,24 +1211,24 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
         }
     }
     __syncwarp();
-    int ns = sCnt[w][0];
+    int ns = W.cnt[0];
     if (ns > VX3_MAX_SURVIVORS) {
         if (lane == 0) dy.err = VX3_ERR_CAPACITY;
         ns = VX3_MAX_SURVIVORS;
     }
     // ---- stage 2: one lane per survivor: its record, the exact test (same cell-independent arithmetic as the all-pairs sweep) ----
     for (int i = lane; i < ns; i += 32) {
-        const int tag = sSurv[w][i], u = tag & 0x3FFFFFFF;
+        const int tag = W.surv[i], u = tag & 0x3FFFFFFF;
         const ContactRec ur = load_crec(D, u);
         // two of the 27 cells (or a cell of another simulation) may share a hash bucket: a voxel counts only under its own cell
-        const int from = sFrom[w][i];
+        const int from = W.from[i];
         if (ur.cx != cs.r.cx + from % 3 - 1 || ur.cy != cs.r.cy + (from / 3) % 3 - 1 || ur.cz != cs.r.cz + from / 9 - 1 || ur.sim != cs.r.sim) continue;
         if (!contact_envelope(cs.r, v, ur, u)) continue;
-        const int k = atomicAdd(&sCnt[w][1], 1);
-        if (k < VX3_MAX_PARTNERS) sList[w][k] = tag;
+        const int k = atomicAdd(&W.cnt[1], 1);
+        if (k < VX3_MAX_PARTNERS) W.list[k] = tag;
     }
     __syncwarp();
-    int n = sCnt[w][1];
+    int n = W.cnt[1];
     if (n > VX3_MAX_PARTNERS) {
         if (lane == 0) dy.err = VX3_ERR_CAPACITY;
         n = VX3_MAX_PARTNERS;
@@ -1354,17 +1239,17 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
     }
     // rank by partner index (indices are unique)
     for (int i = lane; i < n; i += 32) {
-        const int key = sList[w][i] & 0x3FFFFFFF;
+        const int key = W.list[i] & 0x3FFFFFFF;
         int r = 0;
-        for (int j = 0; j < n; j++) r += (sList[w][j] & 0x3FFFFFFF) < key;
-        sSorted[w][r] = sList[w][i];
+        for (int j = 0; j < n; j++) r += (W.list[j] & 0x3FFFFFFF) < key;
+        W.sorted[r] = W.list[i];
     }
     __syncwarp();
     int hits = 0;
     bool fire = false;
     for (int i = lane; i < n; i += 32) {
-        const V3 f = contact_partner(D, S, v, sSorted[w][i], true, hits, fire);
-        sForce[w][i][0] = f.x; sForce[w][i][1] = f.y; sForce[w][i][2] = f.z;
+        const V3 f = contact_partner(D, S, v, W.sorted[i], emit, hits, fire);
+        W.force[i][0] = f.x; W.force[i][1] = f.y; W.force[i][2] = f.z;
     }
     __syncwarp();
     hits = __reduce_add_sync(0xFFFFFFFFu, hits);
@@ -1372,14 +1257,22 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
     if (lane == 0 && S.enable_collision) {
         V3 c(0, 0, 0);
         for (int i = 0; i < n; i++) {
-            const V3 f(sForce[w][i][0], sForce[w][i][1], sForce[w][i][2]);
+            const V3 f(W.force[i][0], W.force[i][1], W.force[i][2]);
             c += f;
-            if ((sSorted[w][i] >> 30) & 1) c -= f;
+            if ((W.sorted[i] >> 30) & 1) c -= f;
         }
         store3(D.contact, v, c);
-        if (hits) atomicAdd(&dy.collision_count, hits);
-        if (fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.r.mat);
+        if (emit && hits) atomicAdd(&dy.collision_count, hits);
+        if (emit && fire && S.enable_signals) contact_fire_signal(D, dy, v, cs.r.mat);
     }
+}
+
+__global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) k_contact(Dev D) {
+    __shared__ ContactWarpSmem sm[VX3_CONTACT_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int v = blockIdx.x * VX3_CONTACT_WARPS + w;
+    if (v >= D.nvox) return; // (whole warps leave together)
+    contact_warp(D, v, true, lane, sm[w]);
 }
 
 // Attach resolution, then detach, for ONE simulation per CTA.
@@ -1394,14 +1287,15 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
 #ifndef VX3_RESOLVE_T
 #define VX3_RESOLVE_T 256
 #endif
-__device__ void resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, unsigned long long key, int info) {
+// (true: the link was made — the caller re-evaluates the two voxels' contact forces)
+__device__ bool resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, unsigned long long key, int info) {
     const int hi = (int)(key >> 32), lo = (int)(key & 0xFFFFFFFFu);
     const int dir1 = info & 7, dir2 = (info >> 3) & 7, axis = (info >> 6) & 3, rev = (info >> 8) & 1;
-    if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) return;
-    if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) return;
-    if (dy.link_cnt >= S.lcap) { dy.err = VX3_ERR_CAPACITY; return; }
+    if (D.vlinks[6 * (size_t)hi + dir1] >= 0 || D.vlinks[6 * (size_t)lo + dir2] >= 0) return false;
+    if (!uf_disconnected(D, hi, lo) && is_neighbor(D, hi, lo, 5)) return false;
+    if (dy.link_cnt >= S.lcap) { dy.err = VX3_ERR_CAPACITY; return false; }
     const VoxMatC &mh = D.vmat_tab[D.vmat[hi]];
-    if (mh.self_lmat < 0) { dy.err = VX3_ERR_INVALID; return; }
+    if (mh.self_lmat < 0) { dy.err = VX3_ERR_INVALID; return false; }
     const int g = S.loff + dy.link_cnt++;
     const int vneg = rev ? lo : hi, vpos = rev ? hi : lo; // pVNeg/pVPos of VX3_Link(voxelA, dirA, voxelB, dirB)
     D.vlinks[6 * (size_t)hi + dir1] = g;
@@ -1428,15 +1322,13 @@ __device__ void resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, u
         if (ra != rb) D.uf[ra > rb ? ra : rb] = ra > rb ? rb : ra;
     }
     __threadfence_block();
-    if (S.enable_collision) { // take this pair's contact force back in sequence position (:827-830)
-        contact_phase(D, hi, false);
-        contact_phase(D, lo, false);
-    }
+    return true;
 }
 
 __global__ void __launch_bounds__(VX3_RESOLVE_T) k_resolve_detach(Dev D) {
     __shared__ unsigned long long skey[VX3_RESOLVE_SM];
     __shared__ int sinfo[VX3_RESOLVE_SM];
+    __shared__ ContactWarpSmem cw;
     const int sim = blockIdx.x;
     const SimC &S = D.simc[sim];
     SimD &dy = D.simd[sim];
@@ -1483,11 +1375,23 @@ __global__ void __launch_bounds__(VX3_RESOLVE_T) k_resolve_detach(Dev D) {
                 }
                 __syncthreads();
             }
-        if (threadIdx.x == 0)
+        if (threadIdx.x < 32) { // one warp: lane 0 takes the candidates in order; an accepted pair's two voxels get their contact forces
+                                // re-evaluated by the whole warp (the pair's force is added and taken back in its place, :827-830)
+            const int lane = threadIdx.x;
             for (int c = 0; c < n; c++) {
-                if (in_sm) resolve_accept(D, S, dy, sim, skey[c], sinfo[c]);
-                else resolve_accept(D, S, dy, sim, cands[c].key, cands[c].info);
+                const unsigned long long key = in_sm ? skey[c] : cands[c].key;
+                int made = 0;
+                if (lane == 0) made = resolve_accept(D, S, dy, sim, key, in_sm ? sinfo[c] : cands[c].info) ? 1 : 0;
+                made = __shfl_sync(0xFFFFFFFFu, made, 0);
+                if (made && S.enable_collision) {
+                    __syncwarp();
+                    contact_warp(D, (int)(key >> 32), false, lane, cw);
+                    __syncwarp();
+                    contact_warp(D, (int)(key & 0xFFFFFFFFu), false, lane, cw);
+                    __syncwarp();
+                }
             }
+        }
     }
     __syncthreads(); // detach after attach
     if (nfail > 0 && running) {
