@@ -121,11 +121,16 @@ def test_face_lists_agree_world2_gloo():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 3])
-def test_slabs_with_halo_exchange_match_whole_body_bit_exactly(world):
+@pytest.mark.parametrize("world,exchange", [(2, "kernels"), (3, "kernels"), (2, "in_step"), (3, "in_step")])
+def test_slabs_with_halo_exchange_match_whole_body_bit_exactly(world, exchange, monkeypatch):
     """One process drives all slabs (batches on one device, wired with halo_connect_local) against the whole body: the face
-    links are evaluated on both sides from identical inputs, so every owned voxel must agree bit for bit."""
+    links are evaluated on both sides from identical inputs, so every owned voxel must agree bit for bit.  `kernels`: the
+    stand-alone send / wait / receive kernels (the default between slabs of one process); `in_step`: the multi-GPU default —
+    the voxel pass sends, the link pass reads the receive buffers (vx3_halo.cuh) — forced onto the one-process set-up."""
     from util import EngineBatch
+    if exchange == "in_step":
+        monkeypatch.setenv("VX3_HALO_INKERNEL", "2")
+        monkeypatch.setenv("VX3_HALO_TIMEOUT_MS", "5000")
     lib, b, d = build_full((9, 4, 3), seed=21, holes=0.1)
     try:
         dt = float(np.float32(0.9 * lib.vx3_model_recommended_dt(d)))

@@ -1338,7 +1338,10 @@ static int halo_prepare(vx3_batch *b) {
     H.spin_cycles = (long long)(ms * (double)khz);
     H.face_tile0 = 0;
     const char *ik = getenv("VX3_HALO_INKERNEL");
-    H.inkernel = !(ik && ik[0] == '0') && !H.side[0].peer_local && !H.side[1].peer_local && !(b->use_fused && b->fplan.ok) && b->D.nlinkslots > 0;
+    // (VX3_HALO_INKERNEL=2, a test hook: also between two small slabs of one process, where the stand-alone kernels are the default
+    // because a waiting link pass of one slab could hold the CTA slots the other slab needs)
+    const bool local = H.side[0].peer_local || H.side[1].peer_local;
+    H.inkernel = !(ik && ik[0] == '0') && (!local || (ik && ik[0] == '2')) && !(b->use_fused && b->fplan.ok) && b->D.nlinkslots > 0;
     // two-range link pass (interior links before the receive) as two launches: opt-in — measured no faster than send-early /
     // receive-late alone (4 GPUs 359 vs 353, 8 GPUs 216 vs 211 us per step): the second link launch costs what the hidden wait saves
     const bool two_launch = !H.inkernel && b->D.nlinkslots > 0 && getenv("VX3_HALO_OVERLAP") && getenv("VX3_HALO_OVERLAP")[0] == '1';
