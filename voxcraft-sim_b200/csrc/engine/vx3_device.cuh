@@ -205,6 +205,7 @@ struct Dev {
     int32_t nsims, nvox, nlinkslots, nchunks;
     const HaloIn *hin;   // slab batches whose link pass reads the receive buffers itself, else NULL
     const HaloOut *hout; // slab batches whose voxel pass sends, else NULL
+    unsigned int *vox_count; // arrival counter of the voxel pass's CTAs (the last one does the end-of-step bookkeeping, k_voxels)
     const SimC *simc;
     SimD *simd;
     const VoxMatC *vmat_tab;

@@ -297,6 +297,7 @@ struct vx3_batch {
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
     bool any_ghost = false;
+    bool tail_in_voxels = false; // plain steps of batches of <= 128 simulations: k_voxels' last CTA does k_tail_light's work (VX3_TAIL_FUSED=0: off)
     size_t vox_active = 0; // voxels [vox_active, nvox) are all ghosts (a slab model lists them last): the voxel pass leaves their tiles out
     int link_queue = -1; // link pass variant: -1 = still being timed (launch_links), 0 = in place, 1 = deferred dense passes
     int lq_trials = 0;
@@ -966,6 +967,13 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
 #undef UP
     plan.zeroed(&D.lf2, 6 * LS);
     plan.zeroed(&D.com_part, chunks.size() * 6);
+    plan.zeroed(&D.vox_count, 1);
+    {
+        const char *tf = getenv("VX3_TAIL_FUSED");
+        // measured: config 4 (one simulation) 61.8 -> 59.4 us per step; config 3 (512 simulations: four rounds of dependent loads in one
+        // CTA at the end of the pass) 91.4 -> 94.9 — so only where one round covers every simulation
+        b->tail_in_voxels = !(tf && tf[0] == '0') && !b->any_signals && !b->any_secondary && n <= VX3_VOX_T;
+    }
     if (b->any_collide) {
         int H = 1024; // buckets >= 2 x voxels: two occupied cells in one bucket are rare, a walk meets few foreign voxels
         while ((size_t)H < 2 * nvox && H < (1 << 24)) H <<= 1;
@@ -1475,13 +1483,17 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     // attach resolution, then detach, one CTA per simulation (both usually find empty lists and leave at once)
     if ((b->any_sticky || b->any_detach) && D.nlinkslots > 0) LAUNCH(KC_RESOLVE, k_resolve_detach, b->nsims, VX3_RESOLVE_T, D);
     const bool com = !b->capturing && com_step(b, b->hsteps + 1);
+    int tail_in_voxels = -1; // >= 0: the voxel pass's last CTA does the end-of-step bookkeeping
     if (fused) {
     } else if (b->halo.on && b->halo.send_fused) { // the voxel pass sends the face poses and, on a plain step, does the end-of-step bookkeeping
         const int tail = com ? -1 : (check_stop ? 1 : 0);
         if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, (k_voxels<true, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
         else LAUNCH_SM(KC_VOXELS, (k_voxels<false, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
-    } else if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, -1);
-    else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, -1);
+    } else {
+        tail_in_voxels = !com && b->tail_in_voxels ? (check_stop ? 1 : 0) : -1;
+        if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail_in_voxels);
+        else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail_in_voxels);
+    }
     if (b->any_signals) LAUNCH(KC_SIGNALS, k_signals, b->nsims, 256, D); // end of timeStep (VX3_Voxel.cu:270-275), before removeVoxels
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
@@ -1489,7 +1501,7 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     int tail_in_send = -1;
     const bool sent_by_voxel_pass = !fused && b->halo.on && b->halo.send_fused;
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
-    else if (sent_by_voxel_pass) {
+    else if (sent_by_voxel_pass || tail_in_voxels >= 0) {
     } else if (b->halo.on && b->halo.send_blocks > 0) tail_in_send = check_stop ? 1 : 0;
     else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
     if (sent_by_voxel_pass) b->halo.pending = true;

@@ -722,6 +722,18 @@ template <bool SMTAB, bool HALO = false> __global__ void __launch_bounds__(VX3_V
             } else if (tid == 32 && tail >= 0)
                 tail_light(D, 0, tail);
         }
+    } else if (tail >= 0) {
+        // plain steps of any other batch: the last CTA to finish does what k_tail_light would do in a launch of its own (every CTA
+        // has consumed the simulations' scalars before it counts itself in; nothing between the voxel pass and the end of the step
+        // reads them in the batches this is used for — no signals, no voxel removal)
+        __shared__ int sLastT;
+        __syncthreads();
+        if (tid == 0) sLastT = atomicAdd(D.vox_count, 1u) == (unsigned int)G - 1;
+        __syncthreads();
+        if (sLastT) {
+            if (tid == 0) *D.vox_count = 0u;
+            for (int sim = tid; sim < D.nsims; sim += VX3_VOX_T) tail_light(D, sim, tail);
+        }
     }
 }
 
