@@ -297,6 +297,7 @@ struct vx3_batch {
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
     bool any_ghost = false;
+    bool pdl = false; // programmatic dependent launch between the step kernels (launch_pdl; VX3_PDL=1)
     bool tail_in_voxels = false; // plain steps of batches of <= 128 simulations: k_voxels' last CTA does k_tail_light's work (VX3_TAIL_FUSED=0: off)
     size_t vox_active = 0; // voxels [vox_active, nvox) are all ghosts (a slab model lists them last): the voxel pass leaves their tiles out
     int link_queue = -1; // link pass variant: -1 = still being timed (launch_links), 0 = in place, 1 = deferred dense passes
@@ -969,6 +970,8 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     plan.zeroed(&D.com_part, chunks.size() * 6);
     plan.zeroed(&D.vox_count, 1);
     {
+        const char *pe = getenv("VX3_PDL");
+        b->pdl = pe && pe[0] == '1';
         const char *tf = getenv("VX3_TAIL_FUSED");
         // measured: config 4 (one simulation) 61.8 -> 59.4 us per step; config 3 (512 simulations: four rounds of dependent loads in one
         // CTA at the end of the pass) 91.4 -> 94.9 — so only where one round covers every simulation
@@ -1186,6 +1189,35 @@ static long long next_com_step(const vx3_batch *b) {
     return best;
 }
 
+// Programmatic dependent launch for the kernels that begin with VX3_PDL_ENTRY (vx3_kernels.cuh): the next kernel's CTAs are scheduled
+// while the previous kernel drains and wait at their first instruction until it has completed and its writes are visible —
+// what overlaps is the launch gap between two dependent kernels, nothing else.  Opt-in (VX3_PDL=1): measured no faster inside the
+// replayed graphs (config 3 92.5 -> 93.5, config 4 59.6 -> 60.3 us per step; the early CTAs hold slots the draining kernel's tail could use).
+template <class... KArgs, class... Args>
+static inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+#define LAUNCH_P(cls, kern, grid, block, smem, ...)                                                                     \
+    do {                                                                                                                \
+        const bool p_ = b->prof.begin(cls, st);                                                                         \
+        launch_pdl(kern, dim3(grid), dim3(block), smem, st, b->pdl && !p_, __VA_ARGS__);                                \
+        if (p_) b->prof.end(st);                                                                                        \
+        b->launches++;                                                                                                  \
+    } while (0)
+
 #define LAUNCH(cls, kern, grid, block, ...)                                                                            \
     do {                                                                                                                \
         const bool p_ = b->prof.begin(cls, st);                                                                         \
@@ -1263,16 +1295,16 @@ static void launch_links(vx3_batch *b, int tile0 = 0, int tile_end = -1, bool co
         }
     }
     if (collect) { // slab batch: the face links read their ghost ends from the receive buffers (vx3_kernels.cuh, halo_arrival_wait)
-        if (b->link_smtab) LAUNCH_SM(KC_LINKS, (k_links_deferred<true, true>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
-        else LAUNCH_SM(KC_LINKS, (k_links_deferred<false, true>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        if (b->link_smtab) LAUNCH_P(KC_LINKS, (k_links_deferred<true, true>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        else LAUNCH_P(KC_LINKS, (k_links_deferred<false, true>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
         return;
     }
     if (b->link_smtab) {
-        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<true>, grid, VX3_LINK_T, 0, D, tile_end, tile0);
-        else LAUNCH_SM(KC_LINKS, k_links<true>, grid, VX3_LINK_T, 0, D, tile_end, nullptr, nullptr, 0, tile0);
+        if (variant) LAUNCH_P(KC_LINKS, (k_links_deferred<true, false>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        else LAUNCH_P(KC_LINKS, (k_links<true, false>), grid, VX3_LINK_T, 0, D, tile_end, nullptr, nullptr, 0, tile0);
     } else {
-        if (variant) LAUNCH_SM(KC_LINKS, k_links_deferred<false>, grid, VX3_LINK_T, 0, D, tile_end, tile0);
-        else LAUNCH_SM(KC_LINKS, k_links<false>, grid, VX3_LINK_T, 0, D, tile_end, nullptr, nullptr, 0, tile0);
+        if (variant) LAUNCH_P(KC_LINKS, (k_links_deferred<false, false>), grid, VX3_LINK_T, 0, D, tile_end, tile0);
+        else LAUNCH_P(KC_LINKS, (k_links<false, false>), grid, VX3_LINK_T, 0, D, tile_end, nullptr, nullptr, 0, tile0);
     }
     if (trial) {
         cudaEventRecord(b->lq_ev[1], st);
@@ -1476,23 +1508,23 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     if (b->any_collide) {
         cudaMemsetAsync(D.cell_cnt, 0, 2 * sizeof(int32_t) * ((size_t)D.hmask + 1), st); // every bucket empty (counts and overflow heads)
         LAUNCH(KC_GRID_BUILD, k_grid_build, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
-        LAUNCH(KC_CONTACT, k_contact, cdiv(D.nvox, VX3_CONTACT_WARPS), 32 * VX3_CONTACT_WARPS, D);
+        LAUNCH_P(KC_CONTACT, k_contact, cdiv(D.nvox, VX3_CONTACT_WARPS), 32 * VX3_CONTACT_WARPS, 0, D);
     } else if (b->any_detach || b->any_secondary) { // keep the surface flags current (regenerateSurfaceVoxels after a detach / removal)
         LAUNCH(KC_SURFACE, k_surface, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     }
     // attach resolution, then detach, one CTA per simulation (both usually find empty lists and leave at once)
-    if ((b->any_sticky || b->any_detach) && D.nlinkslots > 0) LAUNCH(KC_RESOLVE, k_resolve_detach, b->nsims, VX3_RESOLVE_T, D);
+    if ((b->any_sticky || b->any_detach) && D.nlinkslots > 0) LAUNCH_P(KC_RESOLVE, k_resolve_detach, b->nsims, VX3_RESOLVE_T, 0, D);
     const bool com = !b->capturing && com_step(b, b->hsteps + 1);
     int tail_in_voxels = -1; // >= 0: the voxel pass's last CTA does the end-of-step bookkeeping
     if (fused) {
     } else if (b->halo.on && b->halo.send_fused) { // the voxel pass sends the face poses and, on a plain step, does the end-of-step bookkeeping
         const int tail = com ? -1 : (check_stop ? 1 : 0);
-        if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, (k_voxels<true, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
-        else LAUNCH_SM(KC_VOXELS, (k_voxels<false, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
+        if (b->vox_smtab) LAUNCH_P(KC_VOXELS, (k_voxels<true, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
+        else LAUNCH_P(KC_VOXELS, (k_voxels<false, true>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail);
     } else {
         tail_in_voxels = !com && b->tail_in_voxels ? (check_stop ? 1 : 0) : -1;
-        if (b->vox_smtab) LAUNCH_SM(KC_VOXELS, k_voxels<true>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail_in_voxels);
-        else LAUNCH_SM(KC_VOXELS, k_voxels<false>, b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail_in_voxels);
+        if (b->vox_smtab) LAUNCH_P(KC_VOXELS, (k_voxels<true, false>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail_in_voxels);
+        else LAUNCH_P(KC_VOXELS, (k_voxels<false, false>), b->vox_grid, VX3_VOX_T, 0, D, b->vox_tiles, tail_in_voxels);
     }
     if (b->any_signals) LAUNCH(KC_SIGNALS, k_signals, b->nsims, 256, D); // end of timeStep (VX3_Voxel.cu:270-275), before removeVoxels
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
@@ -1503,7 +1535,7 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
     else if (sent_by_voxel_pass || tail_in_voxels >= 0) {
     } else if (b->halo.on && b->halo.send_blocks > 0) tail_in_send = check_stop ? 1 : 0;
-    else LAUNCH(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, D, check_stop ? 1 : 0);
+    else LAUNCH_P(KC_TAIL, k_tail_light, cdiv(b->nsims, 128), 128, 0, D, check_stop ? 1 : 0);
     if (sent_by_voxel_pass) b->halo.pending = true;
     else if (b->halo.on) { // my face poses to the neighbour slabs (vx3_halo.cuh); their poses are collected before the next face-link pass
         Halo &H = b->halo;

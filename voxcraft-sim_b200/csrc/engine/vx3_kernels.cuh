@@ -17,6 +17,12 @@ namespace vx3 {
 #define VX3_LINKS_MIN_CTAS 4
 #endif
 #ifndef VX3_VOX_T
+// First statement of every kernel that may be launched programmatically (launch_pdl, vx3_engine.cu): wait until the preceding kernel
+// of the stream has completed and its writes are visible, then allow the NEXT kernel's CTAs to be scheduled behind this grid's.
+// Both are no-ops in a normal launch.
+#define VX3_PDL_ENTRY()                                              \
+    asm volatile("griddepcontrol.wait;" ::: "memory");               \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define VX3_VOX_T 128
 #endif
 #ifndef VX3_VOXELS_MIN_CTAS
@@ -177,6 +183,7 @@ __device__ __forceinline__ int4 link_c4(const Dev &D, long long g) { return g < 
 // the pre-pass of the fused step (vx3_fused.cuh), which evaluates only the links across block faces.
 template <bool SMTAB, bool LIST = false>
 __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links(Dev D, int ntiles, const int *__restrict__ list_slot = nullptr, const int4 *__restrict__ list_c4 = nullptr, int nlist = 0, int tile0 = 0) {
+    VX3_PDL_ENTRY();
     __shared__ LinkSmem sm;
     const int tid = threadIdx.x;
     const long long G = gridDim.x;
@@ -370,6 +377,7 @@ __device__ __forceinline__ const double2 *halo_pose_row(const HaloIn *hin, const
 // to k_links.  No CTA barrier anywhere.
 // HALO (slab batches): links of tiles >= HaloIn::face_tile0 may have a ghost end, whose pose comes from the receive buffers.
 template <bool SMTAB, bool HALO = false> __global__ void __launch_bounds__(VX3_LINK_T, VX3_LINKS_MIN_CTAS) k_links_deferred(Dev D, int ntiles, int tile0 = 0) {
+    VX3_PDL_ENTRY();
     __shared__ LinkSmem sm;
     __shared__ int sDef[VX3_LINK_T / 32][64];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -562,6 +570,7 @@ __device__ void tail_light(const Dev &D, int sim, int check_stop);
 // HALO (slab batches, vx3_halo.cuh): a face voxel's record also goes into the neighbour's receive buffer, and the last CTA to finish
 // publishes the send number to both neighbours and, with tail >= 0, does the end-of-step bookkeeping (tail_light, check_stop = tail).
 template <bool SMTAB, bool HALO = false> __global__ void __launch_bounds__(VX3_VOX_T, VX3_VOXELS_MIN_CTAS) k_voxels(Dev D, int ntiles, int tail = -1) {
+    VX3_PDL_ENTRY();
     __shared__ VoxSmem sm;
     const int tid = threadIdx.x;
     const long long G = gridDim.x;
@@ -1280,6 +1289,7 @@ __device__ __forceinline__ void contact_warp(const Dev &D, int v, bool emit, int
 }
 
 __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) k_contact(Dev D) {
+    VX3_PDL_ENTRY();
     __shared__ ContactWarpSmem sm[VX3_CONTACT_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int v = blockIdx.x * VX3_CONTACT_WARPS + w;
@@ -1338,6 +1348,7 @@ __device__ bool resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, u
 }
 
 __global__ void __launch_bounds__(VX3_RESOLVE_T) k_resolve_detach(Dev D) {
+    VX3_PDL_ENTRY();
     __shared__ unsigned long long skey[VX3_RESOLVE_SM];
     __shared__ int sinfo[VX3_RESOLVE_SM];
     __shared__ ContactWarpSmem cw;
@@ -1790,6 +1801,7 @@ __device__ void tail_light(const Dev &D, int sim, int check_stop) {
     if (check_stop && (hot & SHF_STOP_PROG) && stop_condition_met(D, D.simc[sim], dy)) dy.status = VX3_SIM_STOPPED;
 }
 __global__ void __launch_bounds__(128) k_tail_light(Dev D, int check_stop) {
+    VX3_PDL_ENTRY();
     const int sim = blockIdx.x * blockDim.x + threadIdx.x;
     if (sim < D.nsims) tail_light(D, sim, check_stop);
 }
