@@ -102,6 +102,14 @@ static inline double jitter_ulp(double v) {
     const unsigned r = (unsigned)(z >> 33) % 3u;
     return r == 0 ? v : nextafter(v, r == 1 ? INFINITY : -INFINITY);
 }
+static inline float jitter_ulp_f(float v) { // the same model for a float result (powf of the poissons strain): CUDA documents 4 ulp for powf,
+                                            // glibc rounds correctly; the model moves the result by two float ulps
+    if (!g_libm_jitter) return v;
+    const double d = jitter_ulp((double)v); // draws the direction: one DOUBLE ulp up / down / unchanged ...
+    if (d == (double)v) return v;
+    const float dir = d > (double)v ? INFINITY : -INFINITY;
+    return nextafterf(nextafterf(v, dir), dir); // ... applied as two FLOAT ulps
+}
 static inline double m_sin(double x) { return jitter_ulp(sin(x)); }
 static inline double m_cos(double x) { return jitter_ulp(cos(x)); }
 static inline double m_acos(double x) { return jitter_ulp(acos(x)); }
@@ -326,6 +334,10 @@ struct OVoxel {
     // signals (VX3_Voxel.h:304-309): d_signal {value, activeTime}, localSignal(+dt), inactiveUntil, packmakerNextPulse
     double localSignal = 0, localSignaldt = 0, inactiveUntil = 0, packmakerNextPulse = 0;
     double sigValue = 0, sigActiveTime = 0;
+    // cached poissonsStrain() and its flag (VX3_Voxel.h:287-288).  VX3 never refreshes a link's transverse info while stepping
+    // (VX3_Link.cu:146-150, commented out), so the cache only matters when a link is CREATED: the attach ctor's reset()
+    float pStrain[3] = {0, 0, 0};
+    bool poissonsStrainInvalid = true;
 };
 
 struct OLink {
@@ -357,6 +369,7 @@ struct vx3o_sim {
     //   * no per-step temperature, collisions, attach/detach, force field, CoM sampling
     //   * material data arrays without the duplicated leading 0
     int cpu_lib_mode = 0;
+    bool importing = false; // vx3o_create is building the model's own links (resetLink)
     std::string name;
     vx3_sim_options opt;
     std::vector<OMat> vmats, lmats;
@@ -427,9 +440,63 @@ struct vx3o_sim {
     void updateRestLength(OLink &l) { // VX3_Link.cu:80-83
         l.currentRestLength = 0.5 * (baseSizeAxis(vox[l.vNeg], l.axis) + baseSizeAxis(vox[l.vPos], l.axis));
     }
-    float transverseArea(const OVoxel &v) const { // VX3_Voxel.cu:494-513 with zero poissons strain
+    float axialStrain(const OLink &l, bool positiveEnd) const { // VX3_Link.cu:72-74
+        return positiveEnd ? 2.0f * l.strain * l.strainRatio / (1.0f + l.strainRatio) : 2.0f * l.strain / (1.0f + l.strainRatio);
+    }
+    void voxelStrain(const OVoxel &v, bool poissons, float out[3]) const { // VX3_Voxel::strain, VX3_Voxel.cu:428-468
+        float intStrRet[3] = {0, 0, 0};
+        int numBondAxis[3] = {0, 0, 0};
+        bool tension[3] = {false, false, false};
+        for (int i = 0; i < 6; i++)
+            if (v.links[i] >= 0) {
+                const int axis = i / 2;
+                intStrRet[axis] += axialStrain(links[v.links[i]], isNegative(i));
+                numBondAxis[axis]++;
+            }
+        for (int i = 0; i < 3; i++) {
+            if (numBondAxis[i] == 2) intStrRet[i] *= 0.5f;
+            if (poissons)
+                tension[i] = (numBondAxis[i] == 2) ||
+                             (v.ext >= 0 && (numBondAxis[i] == 1 && (exts[v.ext].isFixed(1 << i) || (float)exts[v.ext].e.force[i] != 0)));
+        }
+        if (poissons && !(tension[0] && tension[1] && tension[2])) {
+            float add = 0;
+            for (int i = 0; i < 3; i++)
+                if (tension[i]) add += intStrRet[i];
+            const float value = jitter_ulp_f(powf(1.0f + add, -vm(v).m.nu)) - 1.0f;
+            for (int i = 0; i < 3; i++)
+                if (!tension[i]) intStrRet[i] = value;
+        }
+        for (int i = 0; i < 3; i++) out[i] = intStrRet[i];
+    }
+    const float *poissonsStrain(OVoxel &v) { // VX3_Voxel.cu:470-476
+        if (v.poissonsStrainInvalid) {
+            voxelStrain(v, true, v.pStrain);
+            v.poissonsStrainInvalid = false;
+        }
+        return v.pStrain;
+    }
+    float transverseStrainSum(OVoxel &v, int axis) { // VX3_Voxel.cu:478-494
+        if (vm(v).m.nu == 0) return 0;
+        const float *ps = poissonsStrain(v);
+        switch (axis) {
+        case 0: return ps[1] + ps[2];
+        case 1: return ps[0] + ps[2];
+        case 2: return ps[0] + ps[1];
+        default: return 0.0f;
+        }
+    }
+    float transverseArea(OVoxel &v, int axis) { // VX3_Voxel.cu:496-513
         float size = (float)vm(v).m.nomSize;
-        return size * size;
+        if (vm(v).m.nu == 0) return size * size;
+        const float *p = poissonsStrain(v);
+        const double ps[3] = {p[0], p[1], p[2]};
+        switch (axis) {
+        case 0: return (float)(size * size * (1 + ps[1]) * (1 + ps[2]));
+        case 1: return (float)(size * size * (1 + ps[0]) * (1 + ps[2]));
+        case 2: return (float)(size * size * (1 + ps[0]) * (1 + ps[1]));
+        default: return size * size;
+        }
     }
     void resetLink(OLink &l) { // VX3_Link.cu:58-70
         l.pos2 = l.angle1v = l.angle2v = V3();
@@ -440,9 +507,22 @@ struct vx3o_sim {
         l.smallAngle = true;
         l.boolStates &= ~VX3_LINK_LOCAL_VELOCITY_VALID;
         updateRestLength(l);
-        // updateTransverseInfo (VX3_Link.cu:85-88): a fresh link has zero strain everywhere
-        l.currentTransverseArea = 0.5f * (transverseArea(vox[l.vNeg]) + transverseArea(vox[l.vPos]));
-        l.currentTransverseStrainSum = 0.0f;
+        // updateTransverseInfo (VX3_Link.cu:85-88).  At import every strain is zero (area = size^2, sum = 0, and the end voxels'
+        // caches become valid with zeros); for a link the attach phase creates the end voxels' CURRENT poissons strains go in —
+        // this link (strain 0) already sits in their slots — and stay frozen for the link's life
+        if (importing) { // host import (CVX_Link::reset with every strain zero): the same calls, whose answers are size^2 and 0
+            for (int vi : {l.vNeg, l.vPos})
+                if (vm(vox[vi]).m.nu != 0) {
+                    vox[vi].pStrain[0] = vox[vi].pStrain[1] = vox[vi].pStrain[2] = 0.0f;
+                    vox[vi].poissonsStrainInvalid = false;
+                }
+            const float sn = (float)vm(vox[l.vNeg]).m.nomSize, sp = (float)vm(vox[l.vPos]).m.nomSize;
+            l.currentTransverseArea = 0.5f * (sn * sn + sp * sp);
+            l.currentTransverseStrainSum = 0.0f;
+            return;
+        }
+        l.currentTransverseArea = 0.5f * (transverseArea(vox[l.vNeg], l.axis) + transverseArea(vox[l.vPos], l.axis));
+        l.currentTransverseStrainSum = 0.5f * (transverseStrainSum(vox[l.vNeg], l.axis) + transverseStrainSum(vox[l.vPos], l.axis));
     }
 
     void orientLink(OLink &l) { // VX3_Link.cu:90-133
@@ -686,6 +766,7 @@ struct vx3o_sim {
                 if (v.boolStates & VX3_VOX_FLOOR_STATIC_FRICTION) v.angMom = V3(0, 0, 0);
             }
         }
+        v.poissonsStrainInvalid = true; // VX3_Voxel.cu:266 (not reached by a voxel that returns early: dt = 0, all DOFs fixed)
     }
 
     // ---- signals (VX3_Voxel.cu:279-348).  The reference runs these at the end of every voxel's timeStep with the
@@ -1206,7 +1287,9 @@ vx3o_sim *vx3o_create(const vx3_model_desc *m, int cpu_lib_mode) {
     for (int i = 0; i < m->n_links; i++) {
         OLink &l = s->links[i];
         l.vNeg = m->link_vneg[i]; l.vPos = m->link_vpos[i]; l.axis = m->link_axis[i]; l.mat = m->link_mat[i];
+        s->importing = true;
         s->resetLink(l);
+        s->importing = false;
         if (m->link_pos2) l.pos2 = V3(m->link_pos2[3 * i], m->link_pos2[3 * i + 1], m->link_pos2[3 * i + 2]);
         if (m->link_angle1v) l.angle1v = V3(m->link_angle1v[3 * i], m->link_angle1v[3 * i + 1], m->link_angle1v[3 * i + 2]);
         if (m->link_angle2v) l.angle2v = V3(m->link_angle2v[3 * i], m->link_angle2v[3 * i + 1], m->link_angle2v[3 * i + 2]);

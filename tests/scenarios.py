@@ -39,15 +39,19 @@ def cube_spec(n=(3, 3, 3), seed=42, actuated=True, lift=0, holes=0.0, name="cube
     return spec
 
 
-def collide_spec(sticky, detach=False, name="pile"):
+def collide_spec(sticky, detach=False, name="pile", nu=0.0):
     """Two 2x2x2 blocks, the upper one offset and dropped onto the lower: collisions (and sticky attach)."""
     spec = ModelSpec(0.01, name)
     if detach:
         spec.add_material(name="S", mat_model=1, elastic_mod=1e6, fail_stress=2.5e3, density=1e3, u_static=1.0, u_dynamic=0.8, sticky=int(sticky))
     else:
-        spec.add_material(name="S", elastic_mod=1e6, density=1e3, u_static=1.0, u_dynamic=0.8, sticky=int(sticky))
+        spec.add_material(name="S", elastic_mod=1e6, density=1e3, u_static=1.0, u_dynamic=0.8, sticky=int(sticky), poissons_ratio=nu)
     spec.add_material(name="T", elastic_mod=2e6, density=1.2e3, u_static=1.0, u_dynamic=0.8, is_target=1)
-    spec.set_env(bond_damping_z=1.0, col_damping_z=0.8, slow_damping_z=0.01)
+    spec.set_env(bond_damping_z=1.0, col_damping_z=0.8, slow_damping_z=0.01, volume_effects_enabled=int(nu != 0))  # (nu is forced to 0 without it)
+    if nu != 0:  # actuation, so that the voxels are strained when the attach makes its link (the new link's transverse info takes that in)
+        spec.set_env(temp_enabled=1, vary_temp_enabled=1, temp_amplitude=15.0, temp_period=0.02)
+        for m in spec.materials:
+            m["cte"] = 0.01
     spec.set_options(enable_collision=1, enable_attach=int(sticky), enable_detach=int(detach), safety_guard=50)
     st = np.zeros((5, 3, 4), np.uint8)
     st[0:2, 0:2, 0:2] = 1
@@ -182,6 +186,61 @@ def bar_material_spec(mat_model, nu=0.0, name="bar", fail=False, n=8, force=2.2)
     return spec
 
 
+def random_spec(seed):
+    """A seeded random model over the option space of the step loop: shape, holes, a 2-3 entry palette with random stiffness /
+    density / CTE / friction / Poisson's ratio / material model, actuation with random per-voxel phases (contraction-only or with
+    expansion), floor on or off, a thermal start delay, an external force or a fixed voxel, and — on every second seed —
+    collisions with sticky attach (and detach on every fourth).  Parameters stay in the range where the run is stable."""
+    rs = np.random.RandomState(1000 + seed)
+    U = lambda a, b: float(rs.uniform(a, b))
+    nx, ny, nz = int(rs.randint(2, 5)), int(rs.randint(2, 5)), int(rs.randint(2, 4))
+    collide = seed % 2 == 1
+    detach = seed % 4 == 3
+    spec = ModelSpec(0.01, "fuzz%d" % seed)
+    npal = int(rs.randint(2, 4))
+    for k in range(npal):
+        model = int(rs.choice([0, 0, 1, 2])) if not detach else 1
+        kw = dict(name="M%d" % k, elastic_mod=U(3e5, 2e6), density=U(800, 1500), cte=float(rs.choice([-1, 1])) * U(0.004, 0.015),
+                  u_static=U(0.6, 1.2), u_dynamic=U(0.3, 0.6), poissons_ratio=float(rs.choice([0.0, 0.0, U(0.15, 0.35)])),
+                  material_temp_phase=U(0, 1), thermal_on_after_s=float(rs.choice([0.0, U(0.0005, 0.003)])))
+        if model == 1:
+            kw.update(mat_model=1, fail_stress=kw["elastic_mod"] * (U(0.1, 0.2) if detach else 0.5))
+        elif model == 2:
+            ys = kw["elastic_mod"] * U(0.01, 0.03)
+            kw.update(mat_model=2, plastic_mod=kw["elastic_mod"] * U(0.1, 0.5), yield_stress=ys, fail_stress=ys * U(3, 6))
+        if collide:
+            kw.update(sticky=1)
+        spec.add_material(**kw)
+    if collide:  # every voxel of a sticky pile is the same material: attach needs equal materials on both sides
+        spec.materials = spec.materials[:1]
+        npal = 1
+    spec.set_env(bond_damping_z=U(0.5, 1.0), col_damping_z=U(0.5, 0.9), slow_damping_z=U(0.005, 0.03), floor_enabled=int(rs.rand() < 0.8),
+                 temp_enabled=1, vary_temp_enabled=1, temp_amplitude=U(2, 6) if collide else U(8, 25), temp_period=U(0.01, 0.05),
+                 volume_effects_enabled=int(rs.rand() < 0.3))
+    spec.set_options(enable_collision=int(collide), enable_attach=int(collide), enable_detach=int(detach), safety_guard=int(rs.randint(20, 80)),
+                     enable_expansion=int(rs.rand() < 0.4))
+    lift = int(rs.randint(0, 3))
+    if collide:  # two bodies one empty layer apart, the upper one shifted by a cell; strong gravity so that they meet within a few hundred steps
+        spec.set_env(grav_acc=-U(150.0, 400.0))
+        st = np.zeros((2 * nz + 1 + lift, ny + 1, nx + 1), np.uint8)
+        st[lift:lift + nz, :ny, :nx] = 1
+        st[lift + nz + 1:lift + 2 * nz + 1, 1:, 1:] = 1
+    else:
+        st = np.zeros((nz + lift, ny, nx), np.uint8)
+        st[lift:] = rs.randint(1, npal + 1, size=(nz, ny, nx))
+        st[lift:][rs.rand(nz, ny, nx) < U(0.0, 0.25)] = 0
+        if not st.any():
+            st[lift, 0, 0] = 1
+    spec.set_structure(st, phase_offset=rs.rand(*st.shape))
+    nvox = int((st > 0).sum())
+    if not collide and nvox > 2:
+        if rs.rand() < 0.5:
+            spec.set_external(int(rs.randint(0, nvox)), force=(U(-2e-3, 2e-3), U(-2e-3, 2e-3), U(-2e-3, 2e-3)))
+        if rs.rand() < 0.4:
+            spec.set_external(0, dof_fixed=int(rs.choice([0x3F, 0x07, 0x04])))
+    return spec
+
+
 SCENARIOS = {
     "act333": dict(spec=lambda: cube_spec((3, 3, 3), seed=11, actuated=True, name="act333"), steps=1000, chunk=250,
                    covers="per-voxel phase actuation, rest length from end temperatures"),
@@ -192,6 +251,9 @@ SCENARIOS = {
     "pile": dict(spec=lambda: collide_spec(False), steps=4000, chunk=1000, covers="all-pairs sweep, VX3_Collision, collisionCount"),
     "pile_sticky": dict(spec=lambda: collide_spec(True, name="pile_sticky"), steps=4000, chunk=1000,
                         covers="attach: link ctor, combinedMaterial, isNewLink ramp, surface regeneration"),
+    "pile_sticky_nu": dict(spec=lambda: collide_spec(True, name="pile_sticky_nu", nu=0.3), steps=4000, chunk=1000,
+                           covers="attach with nu != 0: the new link's frozen transverse area / strain sum from the end voxels' poissons strain "
+                                  "(VX3_Link.cu:58-70, 85-88; VX3_Voxel.cu:428-513)"),
     "detach": dict(spec=lambda: collide_spec(True, detach=True, name="detach"), steps=3000, chunk=750, link_capacity=4096,
                    covers="gpu_update_detach, repeated attach/fail/detach cycles"),
     "c4small": dict(spec=lambda: W.c4_spec(grid=(2, 2, 2), body=3, name="c4small"), steps=2000, chunk=500, dt="auto", link_capacity=4096,
@@ -221,6 +283,13 @@ SCENARIOS = {
     "poisson_data": dict(spec=lambda: bar_material_spec(3, nu=0.25, name="poisson_data"), steps=1500, chunk=250,
                          covers="nu != 0 on the piece-wise branch (VX3_Material.cu:108-121)"),
 }
+# seeded random models (random_spec): the same three-way check as the named scenarios — reference VX3 code = oracle bit for bit,
+# GPU within the gate — on option combinations nobody picked by hand
+for _k in range(8):
+    SCENARIOS["fuzz%d" % _k] = dict(spec=(lambda k=_k: random_spec(k)), steps=1600 if _k % 2 else 600, chunk=400 if _k % 2 else 150, dt="auto" if _k % 2 else "fixed",
+                                    link_capacity=2048 if _k % 2 else None,
+                                    covers="random model %d: %s" % (_k, "two sticky bodies, collisions + attach%s" % (" + detach" if _k % 4 == 3 else "")
+                                                                    if _k % 2 else "random palette / actuation / externals"))
 
 
 def scenario(name):

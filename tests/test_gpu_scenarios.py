@@ -4,7 +4,8 @@ bit to the reference's own VX3 code (tests/test_oracle_vs_vx3ref.py, fixtures te
 Gates (stated once, used everywhere):
   * integer state — link topology (ends, axis, material), voxel link slots, voxel / link flags incl. the isNewLink
     countdown, collision and event counts, signal state — BIT-EXACT;
-  * floating-point state — element-wise |gpu - oracle| <= max(1e-9 * max|oracle|, 8 x libm envelope): the product is built
+  * floating-point state — element-wise |gpu - oracle| <= max(1e-9 * max|oracle|, 8 x libm envelope) — for link forces / moments also
+    stiffness x 1e-9 x max|pos| (util.link_force_floors: what the position bar itself implies for a stiff link) —: the product is built
     with -fmad=false, so the only arithmetic that may differ from the oracle's is libdevice vs glibc sin / cos / acos
     (each within 1 ulp, not identically rounded); the envelope is the oracle's own spread when exactly those results are
     jittered by +-1 ulp (util.libm_envelope).  Kinematic state passes the flat 1e-9 bar on the small scenarios; the envelope
@@ -52,7 +53,7 @@ def run_scenario(name, persistent=True, fused=False):
             for k in INT_KEYS:
                 np.testing.assert_array_equal(se[k], so[k], err_msg="%s: %s" % (what, k))
             np.testing.assert_array_equal(se["signal"], so["signal"], err_msg=what + ": signal state")
-            w = gate_within_envelope(se, so, env, FLOAT_KEYS, what)
+            w = gate_within_envelope(se, so, env, FLOAT_KEYS, what, abs_floor=util.link_force_floors(d, so))
             # strain / stress / temperature are STORED as float: a 1e-16 relative difference in the double they are rounded from
             # can flip the rounding, so their floor is one float ulp at the array's scale
             w.update(gate_within_envelope(se, so, env, F32_EXACTISH, what, rel_floor=1.2e-7))
@@ -61,8 +62,11 @@ def run_scenario(name, persistent=True, fused=False):
             re, ro = eng.results()[0], orc.result()
             assert (re.steps, re.num_links, re.collision_count, re.num_close_pairs, re.num_measured_voxel) == \
                    (ro.steps, ro.num_links, ro.collision_count, ro.num_close_pairs, ro.num_measured_voxel), what
-            np.testing.assert_allclose([re.current_time, re.target_closeness, re.recent_angle], [ro.current_time, ro.target_closeness, ro.recent_angle],
-                                       rtol=1e-9, atol=1e-12, err_msg=what)
+            np.testing.assert_allclose([re.current_time, re.target_closeness], [ro.current_time, ro.target_closeness], rtol=1e-9, atol=1e-12, err_msg=what)
+            # recentAngle = acos of the normalised dot product of two successive centre-of-mass displacements (:318-333): the
+            # displacements are differences of positions that agree to 1e-9 * 0.03 m, and between two samples the centre of mass of a
+            # body that mostly stands still moves 1e-5 m — the ANGLE is then only good to ~1e-6 however exact the positions are
+            np.testing.assert_allclose(re.recent_angle, ro.recent_angle, rtol=1e-6, atol=1e-9, err_msg=what)
             np.testing.assert_allclose(list(re.current_com) + list(re.initial_com), list(ro.current_com) + list(ro.initial_com), rtol=1e-9, atol=1e-15,
                                        err_msg=what)
             np.testing.assert_allclose(re.fitness_score, ro.fitness_score, rtol=1e-9, atol=1e-15, err_msg=what)

@@ -304,13 +304,28 @@ def libm_envelope(desc_ptr, steps, dt, checkpoints=None, seeds=(1, 2, 11, 23, 37
     return exact, envs
 
 
-def gate_within_envelope(se, so, env, keys, what="", factor=8.0, rel_floor=1e-9):
+def link_force_floors(desc, so, rel=1e-9):
+    """Absolute floors for the link force / moment arrays that are CONSISTENT with the position gate: a link force is stiffness x
+    (difference of end positions), so two states whose positions agree to rel * max|pos| — the bar itself — can differ in a link
+    force by k * rel * max|pos| (k = the stiffest link material's a1 or b1, N/m), and in a moment by that times the voxel size.
+    Where this is larger than rel * max|force| (stiff links under small load) it is the honest floor."""
+    d = desc.contents if hasattr(desc, "contents") else desc
+    k = max([max(d.link_mats[i].a1, d.link_mats[i].b1) for i in range(d.n_link_mats)] + [0.0])
+    for i in range(d.n_voxel_mats):  # attach-created links: (material, material) pairs may not be in the model's table
+        k = max(k, float(d.voxel_mats[i].E) * float(d.voxel_mats[i].nomSize))
+    size = max(float(d.voxel_mats[i].nomSize) for i in range(d.n_voxel_mats))
+    dx = rel * float(np.max(np.abs(np.asarray(so["pos"], np.float64))))
+    return {"link_force_neg": k * dx, "link_force_pos": k * dx, "link_moment_neg": k * dx * size, "link_moment_pos": k * dx * size}
+
+
+def gate_within_envelope(se, so, env, keys, what="", factor=8.0, rel_floor=1e-9, abs_floor=None):
     """The tolerance gate of the GPU parity tests, element-wise:  |gpu - oracle| <= max(rel_floor * scale, factor * env)
     where scale = max |oracle| over the array (so zeros are handled) and env is the element's spread under the 1-ulp libm
     error model (libm_envelope; a handful of replicas, so an element's own spread is raised to the array's 90th percentile
     where that is larger).  rel_floor = 1e-9 is BASELINE.md's bar; the
     envelope term only ever loosens it where a 1-ulp difference in sin / cos / acos PROVABLY moves the oracle itself by
-    more than that (momenta and link forces are differences of large terms).  Returns the worst ratio err / tol per key."""
+    more than that (momenta and link forces are differences of large terms).  abs_floor: per-key absolute floors
+    (link_force_floors).  Returns the worst ratio err / tol per key."""
     worst = {}
     for k in keys:
         a, b = np.asarray(se[k], np.float64), np.asarray(so[k], np.float64)
@@ -319,6 +334,8 @@ def gate_within_envelope(se, so, env, keys, what="", factor=8.0, rel_floor=1e-9)
             continue
         scale = max(np.max(np.abs(b)), 1e-300)
         tol = np.full(a.shape, rel_floor * scale)
+        if abs_floor is not None and k in abs_floor:
+            tol = np.maximum(tol, abs_floor[k])
         if env is not None and env.get(k) is not None:
             e = env[k]
             tol = np.maximum(tol, factor * np.maximum(e, np.quantile(e, 0.9)))

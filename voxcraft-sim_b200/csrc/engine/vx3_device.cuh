@@ -45,7 +45,7 @@ struct VoxMatC {
     float E;
     int32_t fixed, sticky, is_target, is_measured, matid;
     int32_t self_lmat; // link material of a (this,this) pair: used by attach (global link-material index), -1 if none
-    int32_t _pad;
+    float nu;          // poissonsRatio()
 };
 
 // What the link pass needs of an end voxel's material (one record per VoxMatC entry, same index)
@@ -97,6 +97,8 @@ struct SimC {
     double vox_size, pair_radius; // MaxDistInVoxelLengthsToCountAsPair * voxSize (0 = closeness off)
     double cell_inv;              // 1 / collision grid cell edge
     double dt_frac, optimal_dt;
+    int32_t dt_from_state, _pad_dt; // a model link's material has nu != 0: recommendedTimeStep() depends on the rest lengths at the first
+                                    // step's temperatures (k_optimal_dt), not only on the model
 };
 
 // bits of SimD::hot_flags (constants of the simulation mirrored next to the per-step scalars)
@@ -260,6 +262,9 @@ struct Dev {
     CellItem *cell_items;
     struct ContactRec *crec; // [nvox] what the contact phase needs of a voxel, in one 64-byte record (written by k_grid_build)
     int32_t *uf;      // [nvox] union-find parents over the voxels (NULL unless a simulation can attach), see uf_find
+    float4 *pcache;   // [nvox] {poissonsStrain() x, y, z, validity stamp as int bits} (VX3_Voxel.h:287-288), for the transverse info of a link
+                      // the attach phase creates; NULL unless an attaching simulation has a material with nu != 0.  Stamp: -2 invalid,
+                      // -1 valid since import (every strain was zero), s >= 0 computed during step s (resolve_link_transverse)
     int2 *nbcache;    // [nvox][8] {partner, topo_epoch << 1 | answer}: what within_five_links said about (voxel, partner) while the link graph
                       // was at that epoch — a settled pile asks the same questions every step (allocated with vnb)
     int32_t *vnb;     // [nvox][8] the voxel at the far end of each of the six link slots (-1: none; two pad entries) — the link graph as

@@ -26,6 +26,48 @@
 
 using namespace vx3;
 
+// recommendedTimeStep() (VX3_VoxelyzeKernel.cu:184-217) where it depends on the state.  For a link whose material has nu != 0 the
+// stiffness is eHat * transverse area / ((1 + strain) * rest length) (VX3_Link::axialStiffness, VX3_Link.cu:268-277), and the
+// reference evaluates OptimalDt ONCE, in its first doTimeStep(dt < 0), AFTER that step's updateTemperature (:240-247): the rest
+// lengths are those at the t = 0 temperatures, which per-voxel phase offsets make non-zero — not the model's.  Same mixed
+// precision as the reference; vx3_model_recommended_dt (host library) keeps answering for the model as imported.
+static double first_step_recommended_dt(const vx3_model_desc &m) {
+    const bool vary = m.opt.vary_temp_enabled && m.opt.temp_period > 0;
+    std::vector<float> te((size_t)m.n_voxels);
+    for (int i = 0; i < m.n_voxels; i++) {
+        const vx3_voxel_material &vm = m.voxel_mats[m.vox_mat[i]];
+        te[(size_t)i] = m.temp ? m.temp[i] : 0.0f;
+        if (!vary || vm.thermal_on_after_s > 0.0 || vm.fixed) continue; // gpu_update_temperature (:625-650) at currentTime = 0
+        double cur = m.opt.temp_amplitude * sin(2 * 3.1415926f * (0.0 / m.opt.temp_period + (m.phase_offset ? m.phase_offset[i] : 0.0)));
+        if (!m.opt.enable_expansion && cur > 0) cur = 0;
+        te[(size_t)i] = (float)cur;
+    }
+    double MaxFreq2 = 0.0f;
+    for (int i = 0; i < m.n_links; i++) {
+        const vx3_link_material &lm = m.link_mats[m.link_mat[i]];
+        const int vn = m.link_vneg[i], vp = m.link_vpos[i], axis = m.link_axis[i];
+        const vx3_voxel_material &mn = m.voxel_mats[m.vox_mat[vn]], &mp = m.voxel_mats[m.vox_mat[vp]];
+        float stiff;
+        if (lm.m.nu == 0.0f) stiff = lm.a1;
+        else {
+            const double rest = 0.5 * ((mn.nomSize * mn.extScale[axis]) * (1 + te[(size_t)vn] * mn.alphaCTE) + (mp.nomSize * mp.extScale[axis]) * (1 + te[(size_t)vp] * mp.alphaCTE));
+            const float strain = m.link_strain ? m.link_strain[i] : 0.0f;
+            stiff = (float)(lm.m.eHat * m.link_transverse_area[i] / ((strain + 1) * rest));
+        }
+        const double m1 = mn.mass, m2 = mp.mass;
+        const double f2 = stiff / (m1 < m2 ? m1 : m2);
+        if (f2 > MaxFreq2) MaxFreq2 = f2;
+    }
+    if (MaxFreq2 <= 0.0f) return vx3_model_recommended_dt(&m);
+    return 1.0f / (6.283185f * sqrt(MaxFreq2));
+}
+
+static inline float __int_as_float_host(int i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -297,6 +339,7 @@ struct vx3_batch {
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
     bool any_ghost = false;
+    bool any_sticky_poisson = false; // an attaching simulation has a sticky material with nu != 0: Dev::pcache
     bool pdl = false; // programmatic dependent launch between the step kernels (launch_pdl; VX3_PDL=1)
     bool tail_in_voxels = false; // plain steps of batches of <= 128 simulations: k_voxels' last CTA does k_tail_light's work (VX3_TAIL_FUSED=0: off)
     size_t vox_active = 0; // voxels [vox_active, nvox) are all ghosts (a slab model lists them last): the voxel pass leaves their tiles out
@@ -668,6 +711,8 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
             vm.gravityForce = -in.mass * 9.80665f * in.gravMult;
             vm.dampMultNum = 2 * in.sqrtMass * in.zetaInternal;
             vm.E = in.E;
+            vm.nu = in.nu;
+            if (in.sticky && in.nu != 0 && m.opt.enable_attach) b->any_sticky_poisson = true;
             vm.fixed = in.fixed != 0; vm.sticky = in.sticky != 0; vm.is_target = in.is_target != 0; vm.is_measured = in.is_measured != 0;
             vm.matid = in.matid;
             vm.self_lmat = -1;
@@ -737,6 +782,9 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.pair_radius = m.opt.max_dist_in_voxel_lengths_to_count_as_pair * m.opt.vox_size;
         S.dt_frac = m.opt.dt_frac;
         S.optimal_dt = vx3_model_recommended_dt(&m);
+        S.dt_from_state = 0;
+        for (int i = 0; i < m.n_links && !S.dt_from_state; i++) S.dt_from_state = m.link_mats[m.link_mat[i]].m.nu != 0.0f;
+        if (S.dt_from_state) S.optimal_dt = first_step_recommended_dt(m);
         dy.hot_flags = ((S.vary_temp && S.temp_period > 0) ? SHF_THERMAL : 0) | (S.enable_expansion ? SHF_EXPANSION : 0) | (S.enable_cilia ? SHF_CILIA : 0) |
                        (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0) |
                        (S.enable_detach ? SHF_DETACH : 0) | (S.secondary_experiment ? SHF_SECONDARY : 0) | (S.prog_n[VX3_PROG_STOP] > 0 ? SHF_STOP_PROG : 0);
@@ -936,6 +984,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
     D.lstride = (int)LS;
     // ---- plan the rest of the arena: the small tables follow the in-place arrays, zero-initialised slices come last ----
     std::vector<int32_t> uf_host, vnb_host;
+    std::vector<float4> pcache_host;
 #define UP(field, vec) plan.upload(const_cast<std::remove_const<std::remove_pointer<decltype(D.field)>::type>::type **>(&D.field), vec)
     UP(simc, b->simc);
     UP(simd, simd);
@@ -1015,6 +1064,16 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
                 }
             plan.upload(&D.vnb, vnb_host);
             plan.zeroed(&D.nbcache, nvox * 8);
+            if (b->any_sticky_poisson) { // cached poissons strain per voxel: valid with zeros since import where the host computed it
+                                         // (CVX_Link::reset of every model link calls it on both ends when nu != 0)
+                pcache_host.assign(nvox, make_float4(0.f, 0.f, 0.f, __int_as_float_host(-2)));
+                for (size_t v = 0; v < nvox; v++) {
+                    bool linked = false;
+                    for (int k = 0; k < 6; k++) linked |= vlinks[6 * v + k] >= 0;
+                    if (linked && vmat_tab[vmat[v]].nu != 0) pcache_host[v].w = __int_as_float_host(-1);
+                }
+                plan.upload(&D.pcache, pcache_host);
+            }
         }
     }
     {

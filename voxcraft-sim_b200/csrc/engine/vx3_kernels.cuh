@@ -1309,6 +1309,76 @@ __global__ void __launch_bounds__(32 * VX3_CONTACT_WARPS, VX3_CONTACT_MIN_CTAS) 
 #ifndef VX3_RESOLVE_T
 #define VX3_RESOLVE_T 256
 #endif
+// ---- transverse info of a link the attach phase creates (VX3_Link::reset -> updateTransverseInfo, VX3_Link.cu:58-70, 85-88) ----
+// VX3 never refreshes a link's transverse area / strain sum while stepping (VX3_Link.cu:146-150, commented out), so they are frozen
+// at creation: size^2 and 0 at import (every strain is zero), but for a link made by the attach phase the end voxels' CURRENT
+// poissons strains when nu != 0 — through the voxel's cache (poissonsStrain(), VX3_Voxel.cu:470-476), which is invalidated at the
+// end of every voxel time step (:266).  The cache lives in Dev::pcache with a validity stamp instead of a flag the voxel pass
+// would have to write every step: -2 invalid; -1 valid since import (zeros) — for good on a voxel that never reaches the end of
+// timeStep (all DOFs fixed), until the first step has been integrated otherwise; s >= 0: computed during step s.
+__device__ __forceinline__ float link_axial_strain(const Dev &D, int li, bool positiveEnd) { // VX3_Link::axialStrain, VX3_Link.cu:72-74
+    const int2 e = D.lends[li];
+    const float strain = D.lstrain[li].x;
+    const float strainRatio = D.vmat_tab[D.vmat[e.y]].E / D.vmat_tab[D.vmat[e.x]].E; // pVPos E / pVNeg E (reset(), :63)
+    return positiveEnd ? 2.0f * strain * strainRatio / (1.0f + strainRatio) : 2.0f * strain / (1.0f + strainRatio);
+}
+__device__ void voxel_poissons_strain(const Dev &D, int v, int steps_now, float ps[3]) { // poissonsStrain() with strain(true), VX3_Voxel.cu:428-476
+    const float4 c = D.pcache[v];
+    const int stamp = __float_as_int(c.w);
+    const int ext = D.vext[v];
+    const bool fixedAll = ext >= 0 && (D.exts[ext].dof & 0x3F) == 0x3F;
+    const bool valid = stamp == -1 ? (fixedAll || steps_now == 0) : stamp == steps_now;
+    if (valid) {
+        ps[0] = c.x; ps[1] = c.y; ps[2] = c.z;
+        return;
+    }
+    float intStrRet[3] = {0.f, 0.f, 0.f};
+    int numBondAxis[3] = {0, 0, 0};
+    bool tension[3];
+    for (int i = 0; i < 6; i++) {
+        const int li = D.vlinks[6 * (size_t)v + i];
+        if (li >= 0) {
+            intStrRet[i >> 1] += link_axial_strain(D, li, (i & 1) != 0); // isNegative(direction): this voxel is that link's positive end
+            numBondAxis[i >> 1]++;
+        }
+    }
+    for (int i = 0; i < 3; i++) {
+        if (numBondAxis[i] == 2) intStrRet[i] *= 0.5f;
+        tension[i] = (numBondAxis[i] == 2) || (ext >= 0 && (numBondAxis[i] == 1 && ((D.exts[ext].dof & (1 << i)) || D.exts[ext].force[i] != 0)));
+    }
+    if (!(tension[0] && tension[1] && tension[2])) {
+        float add = 0;
+        for (int i = 0; i < 3; i++)
+            if (tension[i]) add += intStrRet[i];
+        const float value = powf(1.0f + add, -D.vmat_tab[D.vmat[v]].nu) - 1.0f;
+        for (int i = 0; i < 3; i++)
+            if (!tension[i]) intStrRet[i] = value;
+    }
+    ps[0] = intStrRet[0]; ps[1] = intStrRet[1]; ps[2] = intStrRet[2];
+    D.pcache[v] = make_float4(ps[0], ps[1], ps[2], __int_as_float(fixedAll ? -1 : steps_now));
+}
+// {currentTransverseArea, currentTransverseStrainSum} of the new link g (already in both voxels' slots, strain 0)
+__device__ float2 resolve_link_transverse(const Dev &D, int vneg, int vpos, int axis, int steps_now) {
+    float area[2], sum[2];
+    const int vs[2] = {vneg, vpos};
+    for (int k = 0; k < 2; k++) {
+        const VoxMatC &m = D.vmat_tab[D.vmat[vs[k]]];
+        const float size = (float)m.nomSize;
+        if (m.nu == 0 || !D.pcache) { // transverseArea / transverseStrainSum return early (VX3_Voxel.cu:479, 498)
+            area[k] = size * size;
+            sum[k] = 0.0f;
+            continue;
+        }
+        float p[3];
+        voxel_poissons_strain(D, vs[k], steps_now, p);
+        const int a = (axis + 1) % 3, b = (axis + 2) % 3; // the two other axes, ascending: (y, z), (x, z), (x, y)
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        area[k] = (float)(size * size * (1 + (double)p[lo]) * (1 + (double)p[hi]));
+        sum[k] = p[lo] + p[hi];
+    }
+    return make_float2(0.5f * (area[0] + area[1]), 0.5f * (sum[0] + sum[1]));
+}
+
 // (true: the link was made — the caller re-evaluates the two voxels' contact forces)
 __device__ bool resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, unsigned long long key, int info) {
     const int hi = (int)(key >> 32), lo = (int)(key & 0xFFFFFFFFu);
@@ -1335,8 +1405,7 @@ __device__ bool resolve_accept(const Dev &D, const SimC &S, SimD &dy, int sim, u
     *D.lh(4, g) = make_double2(0.0, 0.5 * (base_size_axis(mn, D.tempe[vneg], axis) + base_size_axis(mp, D.tempe[vpos], axis)));
     for (int k = 0; k < 6; k++) *D.lf(k, g) = make_double2(0.0, 0.0); // the new link's end forces start at zero (VX3_Link::reset)
     D.lstrain[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float sn = (float)mn.nomSize, sp = (float)mp.nomSize; // transverseArea() with zero strain
-    D.larea[g] = make_float2(0.5f * (sn * sn + sp * sp), 0.0f);
+    D.larea[g] = resolve_link_transverse(D, vneg, vpos, axis, (int)dy.steps); // updateTransverseInfo(): frozen for the link's life
     dy.attach_events++;
     dy.topo_epoch++;
     if (D.uf) { // the two voxels' trees become one
