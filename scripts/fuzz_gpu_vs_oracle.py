@@ -3,7 +3,8 @@
 kinematic state to 1e-8 of the array's scale (a screening bar: a seed that fails goes through the full gate of
 tests/test_gpu_scenarios.py as a named scenario).
 
-    python scripts/fuzz_gpu_vs_oracle.py 8 48"""
+    python scripts/fuzz_gpu_vs_oracle.py 8 48
+    python scripts/fuzz_gpu_vs_oracle.py 0 40 b     # random_spec2: signals (state bit-exact), cilia, removal, programs, targets"""
 import os
 import sys
 
@@ -13,13 +14,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 import util  # noqa: E402
-from scenarios import random_spec  # noqa: E402
+from scenarios import random_spec, random_spec2  # noqa: E402
 
 INT_KEYS = ["vox_flags", "vox_links", "link_vneg", "link_vpos", "link_axis", "link_flags"]
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
+family = sys.argv[3] if len(sys.argv) > 3 else "a"  # a: random_spec, b: random_spec2 (optional physics)
 bad = []
 for seed in range(lo, hi):
-    spec = random_spec(seed)
+    spec = random_spec(seed) if family == "a" else random_spec2(seed)
     lib = util.load_engine()
     b, d = spec.build(lib)
     cap = d.contents.n_links + 2048
@@ -27,7 +29,7 @@ for seed in range(lo, hi):
     try:
         eng, orc = util.EngineBatch([d]), util.OracleSim(d)
         dt = -1.0 if seed % 2 else float(np.float32(0.9 * orc.recommended_dt()))
-        steps, chunk = (1600, 400) if seed % 2 else (600, 150)
+        steps, chunk = (1600, 400) if (seed % 2 or family != "a") else (600, 150)
         done, why = 0, None
         while done < steps and why is None:
             eng.step(chunk, dt) if dt > 0 else eng.step(chunk)
@@ -37,7 +39,7 @@ for seed in range(lo, hi):
             if se["link_vneg"].shape != so["link_vneg"].shape:
                 why = "link count %s vs %s" % (se["link_vneg"].shape, so["link_vneg"].shape)
                 break
-            for k in INT_KEYS:
+            for k in INT_KEYS + ["signal"]:
                 if not np.array_equal(se[k], so[k]):
                     why = "%s after %d steps" % (k, done)
                     break

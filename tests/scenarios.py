@@ -241,6 +241,53 @@ def random_spec(seed):
     return spec
 
 
+def random_spec2(seed):
+    """Second random family: the OPTIONAL physics in random combination — signals (pacemaker materials, random delays / decay /
+    inactive periods), cilia driven by signals, SecondaryExperiment (a material that is removed, CoM re-initialisation), force-field
+    and attach-condition programs, target materials with pair counting, a fixed material, collisions with a dropped body on every
+    third seed (so a touch can fire a signal)."""
+    rs = np.random.RandomState(5000 + seed)
+    U = lambda a, b: float(rs.uniform(a, b))
+    nx, ny, nz = int(rs.randint(3, 6)), int(rs.randint(2, 5)), int(rs.randint(2, 4))
+    signals, cilia = bool(rs.rand() < 0.7), bool(rs.rand() < 0.5)
+    secondary, collide = bool(rs.rand() < 0.4), seed % 3 == 2
+    spec = ModelSpec(0.01, "fuzzb%d" % seed)
+    npal = 3
+    for k in range(npal):
+        spec.add_material(name="Q%d" % k, elastic_mod=U(4e5, 1.5e6), density=U(900, 1400), cte=float(rs.choice([-1, 1])) * U(0.003, 0.012),
+                          u_static=U(0.6, 1.2), u_dynamic=U(0.3, 0.6), material_temp_phase=U(0, 1),
+                          is_pacemaker=int(signals and (k == 0 or rs.rand() < 0.3)), pacemaker_period=U(0.002, 0.006),
+                          signal_time_delay=float(rs.choice([0.0, U(0.0005, 0.002)])), signal_value_decay=U(0.6, 0.95),
+                          inactive_period=U(0.001, 0.003), cilia=(U(0.5, 2.0) if cilia else 0.0), cilia_on_after_s=float(rs.choice([0.0, U(0.0005, 0.002)])),
+                          is_target=int(k == 2 and rs.rand() < 0.6), is_measured=int(rs.rand() < 0.8),
+                          remove_after_s=(U(0.002, 0.004) if secondary and k == 1 else 0.0), fixed=int(k == 2 and rs.rand() < 0.15))
+    spec.set_env(bond_damping_z=U(0.5, 1.0), col_damping_z=U(0.5, 0.9), slow_damping_z=U(0.005, 0.03), temp_enabled=1, vary_temp_enabled=int(rs.rand() < 0.7),
+                 temp_amplitude=U(5, 20), temp_period=U(0.002, 0.01))
+    spec.set_options(enable_collision=int(collide), enable_signals=int(signals), enable_cilia=int(cilia), secondary_experiment=int(secondary),
+                     reinit_initial_position_after_s=(U(0.001, 0.003) if secondary else 0.0), enable_expansion=int(rs.rand() < 0.3),
+                     max_dist_in_voxel_lengths_to_count_as_pair=float(rs.choice([0.0, U(1.5, 3.0)])))
+    lift = int(rs.randint(0, 2))
+    extra = nz + 1 if collide else 0
+    st = np.zeros((nz + lift + extra, ny, nx), np.uint8)
+    st[lift:lift + nz] = rs.randint(1, npal + 1, size=(nz, ny, nx))
+    st[lift:lift + nz][rs.rand(nz, ny, nx) < U(0.0, 0.2)] = 0
+    st[lift, 0, 0] = 1
+    if collide:
+        spec.set_env(grav_acc=-U(150.0, 400.0))
+        st[lift + nz + 1:lift + 2 * nz + 1, : max(ny - 1, 1), : max(nx - 1, 1)] = rs.randint(1, npal + 1, size=(nz, max(ny - 1, 1), max(nx - 1, 1)))
+    kw = {}
+    if cilia:
+        kw["base_cilia"] = rs.uniform(-1e-4, 1e-4, st.shape + (3,))
+        kw["shift_cilia"] = rs.uniform(-1e-6, 1e-6, st.shape + (3,))
+    spec.set_structure(st, phase_offset=rs.rand(*st.shape), **kw)
+    if rs.rand() < 0.5:
+        spec.set_program(abi.PROG_FORCE_X, ("MUL", ("CONST", U(1e-4, 1e-3)), ("SIN", ("MUL", ("VAR", "t"), ("CONST", U(200.0, 2000.0))))))
+        spec.set_program(abi.PROG_FORCE_Z, ("MUL", ("CONST", -U(1e-3, 2e-2)), ("VAR", "z")))
+    if rs.rand() < 0.3:
+        spec.set_program(abi.PROG_FITNESS, ("ADD", ("VAR", "x"), ("ADD", ("VAR", "targetCloseness"), ("MUL", ("VAR", "numClosePairs"), ("VAR", "hit")))))
+    return spec
+
+
 SCENARIOS = {
     "act333": dict(spec=lambda: cube_spec((3, 3, 3), seed=11, actuated=True, name="act333"), steps=1000, chunk=250,
                    covers="per-voxel phase actuation, rest length from end temperatures"),
@@ -290,6 +337,9 @@ for _k in range(8):
                                     link_capacity=2048 if _k % 2 else None,
                                     covers="random model %d: %s" % (_k, "two sticky bodies, collisions + attach%s" % (" + detach" if _k % 4 == 3 else "")
                                                                     if _k % 2 else "random palette / actuation / externals"))
+for _k in (0, 2, 8, 11):
+    SCENARIOS["fuzzb%d" % _k] = dict(spec=(lambda k=_k: random_spec2(k)), steps=1600, chunk=400, dt="auto" if _k % 2 else "fixed", link_capacity=None,
+                                     covers="random model b%d: signals / cilia / removal / programs / targets in random combination" % _k)
 
 
 def scenario(name):
