@@ -70,9 +70,17 @@ def demo_spec():
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built (no reference tree on this box)")
-@pytest.mark.parametrize("name", sorted(CASES) + sorted(BUILD_ONLY))
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(BUILD_ONLY) + ["random_a%d" % k for k in range(16)] + ["random_b%d" % k for k in range(8)])
 def test_builder_equals_reference_import(name):
-    spec = make_spec(name)
+    """The host builder's model (what the engine consumes) against the reference's CVX_Sim::LoadVXAFile + Import of the same VXA
+    text, every array and every material constant bit for bit — on the hand-made cases and on seeded random models
+    (tests/scenarios.random_spec / random_spec2: random palettes incl. linear-with-failure and bilinear materials, nu, CTE, holes,
+    externals, two-body structures)."""
+    if name.startswith("random_"):
+        from scenarios import random_spec, random_spec2
+        spec = (random_spec if name[7] == "a" else random_spec2)(int(name[8:]))
+    else:
+        spec = make_spec(name)
     lib = util.load_engine()
     b, d = spec.build(lib)
     try:

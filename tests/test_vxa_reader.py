@@ -59,8 +59,13 @@ def full_spec():
     return spec
 
 
+def _random(family, seed):
+    from scenarios import random_spec, random_spec2
+    return lambda: (random_spec if family == "a" else random_spec2)(seed)
+
+
 @pytest.mark.parametrize("make", [lambda: cube_spec((3, 3, 3), seed=3, actuated=False), lambda: cube_spec((5, 4, 3), seed=5, actuated=True, holes=0.3, lift=1),
-                                  full_spec])
+                                  full_spec] + [_random("a", k) for k in range(12)] + [_random("b", k) for k in range(12)])
 def test_reader_equals_programmatic_builder(make):
     spec = make()
     lib = util.load_engine()
