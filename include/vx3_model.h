@@ -93,6 +93,10 @@ vx3_builder *vx3_vxa_load(const char *vxa_path, const char *vxd_path /* may be N
 
 /* Host recommendedTimeStep (src/VX3/VX3_VoxelyzeKernel.cu:184-217) on a flat model. */
 double vx3_model_recommended_dt(const vx3_model_desc *m);
+/* OptimalDt as the reference's first doTimeStep(dt < 0) evaluates it (VX3_VoxelyzeKernel.cu:240-247): recommendedTimeStep() AFTER that
+ * step's updateTemperature, i.e. with the rest lengths at the t = 0 temperatures — differs from vx3_model_recommended_dt only when a
+ * link material has nu != 0 (stiffness eHat * area / ((1 + strain) * restLength), VX3_Link.cu:268-277).  What a run with dt < 0 uses. */
+double vx3_model_first_step_dt(const vx3_model_desc *m);
 
 const char *vx3_model_last_error(void);
 

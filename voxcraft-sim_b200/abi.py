@@ -166,6 +166,8 @@ def declare_model_api(lib):
     lib.vx3_vxa_load.restype = vp
     lib.vx3_model_recommended_dt.argtypes = [P(ModelDesc)]
     lib.vx3_model_recommended_dt.restype = f64
+    lib.vx3_model_first_step_dt.argtypes = [P(ModelDesc)]
+    lib.vx3_model_first_step_dt.restype = f64
     lib.vx3_model_last_error.restype = C.c_char_p
     return lib
 
@@ -220,4 +222,4 @@ WORKER_SYMBOLS = ["vx3_worker_run_vxt", "vx3_worker_run_files", "vx3_write_repor
 MODEL_SYMBOLS = ["vx3_material_params_default", "vx3_env_params_default", "vx3_sim_options_default", "vx3_builder_create",
                  "vx3_builder_destroy", "vx3_builder_add_material", "vx3_builder_set_env", "vx3_builder_set_options",
                  "vx3_builder_set_name", "vx3_builder_set_program", "vx3_builder_set_structure", "vx3_builder_set_external",
-                 "vx3_builder_build", "vx3_vxa_parse", "vx3_vxa_load", "vx3_model_recommended_dt", "vx3_model_last_error"]
+                 "vx3_builder_build", "vx3_vxa_parse", "vx3_vxa_load", "vx3_model_recommended_dt", "vx3_model_first_step_dt", "vx3_model_last_error"]

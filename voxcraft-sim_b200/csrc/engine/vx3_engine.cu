@@ -26,42 +26,6 @@
 
 using namespace vx3;
 
-// recommendedTimeStep() (VX3_VoxelyzeKernel.cu:184-217) where it depends on the state.  For a link whose material has nu != 0 the
-// stiffness is eHat * transverse area / ((1 + strain) * rest length) (VX3_Link::axialStiffness, VX3_Link.cu:268-277), and the
-// reference evaluates OptimalDt ONCE, in its first doTimeStep(dt < 0), AFTER that step's updateTemperature (:240-247): the rest
-// lengths are those at the t = 0 temperatures, which per-voxel phase offsets make non-zero — not the model's.  Same mixed
-// precision as the reference; vx3_model_recommended_dt (host library) keeps answering for the model as imported.
-static double first_step_recommended_dt(const vx3_model_desc &m) {
-    const bool vary = m.opt.vary_temp_enabled && m.opt.temp_period > 0;
-    std::vector<float> te((size_t)m.n_voxels);
-    for (int i = 0; i < m.n_voxels; i++) {
-        const vx3_voxel_material &vm = m.voxel_mats[m.vox_mat[i]];
-        te[(size_t)i] = m.temp ? m.temp[i] : 0.0f;
-        if (!vary || vm.thermal_on_after_s > 0.0 || vm.fixed) continue; // gpu_update_temperature (:625-650) at currentTime = 0
-        double cur = m.opt.temp_amplitude * sin(2 * 3.1415926f * (0.0 / m.opt.temp_period + (m.phase_offset ? m.phase_offset[i] : 0.0)));
-        if (!m.opt.enable_expansion && cur > 0) cur = 0;
-        te[(size_t)i] = (float)cur;
-    }
-    double MaxFreq2 = 0.0f;
-    for (int i = 0; i < m.n_links; i++) {
-        const vx3_link_material &lm = m.link_mats[m.link_mat[i]];
-        const int vn = m.link_vneg[i], vp = m.link_vpos[i], axis = m.link_axis[i];
-        const vx3_voxel_material &mn = m.voxel_mats[m.vox_mat[vn]], &mp = m.voxel_mats[m.vox_mat[vp]];
-        float stiff;
-        if (lm.m.nu == 0.0f) stiff = lm.a1;
-        else {
-            const double rest = 0.5 * ((mn.nomSize * mn.extScale[axis]) * (1 + te[(size_t)vn] * mn.alphaCTE) + (mp.nomSize * mp.extScale[axis]) * (1 + te[(size_t)vp] * mp.alphaCTE));
-            const float strain = m.link_strain ? m.link_strain[i] : 0.0f;
-            stiff = (float)(lm.m.eHat * m.link_transverse_area[i] / ((strain + 1) * rest));
-        }
-        const double m1 = mn.mass, m2 = mp.mass;
-        const double f2 = stiff / (m1 < m2 ? m1 : m2);
-        if (f2 > MaxFreq2) MaxFreq2 = f2;
-    }
-    if (MaxFreq2 <= 0.0f) return vx3_model_recommended_dt(&m);
-    return 1.0f / (6.283185f * sqrt(MaxFreq2));
-}
-
 static inline float __int_as_float_host(int i) {
     float f;
     memcpy(&f, &i, 4);
@@ -784,7 +748,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.optimal_dt = vx3_model_recommended_dt(&m);
         S.dt_from_state = 0;
         for (int i = 0; i < m.n_links && !S.dt_from_state; i++) S.dt_from_state = m.link_mats[m.link_mat[i]].m.nu != 0.0f;
-        if (S.dt_from_state) S.optimal_dt = first_step_recommended_dt(m);
+        if (S.dt_from_state) S.optimal_dt = vx3_model_first_step_dt(&m);
         dy.hot_flags = ((S.vary_temp && S.temp_period > 0) ? SHF_THERMAL : 0) | (S.enable_expansion ? SHF_EXPANSION : 0) | (S.enable_cilia ? SHF_CILIA : 0) |
                        (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0) |
                        (S.enable_detach ? SHF_DETACH : 0) | (S.secondary_experiment ? SHF_SECONDARY : 0) | (S.prog_n[VX3_PROG_STOP] > 0 ? SHF_STOP_PROG : 0);

@@ -427,3 +427,42 @@ extern "C" double vx3_model_recommended_dt(const vx3_model_desc *m) {
     if (MaxFreq2 <= 0.0f) return 0.0f;
     return 1.0f / (6.283185f * sqrt(MaxFreq2));
 }
+
+// recommendedTimeStep() (VX3_VoxelyzeKernel.cu:184-217) where it depends on the state.  For a link whose material has nu != 0 the
+// stiffness is eHat * transverse area / ((1 + strain) * rest length) (VX3_Link::axialStiffness, VX3_Link.cu:268-277), and the
+// reference evaluates OptimalDt ONCE, in its first doTimeStep(dt < 0), AFTER that step's updateTemperature (:240-247): the rest
+// lengths are those at the t = 0 temperatures, which per-voxel phase offsets make non-zero — not the model's.  Same mixed
+// precision as the reference; vx3_model_recommended_dt keeps answering for the model as imported.  Equal to it when no link
+// material has nu != 0.
+extern "C" double vx3_model_first_step_dt(const vx3_model_desc *mp) {
+    if (!mp) return 0.0;
+    const vx3_model_desc &m = *mp;
+    const bool vary = m.opt.vary_temp_enabled && m.opt.temp_period > 0;
+    std::vector<float> te((size_t)m.n_voxels);
+    for (int i = 0; i < m.n_voxels; i++) {
+        const vx3_voxel_material &vm = m.voxel_mats[m.vox_mat[i]];
+        te[(size_t)i] = m.temp ? m.temp[i] : 0.0f;
+        if (!vary || vm.thermal_on_after_s > 0.0 || vm.fixed) continue; // gpu_update_temperature (:625-650) at currentTime = 0
+        double cur = m.opt.temp_amplitude * sin(2 * 3.1415926f * (0.0 / m.opt.temp_period + (m.phase_offset ? m.phase_offset[i] : 0.0)));
+        if (!m.opt.enable_expansion && cur > 0) cur = 0;
+        te[(size_t)i] = (float)cur;
+    }
+    double MaxFreq2 = 0.0f;
+    for (int i = 0; i < m.n_links; i++) {
+        const vx3_link_material &lm = m.link_mats[m.link_mat[i]];
+        const int vn = m.link_vneg[i], vp = m.link_vpos[i], axis = m.link_axis[i];
+        const vx3_voxel_material &mn = m.voxel_mats[m.vox_mat[vn]], &mp = m.voxel_mats[m.vox_mat[vp]];
+        float stiff;
+        if (lm.m.nu == 0.0f) stiff = lm.a1;
+        else {
+            const double rest = 0.5 * ((mn.nomSize * mn.extScale[axis]) * (1 + te[(size_t)vn] * mn.alphaCTE) + (mp.nomSize * mp.extScale[axis]) * (1 + te[(size_t)vp] * mp.alphaCTE));
+            const float strain = m.link_strain ? m.link_strain[i] : 0.0f;
+            stiff = (float)(lm.m.eHat * m.link_transverse_area[i] / ((strain + 1) * rest));
+        }
+        const double m1 = mn.mass, m2 = mp.mass;
+        const double f2 = stiff / (m1 < m2 ? m1 : m2);
+        if (f2 > MaxFreq2) MaxFreq2 = f2;
+    }
+    if (MaxFreq2 <= 0.0f) return vx3_model_recommended_dt(&m);
+    return 1.0f / (6.283185f * sqrt(MaxFreq2));
+}
