@@ -1552,7 +1552,8 @@ static void launch_step(vx3_batch *b, bool check_stop, bool last) {
     if (b->any_signals) LAUNCH(KC_SIGNALS, k_signals, b->nsims, 256, D); // end of timeStep (VX3_Voxel.cu:270-275), before removeVoxels
     if (b->any_secondary) LAUNCH(KC_SECONDARY, k_secondary, cdiv(D.nvox, VX3_BLOCK), VX3_BLOCK, D);
     if (com) LAUNCH(KC_COM, k_com_partial, D.nchunks, VX3_BLOCK, D);
-    // (a slab batch is one simulation, and on a plain step its end-of-step bookkeeping rides in the send kernel)
+    // end-of-step bookkeeping: k_tail on a sampling step; otherwise inside the voxel pass (its last CTA: slab batches that send from
+    // the voxel pass, and any batch of <= 128 simulations), inside the stand-alone send kernel of a slab batch, or k_tail_light
     int tail_in_send = -1;
     const bool sent_by_voxel_pass = !fused && b->halo.on && b->halo.send_fused;
     if (com) LAUNCH(KC_TAIL, k_tail, b->nsims, 128, D, 1, check_stop ? 1 : 0);
