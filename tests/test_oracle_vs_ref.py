@@ -105,10 +105,19 @@ def test_builder_equals_reference_import(name):
         lib.vx3_builder_destroy(b)
 
 
+def passive_random_spec(seed):
+    """tests/scenarios.random_spec within what the CPU library can do: no per-voxel phase actuation, nu = 0."""
+    from scenarios import random_spec
+    spec = random_spec(seed)
+    spec.set_env(vary_temp_enabled=0, temp_amplitude=0.0, volume_effects_enabled=0)
+    spec.phase_offset = None
+    return spec
+
+
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built (no reference tree on this box)")
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(CASES) + ["random_a%d" % k for k in range(0, 24, 2)])
 def test_oracle_cpu_mode_bit_equals_reference_steps(name):
-    spec = make_spec(name)
+    spec = passive_random_spec(int(name[8:])) if name.startswith("random_a") else make_spec(name)
     ref = RefSim(spec)
     orc = OracleSim(ref.desc, cpu_lib_mode=1)
     dt = float(np.float32(0.9 * ref.recommended_dt()))
