@@ -303,6 +303,7 @@ struct vx3_batch {
     int link_tiles = 0, vox_tiles = 0, link_grid = 1, vox_grid = 1; // persistent tile loops of the streaming kernels
     Halo halo;            // slab decomposition of one body over several GPUs (vx3_batch_halo_*)
     bool any_ghost = false;
+    std::vector<double> model_dt; // per simulation: recommendedTimeStep() before the first step (VX3_SimulationManager.cu:56-58)
     bool any_sticky_poisson = false; // an attaching simulation has a sticky material with nu != 0: Dev::pcache
     bool pdl = false; // programmatic dependent launch between the step kernels (launch_pdl; VX3_PDL=1)
     bool tail_in_voxels = false; // plain steps of batches of <= 128 simulations: k_voxels' last CTA does k_tail_light's work (VX3_TAIL_FUSED=0: off)
@@ -748,6 +749,7 @@ extern "C" int vx3_batch_create(int device, const vx3_model_desc *models, int n,
         S.optimal_dt = vx3_model_recommended_dt(&m);
         S.dt_from_state = 0;
         for (int i = 0; i < m.n_links && !S.dt_from_state; i++) S.dt_from_state = m.link_mats[m.link_mat[i]].m.nu != 0.0f;
+        b->model_dt.push_back(S.optimal_dt); // recommendedTimeStep() of the model as imported: what CUDA_Simulation prints before its loop
         if (S.dt_from_state) S.optimal_dt = vx3_model_first_step_dt(&m);
         dy.hot_flags = ((S.vary_temp && S.temp_period > 0) ? SHF_THERMAL : 0) | (S.enable_expansion ? SHF_EXPANSION : 0) | (S.enable_cilia ? SHF_CILIA : 0) |
                        (S.has_ff ? SHF_FORCE_FIELD : 0) | (S.has_attach_cond ? SHF_ATTACH_COND : 0) | (S.enable_signals ? SHF_SIGNALS : 0) |
@@ -1816,7 +1818,9 @@ extern "C" int vx3_batch_run(vx3_batch *b, const vx3_run_opts *opts, vx3_history
             std::string pre;
             snprintf(line, sizeof(line), "\033[0;32m%d) Simulation %d runs: %s.\n\033[0m", b->device, s, b->names[s].c_str());
             pre += line;
-            const double rec = b->simc[s].optimal_dt; // recommendedTimeStep()
+            // recommendedTimeStep() called BEFORE the loop (:56-58): the model as imported — the OptimalDt the steps use is evaluated in
+            // the first doTimeStep and differs when a link material has nu != 0 (vx3_model_first_step_dt)
+            const double rec = (size_t)s < b->model_dt.size() ? b->model_dt[(size_t)s] : b->simc[s].optimal_dt;
             const int real_stepsize = (int)(o.record_step_size / (10000 * rec * o.dt_frac)) + 1;
             if (o.record_step_size) {
                 frame_every[s] = real_stepsize;
