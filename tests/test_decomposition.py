@@ -44,6 +44,13 @@ def check_partition(d, world):
         vl = np.ctypeslib.as_array(sd.vox_links, shape=(n_v * 6,)).reshape(n_v, 6)
         fl = np.ctypeslib.as_array(sd.vox_flags, shape=(n_v,))
         assert ((fl & abi.VOX_GHOST) != 0).tolist() == (~s.owned).tolist()
+        # owned voxels first, ghosts last (the engine's voxel pass runs over the owned prefix), each group in the body's own order;
+        # links with two owned ends first, links across a face last (the link pass meets its ghosts only in the last tiles)
+        n_own = int(s.owned.sum())
+        assert s.owned[:n_own].all() and not s.owned[n_own:].any()
+        assert (np.diff(s.voxels[:n_own]) > 0).all() and (np.diff(s.voxels[n_own:]) > 0).all()
+        face = ~(s.owned[ln] & s.owned[lp])
+        assert not face[: int((~face).sum())].any()
         assert (s.owned[ln] | s.owned[lp]).all(), "every link of a slab has an owned end"
         # the engine's slot rule (2*axis at the negative end, 2*axis+1 at the positive end) survives the renumbering
         assert (vl[ln, 2 * la] == np.arange(n_l)).all() and (vl[lp, 2 * la + 1] == np.arange(n_l)).all()
