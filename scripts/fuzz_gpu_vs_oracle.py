@@ -14,21 +14,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 import util  # noqa: E402
-from scenarios import random_spec, random_spec2  # noqa: E402
+from scenarios import random_spec, random_spec2, random_spec3  # noqa: E402
 
 INT_KEYS = ["vox_flags", "vox_links", "link_vneg", "link_vpos", "link_axis", "link_flags"]
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
-family = sys.argv[3] if len(sys.argv) > 3 else "a"  # a: random_spec, b: random_spec2 (optional physics)
+family = sys.argv[3] if len(sys.argv) > 3 else "a"  # a: random_spec, b: random_spec2 (optional physics), c: random_spec3 (everything at once)
 bad = []
 for seed in range(lo, hi):
-    spec = random_spec(seed) if family == "a" else random_spec2(seed)
+    spec = {"a": random_spec, "b": random_spec2, "c": random_spec3}[family](seed)
     lib = util.load_engine()
     b, d = spec.build(lib)
-    cap = d.contents.n_links + 2048
+    cap = d.contents.n_links + 4096
     d.contents.link_capacity = cap
     try:
         eng, orc = util.EngineBatch([d]), util.OracleSim(d)
-        dt = -1.0 if seed % 2 else float(np.float32(0.9 * orc.recommended_dt()))
+        dt = -1.0 if (seed % 2 or family == "c") else float(np.float32(0.9 * orc.recommended_dt()))
         steps, chunk = (1600, 400) if (seed % 2 or family != "a") else (600, 150)
         done, why = 0, None
         while done < steps and why is None:

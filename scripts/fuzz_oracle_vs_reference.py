@@ -15,20 +15,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 import util  # noqa: E402
-from scenarios import random_spec, random_spec2  # noqa: E402
+from scenarios import random_spec, random_spec2, random_spec3  # noqa: E402
 from test_oracle_vs_vx3ref import STATE_KEYS  # noqa: E402
 
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
-family = sys.argv[3] if len(sys.argv) > 3 else "a"  # a: random_spec, b: random_spec2 (optional physics)
+family = sys.argv[3] if len(sys.argv) > 3 else "a"  # a: random_spec, b: random_spec2 (optional physics), c: random_spec3 (everything at once)
 bad = []
 for seed in range(lo, hi):
-    spec = random_spec(seed) if family == "a" else random_spec2(seed)
+    spec = {"a": random_spec, "b": random_spec2, "c": random_spec3}[family](seed)
     lib = util.load_engine()
     b, d = spec.build(lib)
-    d.contents.link_capacity = d.contents.n_links + 2048
+    d.contents.link_capacity = d.contents.n_links + 4096
     try:
         ref, orc = util.Vx3RefSim(spec, d), util.OracleSim(d)
-        dt = -1.0 if seed % 2 else float(np.float32(0.9 * orc.recommended_dt()))
+        dt = -1.0 if (seed % 2 or family == "c") else float(np.float32(0.9 * orc.recommended_dt()))
         steps, chunk = (1600, 400) if (seed % 2 or family != "a") else (600, 150)
         done, ok = 0, True
         while done < steps and ok:

@@ -288,6 +288,23 @@ def random_spec2(seed):
     return spec
 
 
+def random_spec3(seed):
+    """Third random family: everything at once — random_spec2 (signals, cilia, removal, programs, targets) with strong gravity,
+    every material sticky and linear-with-failure, nu != 0 on some of them with volume effects on, collisions + attach, detach on
+    every second seed."""
+    spec = random_spec2(seed)
+    rs = np.random.RandomState(9000 + seed)
+    spec.name = "fuzzc%d" % seed
+    spec.set_env(volume_effects_enabled=1, grav_acc=-float(rs.uniform(150, 400)))
+    for m in spec.materials:
+        m["poissons_ratio"] = float(rs.choice([0.0, rs.uniform(0.15, 0.35)]))
+        m["sticky"] = 1
+        m["mat_model"] = 1
+        m["fail_stress"] = m["elastic_mod"] * float(rs.uniform(0.1, 0.3))
+    spec.set_options(enable_collision=1, enable_attach=1, enable_detach=int(seed % 2), safety_guard=int(rs.randint(20, 80)))
+    return spec
+
+
 SCENARIOS = {
     "act333": dict(spec=lambda: cube_spec((3, 3, 3), seed=11, actuated=True, name="act333"), steps=1000, chunk=250,
                    covers="per-voxel phase actuation, rest length from end temperatures"),
